@@ -1,0 +1,564 @@
+// C ABI of libhpsolver: handle life cycle, sweep / step orchestration (plain stream launches or a CUDA
+// graph with a device-side WHILE around the PCG iteration), statistics, optional NCCL axial slabs.
+// See include/hp_solver.h for the contract and the reference lines each entry point replaces.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "hp_internal.h"
+
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return -1; }
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(std::string(#call) + " -> " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                        std::to_string(__LINE__) + ")");                                           \
+    } while (0)
+
+// ---- minimal NCCL binding, resolved at run time so the library loads without NCCL ------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclFloat64 = 8, ncclSum = 0, ncclMax = 2 };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static bool load_nccl() {
+    if (g_nccl.lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* n : names) {
+        lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) return false;
+#define LD(sym) *(void**)(&g_nccl.sym) = dlsym(lib, "nccl" #sym)
+    LD(GetUniqueId); LD(CommInitRank); LD(CommDestroy); LD(AllReduce); LD(AllGather); LD(Send); LD(Recv);
+    LD(GroupStart); LD(GroupEnd); LD(GetErrorString);
+#undef LD
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.Send || !g_nccl.Recv) return false;
+    g_nccl.lib = lib;
+    return true;
+}
+#define NK(call)                                                                                        \
+    do {                                                                                                \
+        int r_ = (call);                                                                                \
+        if (r_ != 0)                                                                                    \
+            return fail(std::string(#call) + " -> " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error")); \
+    } while (0)
+
+struct GraphEntry {
+    double dt; int sweeps; int has_old; int update_old; hp_solve_opts opts;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    int static_nodes = 0;
+};
+
+struct hp_solver_s {
+    int device = 0, num_sms = 148;
+    cudaStream_t stream = nullptr;
+    hp_phys phys{};
+    hp_solve_opts opts{};
+    HpDev d{};
+    HpLaunchCfg cfg{};
+    std::vector<void*> allocs;
+    size_t field_elems = 0;
+    double* rhs_dbg = nullptr;
+    // host mirrors
+    HpState* h_state = nullptr;     // pinned
+    long long launches_host = 0;    // kernels launched by the host + static graph nodes per graph launch
+    long long stream_mode_iters = 0;
+    long long sweeps_host = 0;
+    std::vector<GraphEntry> graphs;
+    // slabs
+    int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    double* red_local = nullptr;    // [HP_NRED]
+    double* red_all = nullptr;      // [nranks*HP_NRED]
+};
+
+static int dev_alloc(hp_solver_s* h, void** p, size_t bytes) {
+    CK(cudaMalloc(p, bytes ? bytes : 8));
+    h->allocs.push_back(*p);
+    return 0;
+}
+template <typename T>
+static int upload(hp_solver_s* h, const T** dst, const std::vector<T>& v) {
+    void* p = nullptr;
+    if (dev_alloc(h, &p, v.size() * sizeof(T))) return -1;
+    CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = (const T*)p;
+    return 0;
+}
+
+static HpKArgs make_args(const hp_solver_s* h, double dt, int has_old) {
+    HpKArgs a{};
+    a.dt = dt; a.tol = h->opts.tol; a.has_old = has_old; a.max_iter = h->opts.max_iter;
+    a.criterion = h->opts.criterion; a.use_cond = 0; a.cond = 0; a.rhs_out = nullptr;
+    return a;
+}
+
+static int launch(hp_solver_s* h, const HpKernelLaunch& k, void** params) {
+    CK(cudaLaunchKernel(k.func, k.grid, k.block, params, k.smem, h->stream));
+    h->launches_host++;
+    return 0;
+}
+
+extern "C" {
+
+const char* hp_last_error(void) { return g_err.c_str(); }
+int hp_version(void) { return 100; }
+
+int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* stream) {
+    if (!out || !m || !phys) return fail("hp_create: null argument");
+    if (!m->r_v || !m->z_v || !m->cell_band || !m->rface_band || !m->zface_band || !m->zc_flags || !m->zv_flags ||
+        !m->axial_open || !m->q_line || !m->h_line || !m->Tamb_line || !m->eps_line)
+        return fail("hp_create: null array in hp_mesh_desc");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("hp_create: no CUDA device available -- libhpsolver has no CPU fallback");
+    hp_solver_s* h = new hp_solver_s();
+    h->stream = (cudaStream_t)stream;
+    h->phys = *phys;
+    CK(cudaGetDevice(&h->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    h->num_sms = prop.multiProcessorCount;
+    const char* err = nullptr;
+    if (!hpk::pick_config(m->nr, m->nz, h->num_sms, &h->cfg, &err)) { delete h; return fail(std::string("hp_create: ") + err); }
+    const int nr = m->nr, nz = m->nz;
+    for (int i = 0; i < nr; ++i)
+        if (!(m->r_v[i + 1] > m->r_v[i])) { delete h; return fail("hp_create: r_v must be strictly increasing"); }
+    for (int g = 0; g < nz + 2; ++g)
+        if (!(m->z_v[g + 1] > m->z_v[g])) { delete h; return fail("hp_create: z_v must be strictly increasing"); }
+
+    HpDev& d = h->d;
+    d.nr = nr; d.nz = nz;
+    std::vector<double> r_v(m->r_v, m->r_v + nr + 1), r_c(nr), dr(nr), ar(nr, 0.0), dcr(nr, 1.0);
+    for (int i = 0; i < nr; ++i) { r_c[i] = 0.5 * (r_v[i] + r_v[i + 1]); dr[i] = r_v[i + 1] - r_v[i]; }
+    for (int i = 0; i + 1 < nr; ++i) { dcr[i] = r_c[i + 1] - r_c[i]; ar[i] = (r_v[i + 1] - r_c[i]) / dcr[i]; }
+    std::vector<double> z_c(nz + 2), dz(nz + 2), az(nz + 2, 0.0), dcz(nz + 2, 1.0);
+    for (int g = 0; g < nz + 2; ++g) { z_c[g] = 0.5 * (m->z_v[g] + m->z_v[g + 1]); dz[g] = m->z_v[g + 1] - m->z_v[g]; }
+    for (int g = 0; g + 1 < nz + 2; ++g) { dcz[g] = z_c[g + 1] - z_c[g]; az[g] = (m->z_v[g + 1] - z_c[g]) / dcz[g]; }
+    std::vector<double> wc(nr, 1.0), wf(nr + 1, 1.0);
+    if (!m->cartesian) { wc = r_c; wf = r_v; }
+    d.A_out_r = wf[nr];
+    d.d_out = r_v[nr] - r_c[nr - 1];
+#define UP(field, vec) if (upload(h, &d.field, vec)) { hp_destroy(h); return -1; }
+    UP(r_v, r_v); UP(r_c, r_c); UP(dr, dr); UP(wc, wc); UP(wf, wf); UP(ar, ar); UP(dcr, dcr);
+    UP(z_c, z_c); UP(dz, dz); UP(az, az); UP(dcz, dcz);
+    UP(cell_band, std::vector<int8_t>(m->cell_band, m->cell_band + nr));
+    UP(rface_band, std::vector<int8_t>(m->rface_band, m->rface_band + nr));
+    UP(zface_band, std::vector<int8_t>(m->zface_band, m->zface_band + nr));
+    UP(zc_flags, std::vector<uint8_t>(m->zc_flags, m->zc_flags + nz + 2));
+    UP(zv_flags, std::vector<uint8_t>(m->zv_flags, m->zv_flags + nz + 2));
+    UP(axial_open, std::vector<uint8_t>(m->axial_open, m->axial_open + nz + 2));
+    UP(q_line, std::vector<double>(m->q_line, m->q_line + nz + 2));
+    UP(h_line, std::vector<double>(m->h_line, m->h_line + nz + 2));
+    UP(Tamb_line, std::vector<double>(m->Tamb_line, m->Tamb_line + nz + 2));
+    UP(eps_line, std::vector<double>(m->eps_line, m->eps_line + nz + 2));
+#undef UP
+    h->field_elems = (size_t)(nz + 2) * nr + 64;
+    double** fields[] = {&d.T, &d.Told, &d.cR, &d.cZ, &d.diag, &d.dinv, &d.r, &d.q, &d.z, &d.p0, &d.p1};
+    for (double** f : fields) {
+        if (dev_alloc(h, (void**)f, h->field_elems * sizeof(double))) { hp_destroy(h); return -1; }
+        CK(cudaMemsetAsync(*f, 0, h->field_elems * sizeof(double), h->stream));
+    }
+    void* p = nullptr;
+    if (dev_alloc(h, &p, sizeof(double) * (nz + 2))) { hp_destroy(h); return -1; }
+    d.k0_out = (const double*)p;
+    if (dev_alloc(h, (void**)&d.st, sizeof(HpState))) { hp_destroy(h); return -1; }
+    CK(cudaMemsetAsync(d.st, 0, sizeof(HpState), h->stream));
+    if (dev_alloc(h, (void**)&d.stats, sizeof(hp_sweep_stat) * HP_STATS_CAP)) { hp_destroy(h); return -1; }
+    CK(cudaMemsetAsync(d.stats, 0, sizeof(hp_sweep_stat) * HP_STATS_CAP, h->stream));
+    if (dev_alloc(h, (void**)&d.partials, sizeof(double) * HP_NRED * HP_MAX_PARTIALS)) { hp_destroy(h); return -1; }
+    CK(cudaMallocHost((void**)&h->h_state, sizeof(HpState)));
+
+    h->opts.precond = 1; h->opts.criterion = 0; h->opts.tol = 1e-9; h->opts.max_iter = 5000;
+    h->opts.loop_mode = 1; h->opts.poll_chunk = 8; h->opts.refactor_every = 1;
+
+    // initial field + snapshots (main.py:34,133,145,152)
+    CK(hpk::launch_fill_rows(d, d.T, h->stream));
+    CK(hpk::launch_fill_rows(d, d.Told, h->stream));
+    HpKArgs a = make_args(h, 1.0, 0);
+    {
+        HpKernelLaunch k = hpk::desc_snapshot_kout(h->cfg, d);
+        double* k0 = (double*)d.k0_out;
+        void* params[] = {&d, &h->phys, &a, &k0};
+        if (launch(h, k, params)) { hp_destroy(h); return -1; }
+        HpKernelLaunch kc = hpk::desc_coef(h->cfg, d);
+        void* params2[] = {&d, &h->phys, &a};
+        if (launch(h, kc, params2)) { hp_destroy(h); return -1; }
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return 0;
+}
+
+static void destroy_graphs(hp_solver_s* h) {
+    for (auto& g : h->graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (g.graph) cudaGraphDestroy(g.graph);
+    }
+    h->graphs.clear();
+}
+
+int hp_destroy(hp_handle h) {
+    if (!h) return 0;
+    cudaStreamSynchronize(h->stream);
+    destroy_graphs(h);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->h_state) cudaFreeHost(h->h_state);
+    delete h;
+    return 0;
+}
+
+int hp_set_stream(hp_handle h, void* stream) {
+    if (!h) return fail("null handle");
+    CK(cudaStreamSynchronize(h->stream));
+    h->stream = (cudaStream_t)stream;
+    return 0;
+}
+
+int hp_set_opts(hp_handle h, const hp_solve_opts* o) {
+    if (!h || !o) return fail("hp_set_opts: null argument");
+    if (o->precond < 0 || o->precond > 1) return fail("hp_set_opts: precond must be 0 (jacobi) or 1 (rline)");
+    if (o->criterion < 0 || o->criterion > 2) return fail("hp_set_opts: criterion must be 0, 1 or 2");
+    if (!(o->tol > 0.0)) return fail("hp_set_opts: tol must be > 0");
+    if (o->max_iter < 1) return fail("hp_set_opts: max_iter must be >= 1");
+    if (o->loop_mode < 0 || o->loop_mode > 1) return fail("hp_set_opts: loop_mode must be 0 or 1");
+    h->opts = *o;
+    if (h->opts.poll_chunk < 1) h->opts.poll_chunk = 8;
+    if (h->opts.refactor_every < 1) h->opts.refactor_every = 1;
+    return 0;
+}
+
+static size_t owned_bytes(hp_handle h) { return (size_t)h->d.nz * h->d.nr * sizeof(double); }
+
+int hp_set_T_dev(hp_handle h, const double* d_T) {
+    if (!h || !d_T) return fail("hp_set_T_dev: null argument");
+    CK(cudaMemcpyAsync(h->d.T + h->d.nr, d_T, owned_bytes(h), cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+int hp_get_T_dev(hp_handle h, double* d_T) {
+    if (!h || !d_T) return fail("hp_get_T_dev: null argument");
+    CK(cudaMemcpyAsync(d_T, h->d.T + h->d.nr, owned_bytes(h), cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+int hp_set_T_host(hp_handle h, const double* h_T) {
+    if (!h || !h_T) return fail("hp_set_T_host: null argument");
+    CK(cudaMemcpyAsync(h->d.T + h->d.nr, h_T, owned_bytes(h), cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+int hp_get_T_host(hp_handle h, double* h_T) {
+    if (!h || !h_T) return fail("hp_get_T_host: null argument");
+    CK(cudaMemcpyAsync(h_T, h->d.T + h->d.nr, owned_bytes(h), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+const double* hp_T_ptr(hp_handle h) { return h ? h->d.T + h->d.nr : nullptr; }
+
+int hp_update_old(hp_handle h) {
+    if (!h) return fail("null handle");
+    CK(cudaMemcpyAsync(h->d.Told, h->d.T, (size_t)(h->d.nz + 2) * h->d.nr * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+
+// ---- slab halo exchange / scalar all-gather (NCCL) ----------------------------------------------------
+static int exchange_rows(hp_solver_s* h, double* field) {
+    if (h->nranks == 1) return 0;
+    const int nr = h->d.nr, nz = h->d.nz;
+    NK(g_nccl.GroupStart());
+    if (h->rank > 0) {
+        NK(g_nccl.Send(field + (size_t)1 * nr, nr, ncclFloat64, h->rank - 1, h->comm, h->stream));
+        NK(g_nccl.Recv(field, nr, ncclFloat64, h->rank - 1, h->comm, h->stream));
+    }
+    if (h->rank < h->nranks - 1) {
+        NK(g_nccl.Send(field + (size_t)nz * nr, nr, ncclFloat64, h->rank + 1, h->comm, h->stream));
+        NK(g_nccl.Recv(field + (size_t)(nz + 1) * nr, nr, ncclFloat64, h->rank + 1, h->comm, h->stream));
+    }
+    NK(g_nccl.GroupEnd());
+    return 0;
+}
+
+// ---- one sweep with plain stream launches, host-polled PCG loop ------------------------------------------
+static int sweep_stream(hp_solver_s* h, double dt, int has_old, bool refactor) {
+    HpDev& d = h->d;
+    HpKArgs a = make_args(h, dt, has_old);
+    a.rhs_out = h->rhs_dbg;
+    void* params[] = {&d, &h->phys, &a};
+    if (h->phys.gamma == 1) {
+        if (launch(h, hpk::desc_coef(h->cfg, d), params)) return -1;
+    }
+    {
+        int write_dinv = (h->opts.precond == 0) ? 1 : 0;
+        void* p4[] = {&d, &h->phys, &a, &write_dinv};
+        if (launch(h, hpk::desc_diag(h->cfg, d), p4)) return -1;
+    }
+    if (h->opts.precond == 1 && refactor) {
+        if (launch(h, hpk::desc_factor(h->cfg, d), params)) return -1;
+    }
+    if (launch(h, hpk::desc_cg_init(h->cfg, d, h->opts.precond, h->opts.criterion), params)) return -1;
+    const HpKernelLaunch kA = hpk::desc_cg_A(h->cfg, d);
+    const HpKernelLaunch kB = hpk::desc_cg_B(h->cfg, d, h->opts.precond, h->opts.criterion);
+    int launched = 0;
+    while (true) {
+        CK(cudaMemcpyAsync(h->h_state, d.st, sizeof(HpState), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->h_state->done) break;
+        if (launched >= h->opts.max_iter + h->opts.poll_chunk) return fail("sweep_stream: PCG loop did not terminate");
+        for (int k = 0; k < h->opts.poll_chunk; ++k) {
+            if (launch(h, kA, params)) return -1;
+            if (launch(h, kB, params)) return -1;
+            launched++;
+        }
+    }
+    h->stream_mode_iters += h->h_state->iter;
+    h->sweeps_host++;
+    return 0;
+}
+
+// ---- CUDA graph: [updateOld] + sweeps x ( [coef] diag [factor] init WHILE{A,B} ) ---------------------------
+struct NodeChain {
+    cudaGraph_t g; cudaGraphNode_t last = nullptr; int count = 0;
+};
+static int chain_kernel(NodeChain& c, const HpKernelLaunch& k, void** params) {
+    cudaKernelNodeParams np{};
+    np.func = (void*)k.func; np.gridDim = k.grid; np.blockDim = k.block; np.sharedMemBytes = (unsigned)k.smem;
+    np.kernelParams = params; np.extra = nullptr;
+    cudaGraphNode_t n;
+    CK(cudaGraphAddKernelNode(&n, c.g, c.last ? &c.last : nullptr, c.last ? 1 : 0, &np));
+    c.last = n; c.count++;
+    return 0;
+}
+
+static bool same_opts(const hp_solve_opts& a, const hp_solve_opts& b) {
+    return a.precond == b.precond && a.criterion == b.criterion && a.tol == b.tol && a.max_iter == b.max_iter &&
+           a.loop_mode == b.loop_mode && a.refactor_every == b.refactor_every;
+}
+
+static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int update_old, GraphEntry** out) {
+    for (auto& g : h->graphs)
+        if (g.dt == dt && g.sweeps == sweeps && g.has_old == has_old && g.update_old == update_old && same_opts(g.opts, h->opts)) {
+            *out = &g;
+            return 0;
+        }
+    if (h->graphs.size() >= 16) { CK(cudaStreamSynchronize(h->stream)); destroy_graphs(h); }
+    GraphEntry e;
+    e.dt = dt; e.sweeps = sweeps; e.has_old = has_old; e.update_old = update_old; e.opts = h->opts;
+    CK(cudaGraphCreate(&e.graph, 0));
+    NodeChain c{e.graph};
+    HpDev& d = h->d;
+    if (update_old) {
+        cudaGraphNode_t n;
+        CK(cudaGraphAddMemcpyNode1D(&n, e.graph, nullptr, 0, d.Told, d.T, (size_t)(d.nz + 2) * d.nr * sizeof(double),
+                                    cudaMemcpyDeviceToDevice));
+        c.last = n;
+    }
+    for (int s = 0; s < sweeps; ++s) {
+        HpKArgs a = make_args(h, dt, has_old);
+        void* params[] = {&d, &h->phys, &a};
+        if (h->phys.gamma == 1 && chain_kernel(c, hpk::desc_coef(h->cfg, d), params)) return -1;
+        int write_dinv = (h->opts.precond == 0) ? 1 : 0;
+        void* p4[] = {&d, &h->phys, &a, &write_dinv};
+        if (chain_kernel(c, hpk::desc_diag(h->cfg, d), p4)) return -1;
+        if (h->opts.precond == 1 && (s % h->opts.refactor_every) == 0)
+            if (chain_kernel(c, hpk::desc_factor(h->cfg, d), params)) return -1;
+        cudaGraphConditionalHandle cond;
+        CK(cudaGraphConditionalHandleCreate(&cond, e.graph, 0, cudaGraphCondAssignDefault));
+        a.use_cond = 1; a.cond = (unsigned long long)cond;
+        if (chain_kernel(c, hpk::desc_cg_init(h->cfg, d, h->opts.precond, h->opts.criterion), params)) return -1;
+        cudaGraphNodeParams cp{};
+        cp.type = cudaGraphNodeTypeConditional;
+        cp.conditional.handle = cond;
+        cp.conditional.type = cudaGraphCondTypeWhile;
+        cp.conditional.size = 1;
+        cudaGraphNode_t wn;
+        CK(cudaGraphAddNode(&wn, e.graph, c.last ? &c.last : nullptr, c.last ? 1 : 0, &cp));
+        c.last = wn;
+        NodeChain body{cp.conditional.phGraph_out[0]};
+        if (chain_kernel(body, hpk::desc_cg_A(h->cfg, d), params)) return -1;
+        if (chain_kernel(body, hpk::desc_cg_B(h->cfg, d, h->opts.precond, h->opts.criterion), params)) return -1;
+    }
+    e.static_nodes = c.count;
+    CK(cudaGraphInstantiate(&e.exec, e.graph, 0));
+    h->graphs.push_back(e);
+    *out = &h->graphs.back();
+    return 0;
+}
+
+static int run_steps(hp_solver_s* h, double dt, int n_steps, int sweeps, int has_old, int update_old) {
+    if (!(dt > 0.0)) return fail("dt must be > 0");
+    if (sweeps < 1) return fail("sweeps must be >= 1");
+    if (h->opts.loop_mode == 1 && h->nranks == 1 && !h->rhs_dbg) {
+        GraphEntry* g = nullptr;
+        if (get_graph(h, dt, sweeps, has_old, update_old, &g)) return -1;
+        for (int s = 0; s < n_steps; ++s) {
+            CK(cudaGraphLaunch(g->exec, h->stream));
+            h->launches_host += g->static_nodes;
+            h->sweeps_host += sweeps;
+        }
+        return 0;
+    }
+    if (h->nranks > 1) return fail("slab mode: use hp_sweep_slab path (not built in this call)");
+    for (int s = 0; s < n_steps; ++s) {
+        if (update_old && hp_update_old(h)) return -1;
+        for (int k = 0; k < sweeps; ++k)
+            if (sweep_stream(h, dt, has_old, (k % h->opts.refactor_every) == 0)) return -1;
+    }
+    return 0;
+}
+
+int hp_sweep(hp_handle h, double dt, int has_old, double* host_residual) {
+    if (!h) return fail("null handle");
+    if (run_steps(h, dt, 1, 1, has_old, 0)) return -1;
+    if (host_residual) {
+        hp_sweep_stat st;
+        if (hp_get_stats(h, &st, 1) < 1) return fail("hp_sweep: no statistics available");
+        *host_residual = st.residual_l2;
+    }
+    return 0;
+}
+
+int hp_step(hp_handle h, double dt, int sweeps, int has_old) {
+    if (!h) return fail("null handle");
+    return run_steps(h, dt, 1, sweeps, has_old, has_old ? 1 : 0);
+}
+
+int hp_run(hp_handle h, double dt, int n_steps, int sweeps, int has_old) {
+    if (!h) return fail("null handle");
+    if (n_steps < 0) return fail("n_steps must be >= 0");
+    return run_steps(h, dt, n_steps, sweeps, has_old, has_old ? 1 : 0);
+}
+
+int hp_run_host(hp_handle h, const double* h_T_in, double* h_T_out, double dt, int n_steps, int sweeps, int has_old) {
+    if (!h || !h_T_in || !h_T_out) return fail("hp_run_host: null argument");
+    if (hp_set_T_host(h, h_T_in)) return -1;
+    if (hp_run(h, dt, n_steps, sweeps, has_old)) return -1;
+    return hp_get_T_host(h, h_T_out);
+}
+
+static int fetch_state(hp_solver_s* h) {
+    CK(cudaMemcpyAsync(h->h_state, h->d.st, sizeof(HpState), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int hp_get_stats(hp_handle h, hp_sweep_stat* out, int max_n) {
+    if (!h || !out || max_n < 1) { fail("hp_get_stats: bad argument"); return -1; }
+    if (fetch_state(h)) return -1;
+    long long total = h->h_state->sweep_count;
+    long long n = total < max_n ? total : max_n;
+    if (n > HP_STATS_CAP) n = HP_STATS_CAP;
+    for (long long k = 0; k < n; ++k) {
+        long long slot = (total - n + k) % HP_STATS_CAP;
+        if (cudaMemcpy(&out[k], h->d.stats + slot, sizeof(hp_sweep_stat), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            fail("hp_get_stats: copy failed");
+            return -1;
+        }
+    }
+    return (int)n;
+}
+
+int64_t hp_total_sweeps(hp_handle h) { return h ? h->sweeps_host : -1; }
+int64_t hp_total_iters(hp_handle h) {
+    if (!h || fetch_state(h)) return -1;
+    return h->h_state->total_iters;
+}
+int64_t hp_kernel_launches(hp_handle h) {
+    if (!h || fetch_state(h)) return -1;
+    long long graph_iters = h->h_state->total_iters - h->stream_mode_iters;
+    return h->launches_host + 2 * graph_iters;
+}
+
+int hp_assemble_debug(hp_handle h, double dt, int has_old, double* d_cR, double* d_cZ, double* d_diag, double* d_rhs) {
+    if (!h) return fail("null handle");
+    if (!(dt > 0.0)) return fail("dt must be > 0");
+    HpDev& d = h->d;
+    double* scratch = nullptr;
+    CK(cudaMalloc((void**)&scratch, h->field_elems * sizeof(double)));
+    HpKArgs a = make_args(h, dt, has_old);
+    a.rhs_out = scratch;
+    void* params[] = {&d, &h->phys, &a};
+    int rc = 0;
+    if (h->phys.gamma == 1) rc = launch(h, hpk::desc_coef(h->cfg, d), params);
+    if (!rc) {
+        int write_dinv = 0;
+        void* p4[] = {&d, &h->phys, &a, &write_dinv};
+        rc = launch(h, hpk::desc_diag(h->cfg, d), p4);
+    }
+    const long long n = (long long)d.nz * d.nr;
+    cudaError_t e = cudaSuccess;
+    if (!rc && d_cR) e = hpk::launch_copy_owned(d.cR, d_cR, d.nr, n, h->stream);
+    if (!rc && e == cudaSuccess && d_cZ) e = hpk::launch_copy_owned(d.cZ, d_cZ, d.nr, n, h->stream);
+    if (!rc && e == cudaSuccess && d_diag) e = hpk::launch_copy_owned(d.diag, d_diag, d.nr, n, h->stream);
+    if (!rc && e == cudaSuccess && d_rhs) e = hpk::launch_copy_owned(scratch, d_rhs, d.nr, n, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(scratch);
+    if (rc) return -1;
+    if (e != cudaSuccess) return fail(std::string("hp_assemble_debug: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+int hp_eval_property(hp_handle h, int prop_id, const double* d_T, double* d_out, int64_t n) {
+    if (!h || !d_T || !d_out) return fail("hp_eval_property: null argument");
+    CK(hpk::launch_eval_property(h->phys, prop_id, d_T, d_out, n, h->stream));
+    h->launches_host++;
+    return 0;
+}
+
+int hp_eval_property_raw(const hp_phys* phys, int prop_id, const double* d_T, double* d_out, int64_t n, void* stream) {
+    if (!phys || !d_T || !d_out) return fail("hp_eval_property_raw: null argument");
+    CK(hpk::launch_eval_property(*phys, prop_id, d_T, d_out, n, (cudaStream_t)stream));
+    return 0;
+}
+
+int hp_eval_cell_fields(hp_handle h, double* d_rho, double* d_cp, double* d_kavg) {
+    if (!h) return fail("null handle");
+    CK(hpk::launch_cell_fields(h->d, h->phys, d_rho, d_cp, d_kavg, h->stream));
+    h->launches_host++;
+    return 0;
+}
+
+int hp_comm_unique_id(void* id128) {
+    if (!id128) return fail("hp_comm_unique_id: null argument");
+    if (!load_nccl()) return fail("hp_comm_unique_id: libnccl.so.2 not found");
+    ncclUniqueId id;
+    NK(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return 0;
+}
+
+int hp_comm_init(hp_handle h, int rank, int nranks, const void* id128) {
+    if (!h || !id128) return fail("hp_comm_init: null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail("hp_comm_init: bad rank / nranks");
+    if (!load_nccl()) return fail("hp_comm_init: libnccl.so.2 not found");
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    NK(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+    h->rank = rank; h->nranks = nranks;
+    if (dev_alloc(h, (void**)&h->red_local, sizeof(double) * HP_NRED)) return -1;
+    if (dev_alloc(h, (void**)&h->red_all, sizeof(double) * HP_NRED * nranks)) return -1;
+    (void)exchange_rows;
+    return 0;
+}
+
+}  // extern "C"

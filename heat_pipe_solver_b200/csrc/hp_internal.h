@@ -1,0 +1,96 @@
+// Internal declarations shared by hp_kernels.cu (device code + launchers) and hp_api.cu (C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "hp_solver.h"
+
+#define HP_STATS_CAP 4096
+#define HP_MAX_PARTIALS 4096     // max CTAs of any reducing kernel
+#define HP_NRED 4                // reduced values per kernel
+
+// Device-resident scalar state of the running solve (one per handle).
+struct HpState {
+    double alpha, beta, rz, pq, crit, rr, res2, b2;
+    int32_t iter;        // PCG iterations of the current sweep
+    int32_t done;        // 1 -> remaining (A,B) launches of this sweep are no-ops
+    int32_t first;       // 1 -> next direction update uses beta = 0 (p := z)
+    int32_t parity;      // which p buffer holds the current search direction
+    int32_t flags;       // hp_sweep_stat.flags of the current sweep
+    int32_t _pad;
+    unsigned int ticket; // last-CTA election
+    unsigned int _pad2;
+    long long sweep_count;
+    long long total_iters;
+};
+
+// Geometry / region / boundary arrays (device, 1-D) + field arrays (device, ghost-inclusive rows).
+struct HpDev {
+    int nr, nz;
+    // radial 1-D, [nr] unless noted
+    const double *r_v;       // [nr+1]
+    const double *r_c, *dr;
+    const double *wc;        // [nr]   radial weight of cell volumes / axial face areas: r_c (cylindrical) or 1
+    const double *wf;        // [nr+1] radial weight of radial face areas: r_v (cylindrical) or 1
+    const double *ar;        // arithmetic-face weight of radial face i+1/2: (r_v[i+1]-r_c[i])/(r_c[i+1]-r_c[i])
+    const double *dcr;       // r_c[i+1]-r_c[i]
+    const int8_t *cell_band, *rface_band, *zface_band;
+    // axial 1-D, ghost-inclusive [nz+2]
+    const double *z_c, *dz;
+    const double *az;        // weight of the face between row g and g+1
+    const double *dcz;       // z_c[g+1]-z_c[g]
+    const uint8_t *zc_flags, *zv_flags, *axial_open;
+    const double *q_line, *h_line, *Tamb_line, *eps_line;
+    const double *k0_out;    // snapshot of the outer-surface k (main.py:145)
+    double A_out_r;          // wf[nr]
+    double d_out;            // r_v[nr]-r_c[nr-1]
+    // fields, (nz+2)*nr each, row g at g*nr
+    double *T, *Told, *cR, *cZ, *diag, *dinv, *r, *q, *z, *p0, *p1;
+    HpState* st;
+    hp_sweep_stat* stats;    // ring of HP_STATS_CAP
+    double* partials;        // [HP_NRED * HP_MAX_PARTIALS]
+};
+
+// Per-launch scalar arguments shared by all kernels: signature (HpDev, hp_phys, HpKArgs [, extra]).
+struct HpKArgs {
+    double dt;
+    double tol;
+    int32_t has_old;
+    int32_t max_iter;
+    int32_t criterion;
+    int32_t use_cond;
+    unsigned long long cond;   // cudaGraphConditionalHandle of the enclosing WHILE node (use_cond != 0)
+    double* rhs_out;           // optional (debug): full rhs, ghost-inclusive layout
+};
+
+struct HpLaunchCfg {
+    int tpl, ept, vec;       // team kernels: threads per line, elements per thread, vector loads ok
+    int cta_threads, teams_per_cta, grid_team;   // grid for the marching kernels
+    int grid_cell, cta_cell;                     // grid for thread-per-cell kernels
+    int grid_factor, cta_factor;
+};
+
+// launch descriptors (so that hp_api.cu can either launch on a stream or add CUDA-graph kernel nodes)
+struct HpKernelLaunch {
+    const void* func;
+    dim3 grid, block;
+    size_t smem;
+};
+
+namespace hpk {
+bool pick_config(int nr, int nz, int num_sms, HpLaunchCfg* cfg, const char** err);
+
+// Each returns the launch descriptor; kernel arguments are passed by the caller as void*[] pointing to
+// variables with exactly these types/order (documented next to each kernel in hp_kernels.cu).
+HpKernelLaunch desc_snapshot_kout(const HpLaunchCfg&, const HpDev&);
+HpKernelLaunch desc_coef(const HpLaunchCfg&, const HpDev&);
+HpKernelLaunch desc_diag(const HpLaunchCfg&, const HpDev&);
+HpKernelLaunch desc_factor(const HpLaunchCfg&, const HpDev&);
+HpKernelLaunch desc_cg_init(const HpLaunchCfg&, const HpDev&, int precond, int criterion);
+HpKernelLaunch desc_cg_A(const HpLaunchCfg&, const HpDev&);
+HpKernelLaunch desc_cg_B(const HpLaunchCfg&, const HpDev&, int precond, int criterion);
+
+cudaError_t launch_eval_property(const hp_phys& ph, int id, const double* T, double* out, long long n, cudaStream_t s);
+cudaError_t launch_cell_fields(const HpDev& d, const hp_phys& ph, double* rho, double* cp, double* kavg, cudaStream_t s);
+cudaError_t launch_copy_owned(const double* src_ghost, double* dst, int nr, long long n, cudaStream_t s);
+cudaError_t launch_fill_rows(const HpDev& d, double* field, cudaStream_t s);
+}  // namespace hpk

@@ -1,0 +1,778 @@
+// CUDA kernels (sm_100a, fp64) of the transient r-z conduction hot path.
+//
+//   k_snapshot_kout  outer-surface k at T_amb                      (main.py:145  `b = FaceVariable(value=k)`)
+//   k_coef           face conductivities -> couplings cR, cZ       (main.py:103-106,133; FiPy DiffusionTerm)
+//   k_diag           rho*cp, diagonal, boundary terms, r0 = b - L T, ||L T - b||^2   (main.py:108-117,123-150,202)
+//   k_factor_rline   LDL^T pivots of the radial-line tridiagonal blocks
+//   k_cg_B<INIT>     z = M^-1 r0, r.z                                (PCG start)
+//   k_cg_A           p = z + beta p ; q = L p ; p.q                  (PCG, fused direction update + stencil + dot)
+//   k_cg_B           x += alpha p ; r -= alpha q ; z = M^-1 r ; r.z  (PCG, fused updates + line solve + dots)
+//
+// Layout: every field has nz+2 rows of nr doubles (row 0 / nz+1 = ghost rows, zero-coupled at physical
+// ends, a neighbour's row under axial slabs).  r is the fast index, so flat neighbours are idx+-1 (radial;
+// the last coupling of every row is 0, which also terminates the row at idx-1 of the next one) and
+// idx+-nr (axial).  Reductions are deterministic: per-CTA partials + fixed-order final sum by the last
+// CTA (ticket), which also advances the PCG scalar recurrences on the device -- no host round trip.
+#include <cuda_runtime.h>
+#include <math.h>
+#include "hp_internal.h"
+#include "hp_props.cuh"
+
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld256(const double* p, double* v) {
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void st256(double* p, const double* v) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+
+template <int EPT, bool VEC>
+__device__ __forceinline__ void load_row(const double* __restrict__ row, int i0, int nr, double (&v)[EPT]) {
+    if constexpr (VEC) {
+        if (i0 < nr) {
+#pragma unroll
+            for (int k = 0; k < EPT; k += 4) ld256(row + i0 + k, &v[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) v[k] = 0.0;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) v[k] = (i0 + k < nr) ? row[i0 + k] : 0.0;
+    }
+}
+template <int EPT, bool VEC>
+__device__ __forceinline__ void store_row(double* __restrict__ row, int i0, int nr, const double (&v)[EPT]) {
+    if constexpr (VEC) {
+        if (i0 < nr) {
+#pragma unroll
+            for (int k = 0; k < EPT; k += 4) st256(row + i0 + k, &v[k]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < EPT; ++k)
+            if (i0 + k < nr) row[i0 + k] = v[k];
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-reduce NV values (bit k of max_mask: value k is max-reduced, else summed), publish the CTA partial,
+// elect the last CTA by ticket; in the last CTA reduce all partials in a fixed order.  Returns true for every
+// thread of the last CTA; tot[] is valid on thread 0 of it.  All threads of the CTA must call.
+template <int NV>
+__device__ bool cta_publish(double (&v)[NV], unsigned max_mask, double* __restrict__ partials, unsigned int* ticket,
+                            double (&tot)[NV]) {
+    __shared__ double s_red[NV][32];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double w = ((max_mask >> k) & 1u) ? warp_max(v[k]) : warp_sum(v[k]);
+        if (lane == 0) s_red[k][warp] = w;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const bool mx = (max_mask >> k) & 1u;
+            double w = (lane < nwarp) ? s_red[k][lane] : 0.0;   // all reduced quantities are >= 0 where max is used
+            w = mx ? warp_max(w) : warp_sum(w);
+            if (lane == 0) partials[k * HP_MAX_PARTIALS + blockIdx.x] = w;
+        }
+        if (lane == 0) {
+            __threadfence();
+            unsigned t = atomicAdd(ticket, 1u);
+            s_last = (t == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const bool mx = (max_mask >> k) & 1u;
+        double w = 0.0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+            double pv = __ldcg(&partials[k * HP_MAX_PARTIALS + b]);
+            w = mx ? fmax(w, pv) : (w + pv);
+        }
+        w = mx ? warp_max(w) : warp_sum(w);
+        __syncthreads();
+        if (lane == 0) s_red[k][warp] = w;
+        __syncthreads();
+        if (warp == 0) {
+            double u = (lane < nwarp) ? s_red[k][lane] : 0.0;
+            u = mx ? warp_max(u) : warp_sum(u);
+            tot[k] = u;
+        }
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+    return true;
+}
+
+__device__ __forceinline__ void set_cond(const HpKArgs& a, int keep_going) {
+    if (a.use_cond) cudaGraphSetConditional((cudaGraphConditionalHandle)a.cond, keep_going ? 1u : 0u);
+}
+
+__device__ __forceinline__ bool converged(const HpKArgs& a, double crit, double rr, double b2) {
+    if (a.criterion == 2) return rr <= a.tol * a.tol * b2;
+    return crit <= a.tol;
+}
+
+// ------------------------------------------------------------------------------------------------
+// face conductivity helpers
+// ------------------------------------------------------------------------------------------------
+// k on the radial face between (g,i) and (g,i+1)
+__device__ __forceinline__ double k_rface(const HpDev& d, const hp_phys& ph, int g, int i, double Tc, double Te) {
+    const unsigned zf = d.zc_flags[g];
+    if (ph.face_k == 0) {
+        double Tf = Tc + (Te - Tc) * d.ar[i];
+        return hp::k_region(ph, d.rface_band[i], zf, Tf);
+    }
+    double k1 = hp::k_region(ph, d.cell_band[i], zf, Tc);
+    double k2 = hp::k_region(ph, d.cell_band[i + 1], zf, Te);
+    double d1 = d.r_v[i + 1] - d.r_c[i], d2 = d.r_c[i + 1] - d.r_v[i + 1];
+    double kk = (d1 + d2) / (d1 / k1 + d2 / k2);
+    return isfinite(kk) ? kk : 0.0;
+}
+// k on the axial face between (g,i) and (g+1,i)
+__device__ __forceinline__ double k_zface(const HpDev& d, const hp_phys& ph, int g, int i, double Tc, double Tn) {
+    if (ph.face_k == 0) {
+        double Tf = Tc + (Tn - Tc) * d.az[g];
+        return hp::k_region(ph, d.zface_band[i], d.zv_flags[g], Tf);
+    }
+    double k1 = hp::k_region(ph, d.cell_band[i], d.zc_flags[g], Tc);
+    double k2 = hp::k_region(ph, d.cell_band[i], d.zc_flags[g + 1], Tn);
+    double zv = d.z_c[g] + 0.5 * d.dz[g];
+    double e1 = zv - d.z_c[g], e2 = d.z_c[g + 1] - zv;
+    double kk = (e1 + e2) / (e1 / k1 + e2 / k2);
+    return isfinite(kk) ? kk : 0.0;
+}
+// k on the outer surface of row g (exterior face: T_f = T_P)
+__device__ __forceinline__ double k_outface(const HpDev& d, const hp_phys& ph, int g, double Tc) {
+    const int i = d.nr - 1;
+    if (ph.face_k == 0) return hp::k_region(ph, d.rface_band[i], d.zc_flags[g], Tc);
+    return hp::k_region(ph, d.cell_band[i], d.zc_flags[g], Tc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_snapshot_kout : k0_out[g] = k(outer face, T_amb[g])                       grid: rows
+// ------------------------------------------------------------------------------------------------
+__global__ void k_snapshot_kout(HpDev d, hp_phys ph, HpKArgs a, double* k0_out) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < d.nz + 2) k0_out[g] = k_outface(d, ph, g, d.Tamb_line[g]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_coef : cR[g,i] (owned rows), cZ[g,i] (rows 0..nz) from the field T           thread per cell
+//   cR = Gamma_r * (wf[i+1] * dz[g]) / (r_c[i+1]-r_c[i])       FiPy: coeff * faceArea / cellDistance
+//   cZ = Gamma_z * (wc[i] * dr[i])   / (z_c[g+1]-z_c[g])       (interior faces only)
+//   wf = r_v, wc = r_c on CylindricalGrid2D (areas / volumes per radian); 1 on a Cartesian Grid2D
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_coef(HpDev d, hp_phys ph, HpKArgs a) {
+    const long long n = (long long)(d.nz + 1) * d.nr;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(idx / d.nr), i = (int)(idx - (long long)g * d.nr);
+        const double Tc = d.T[idx];
+        double cz = 0.0;
+        if (d.axial_open[g]) {
+            const double Tn = d.T[idx + d.nr];
+            cz = k_zface(d, ph, g, i, Tc, Tn) * ((d.wc[i] * d.dr[i]) / d.dcz[g]);
+        }
+        d.cZ[idx] = cz;
+        if (g >= 1) {
+            double cr = 0.0;
+            if (i < d.nr - 1) {
+                const double Te = d.T[idx + 1];
+                cr = k_rface(d, ph, g, i, Tc, Te) * ((d.wf[i + 1] * d.dz[g]) / d.dcr[i]);
+            }
+            d.cR[idx] = cr;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_diag : per owned cell                                                       thread per cell
+//   cap  = cp*rho*V/dt                         TransientTerm(coeff=cp*rho)        main.py:108-117,148
+//   diag = cap + cE + cW + cN + cS (+ Robin)   DiffusionTerm + ImplicitSourceTerm main.py:148-149
+//   rhs  = cap*T_old (+ Robin*g + evaporator)                                     main.py:146-150
+//   r    = rhs - L T          (PCG start residual; FiPy's `res` = ||L T - rhs||_2) main.py:202
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_diag(HpDev d, hp_phys ph, HpKArgs a, int write_dinv_jacobi) {
+    const long long n = (long long)d.nz * d.nr;
+    double acc[2] = {0.0, 0.0};
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(c / d.nr), i = (int)(c - (long long)j * d.nr), g = j + 1;
+        const long long idx = c + d.nr;
+        const double Tc = d.T[idx];
+        const double Told = a.has_old ? d.Told[idx] : Tc;
+        double rho, cp;
+        hp::rho_cp_region(ph, d.cell_band[i], d.zc_flags[g], Tc, rho, cp);
+        const double vol = d.wc[i] * d.dr[i] * d.dz[g];
+        const double cap = cp * rho * vol / a.dt;
+        const double cE = d.cR[idx], cW = d.cR[idx - 1], cN = d.cZ[idx], cS = d.cZ[idx - d.nr];
+        double dg = cap;
+        dg += cE; dg += cW; dg += cN; dg += cS;
+        double rhs = cap * Told;
+        if (i == d.nr - 1) {
+            const unsigned zf = d.zc_flags[g];
+            const double kout = k_outface(d, ph, g, Tc);
+            const double k0 = (ph.gamma == 0) ? d.k0_out[g] : kout;
+            const double A_out = d.A_out_r * d.dz[g];
+            const double h = d.h_line[g], Ta = d.Tamb_line[g];
+            if (zf & HP_ZF_BC_COND) {
+                const double robin = kout * A_out / (h * d.d_out + k0);
+                dg += robin * h;
+                double gs = h * Ta;
+                if (ph.radiation) gs += ph.sigma * d.eps_line[g] * (Ta * Ta * Ta * Ta - Tc * Tc * Tc * Tc);
+                rhs += robin * gs;
+            }
+            if (zf & HP_ZF_BC_EVAP) {
+                const double q = d.q_line[g];
+                rhs += ((ph.source == 0) ? (q / kout) : q) * A_out;
+            }
+        }
+        const double LT = dg * Tc - cE * d.T[idx + 1] - cW * d.T[idx - 1] - cN * d.T[idx + d.nr] - cS * d.T[idx - d.nr];
+        const double r0 = rhs - LT;
+        d.diag[idx] = dg;
+        d.r[idx] = r0;
+        if (write_dinv_jacobi) d.dinv[idx] = 1.0 / dg;
+        if (a.rhs_out) a.rhs_out[idx] = rhs;
+        acc[0] += r0 * r0;
+        acc[1] += rhs * rhs;
+    }
+    double tot[2];
+    if (cta_publish<2>(acc, 0u, d.partials, &d.st->ticket, tot) && threadIdx.x == 0) {
+        HpState* s = d.st;
+        s->res2 = tot[0];
+        s->b2 = tot[1];
+        s->iter = 0; s->done = 0; s->first = 1; s->flags = 0;
+        hp_sweep_stat* stt = &d.stats[s->sweep_count % HP_STATS_CAP];
+        stt->residual_l2 = sqrt(tot[0]);
+        stt->rhs_l2 = sqrt(tot[1]);
+        stt->crit = 0.0; stt->iters = 0; stt->flags = 0;
+        s->sweep_count += 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_factor_rline : pivots of the radial-line tridiagonal  M_j = tridiag(-cR[i-1], diag[i], -cR[i])
+//   w_0 = diag_0 ; w_i = diag_i - cR_{i-1}^2 / w_{i-1} ; dinv_i = 1/w_i          thread per row
+// A nonlinear first-order recurrence, so rows are the parallel axis; loads of the next block are issued
+// before the dependent chain of the current one.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_factor_rline(HpDev d, hp_phys ph, HpKArgs a) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d.nz) return;
+    const long long base = (long long)(j + 1) * d.nr;
+    const double* __restrict__ dg = d.diag + base;
+    const double* __restrict__ cr = d.cR + base;
+    double* __restrict__ out = d.dinv + base;
+    double prev = 0.0;    // cR_{i-1}^2 * dinv_{i-1}
+    const int nr = d.nr;
+    constexpr int B = 8;
+    double db[B], cb[B];
+    int i = 0;
+    const int nfull = nr / B * B;
+    if (nfull > 0) {
+#pragma unroll
+        for (int k = 0; k < B; ++k) { db[k] = dg[k]; cb[k] = cr[k]; }
+    }
+    for (; i < nfull; i += B) {
+        double dn[B], cn[B];
+        const bool more = (i + B) < nfull;
+        if (more) {
+#pragma unroll
+            for (int k = 0; k < B; ++k) { dn[k] = dg[i + B + k]; cn[k] = cr[i + B + k]; }
+        }
+        double res[B];
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            const double w = db[k] - prev;
+            const double inv = 1.0 / w;
+            res[k] = inv;
+            prev = cb[k] * cb[k] * inv;
+        }
+#pragma unroll
+        for (int k = 0; k < B; ++k) out[i + k] = res[k];
+        if (more) {
+#pragma unroll
+            for (int k = 0; k < B; ++k) { db[k] = dn[k]; cb[k] = cn[k]; }
+        }
+    }
+    for (; i < nr; ++i) {
+        const double w = dg[i] - prev;
+        const double inv = 1.0 / w;
+        out[i] = inv;
+        const double c = cr[i];
+        prev = c * c * inv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// marching "row team" kernels.  A team of TPL threads owns whole rows (EPT consecutive cells per thread,
+// TPL*EPT >= nr) and walks a contiguous block of rows.
+// ------------------------------------------------------------------------------------------------
+template <int TPL>
+struct TeamGeom {
+    static constexpr int CTA = (TPL < 256) ? 256 : TPL;
+    static constexpr int LPC = CTA / TPL;
+    static constexpr int NW = TPL / 32;       // warps per team
+};
+
+template <int TPL>
+__device__ __forceinline__ void team_barrier(int team_in_cta) {
+    if constexpr (TPL > 32) {
+        asm volatile("bar.sync %0, %1;" ::"r"(team_in_cta + 1), "r"(TPL) : "memory");
+    } else {
+        __syncwarp();
+    }
+}
+
+// ---- k_cg_A -------------------------------------------------------------------------------------
+//   p_new = first ? z : z + beta*p_in          (rows ja .. jb+1 incl. halo rows: recomputed, never re-read)
+//   q     = L p_new                             5-point, couplings cR / cZ, diagonal diag
+//   pq    = sum p_new*q
+// last CTA: alpha = rz/pq, parity ^= 1, first = 0
+template <int TPL, int EPT, bool VEC>
+__global__ void __launch_bounds__(TeamGeom<TPL>::CTA) k_cg_A(HpDev d, hp_phys ph, HpKArgs a) {
+    using G = TeamGeom<TPL>;
+    const HpState s0 = *d.st;
+    if (s0.done) return;
+    const int nr = d.nr, nz = d.nz;
+    const int team_in_cta = threadIdx.x / TPL, tl = threadIdx.x % TPL, lane = threadIdx.x & 31;
+    const int i0 = tl * EPT;
+    const long long team = (long long)blockIdx.x * G::LPC + team_in_cta, nteams = (long long)gridDim.x * G::LPC;
+    const int ja = (int)(team * nz / nteams), jb = (int)((team + 1) * nz / nteams);
+    const double beta = s0.beta;
+    const bool first = s0.first != 0;
+    const double* __restrict__ pin = s0.parity ? d.p1 : d.p0;
+    double* __restrict__ pout = s0.parity ? d.p0 : d.p1;
+    const double* __restrict__ zf = d.z;
+
+    auto pnew_row = [&](int g, double (&out)[EPT]) {
+        double zz[EPT];
+        load_row<EPT, VEC>(zf + (long long)g * nr, i0, nr, zz);
+        if (first) {
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) out[e] = zz[e];
+        } else {
+            double pp[EPT];
+            load_row<EPT, VEC>(pin + (long long)g * nr, i0, nr, pp);
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) out[e] = fma(beta, pp[e], zz[e]);
+        }
+    };
+    auto pnew_at = [&](long long idx) -> double {
+        const double zz = zf[idx];
+        return first ? zz : fma(beta, pin[idx], zz);
+    };
+
+    double acc[1] = {0.0};
+    if (jb > ja) {
+        double pm[EPT], pc[EPT], pn[EPT], czm[EPT];
+        pnew_row(ja, pm);          // row g = ja  (the row below the first owned row of this team)
+        pnew_row(ja + 1, pc);
+        load_row<EPT, VEC>(d.cZ + (long long)ja * nr, i0, nr, czm);
+        if (ja == 0) store_row<EPT, VEC>(pout, i0, nr, pm);                      // lower ghost row
+        for (int g = ja + 1; g <= jb; ++g) {
+            const long long rb = (long long)g * nr;
+            pnew_row(g + 1, pn);
+            double cr[EPT], cz[EPT], dg[EPT];
+            load_row<EPT, VEC>(d.cR + rb, i0, nr, cr);
+            load_row<EPT, VEC>(d.cZ + rb, i0, nr, cz);
+            load_row<EPT, VEC>(d.diag + rb, i0, nr, dg);
+            // radial neighbours across thread boundaries
+            double pl = __shfl_up_sync(0xffffffffu, pc[EPT - 1], 1);
+            double crl = __shfl_up_sync(0xffffffffu, cr[EPT - 1], 1);
+            double pr = __shfl_down_sync(0xffffffffu, pc[0], 1);
+            if (lane == 0) {
+                if (tl == 0 || i0 >= nr) { pl = 0.0; crl = 0.0; }
+                else { pl = pnew_at(rb + i0 - 1); crl = d.cR[rb + i0 - 1]; }
+            }
+            if (lane == 31) pr = (i0 + EPT < nr) ? pnew_at(rb + i0 + EPT) : 0.0;
+            double qv[EPT];
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const double left = (e == 0) ? pl : pc[e - 1];
+                const double cleft = (e == 0) ? crl : cr[e - 1];
+                const double right = (e == EPT - 1) ? pr : pc[(e + 1) % EPT];
+                double t = dg[e] * pc[e];
+                t = fma(-cr[e], right, t);
+                t = fma(-cleft, left, t);
+                t = fma(-cz[e], pn[e], t);
+                t = fma(-czm[e], pm[e], t);
+                qv[e] = t;
+                acc[0] = fma(pc[e], t, acc[0]);
+            }
+            store_row<EPT, VEC>(d.q + rb, i0, nr, qv);
+            store_row<EPT, VEC>(pout + rb, i0, nr, pc);
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) { pm[e] = pc[e]; pc[e] = pn[e]; czm[e] = cz[e]; }
+        }
+        if (jb == nz) store_row<EPT, VEC>(pout + (long long)(nz + 1) * nr, i0, nr, pc);   // upper ghost row
+    }
+    double tot[1];
+    if (cta_publish<1>(acc, 0u, d.partials, &d.st->ticket, tot) && threadIdx.x == 0) {
+        HpState* s = d.st;
+        const double pq = tot[0];
+        s->pq = pq;
+        if (pq > 0.0 && isfinite(pq)) {
+            s->alpha = s->rz / pq;
+        } else {
+            s->alpha = 0.0;
+            s->flags |= 4;          // breakdown
+        }
+        s->parity ^= 1;
+        s->first = 0;
+    }
+}
+
+// ---- k_cg_B -------------------------------------------------------------------------------------
+//   INIT = false:  x += alpha p ; r -= alpha q          INIT = true: r as assembled by k_diag
+//   RLINE: z = M^-1 r by two affine first-order scans per row (forward, backward) over precomputed pivots:
+//        y_i = r_i + (cR_{i-1} dinv_{i-1}) y_{i-1} ;  z_i = dinv_i y_i + (cR_i dinv_i) z_{i+1}
+//   JACOBI: z = r * dinv
+//   rz = sum r z ; rr = sum r r ; crit = max|z| (criterion 0) or max|r/diag| (criterion 1)
+// last CTA: beta = rz_new/rz, iter++, convergence flag, sweep statistics, WHILE condition
+template <int TPL, int EPT, bool VEC, bool RLINE, bool INIT>
+__global__ void __launch_bounds__(TeamGeom<TPL>::CTA) k_cg_B(HpDev d, hp_phys ph, HpKArgs a) {
+    using G = TeamGeom<TPL>;
+    const HpState s0 = *d.st;
+    if (!INIT && s0.done) return;
+    __shared__ double s_fA[G::LPC][G::NW], s_fB[G::LPC][G::NW], s_bA[G::LPC][G::NW], s_bB[G::LPC][G::NW];
+    const int nr = d.nr, nz = d.nz;
+    const int team_in_cta = threadIdx.x / TPL, tl = threadIdx.x % TPL, lane = threadIdx.x & 31;
+    const int wt = tl >> 5;     // warp within team
+    const int i0 = tl * EPT;
+    const long long team = (long long)blockIdx.x * G::LPC + team_in_cta, nteams = (long long)gridDim.x * G::LPC;
+    const int ja = (int)(team * nz / nteams), jb = (int)((team + 1) * nz / nteams);
+    const double alpha = s0.alpha;
+    const double* __restrict__ pcur = s0.parity ? d.p1 : d.p0;
+    const bool need_diag = (a.criterion == 1);
+
+    double acc[3] = {0.0, 0.0, 0.0};   // rz, rr, crit(max)
+    for (int g = ja + 1; g <= jb; ++g) {
+        const long long rb = (long long)g * nr;
+        double rv[EPT];
+        load_row<EPT, VEC>(d.r + rb, i0, nr, rv);
+        if constexpr (!INIT) {
+            double xv[EPT], pv[EPT], qv[EPT];
+            load_row<EPT, VEC>(d.T + rb, i0, nr, xv);
+            load_row<EPT, VEC>(pcur + rb, i0, nr, pv);
+            load_row<EPT, VEC>(d.q + rb, i0, nr, qv);
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                xv[e] = fma(alpha, pv[e], xv[e]);
+                rv[e] = fma(-alpha, qv[e], rv[e]);
+            }
+            store_row<EPT, VEC>(d.T + rb, i0, nr, xv);
+            store_row<EPT, VEC>(d.r + rb, i0, nr, rv);
+        }
+        double dv[EPT], zv[EPT];
+        load_row<EPT, VEC>(d.dinv + rb, i0, nr, dv);
+        if constexpr (!RLINE) {
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) zv[e] = rv[e] * dv[e];
+        } else {
+            double cr[EPT];
+            load_row<EPT, VEC>(d.cR + rb, i0, nr, cr);
+            // ---------------- forward scan ----------------
+            double nb[EPT];     // cR_i * dinv_i : backward multiplier of cell i, forward multiplier of cell i+1
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) nb[e] = cr[e] * dv[e];
+            double m0 = __shfl_up_sync(0xffffffffu, nb[EPT - 1], 1);
+            if (lane == 0) m0 = (tl == 0 || i0 >= nr) ? 0.0 : d.cR[rb + i0 - 1] * d.dinv[rb + i0 - 1];
+            double Pe[EPT], ye[EPT];
+            {
+                double P = 1.0, y = 0.0;
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    const double m = (e == 0) ? m0 : nb[e - 1];
+                    y = fma(m, y, rv[e]);
+                    P *= m;
+                    Pe[e] = P; ye[e] = y;
+                }
+            }
+            double A = Pe[EPT - 1], B = ye[EPT - 1];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double Ap = __shfl_up_sync(0xffffffffu, A, o);
+                const double Bp = __shfl_up_sync(0xffffffffu, B, o);
+                if (lane >= o) { B = fma(A, Bp, B); A *= Ap; }
+            }
+            double Ax = __shfl_up_sync(0xffffffffu, A, 1), Bx = __shfl_up_sync(0xffffffffu, B, 1);
+            if (lane == 0) { Ax = 1.0; Bx = 0.0; }
+            double carry = 0.0;
+            if constexpr (G::NW > 1) {
+                if (lane == 31) { s_fA[team_in_cta][wt] = A; s_fB[team_in_cta][wt] = B; }
+                team_barrier<TPL>(team_in_cta);
+                for (int w = 0; w < wt; ++w) carry = fma(s_fA[team_in_cta][w], carry, s_fB[team_in_cta][w]);
+            }
+            const double ybefore = fma(Ax, carry, Bx);
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) ye[e] = fma(Pe[e], ybefore, ye[e]);
+            // ---------------- backward scan ----------------
+            {
+                double Q = 1.0, zz = 0.0;
+#pragma unroll
+                for (int e = EPT - 1; e >= 0; --e) {
+                    zz = fma(nb[e], zz, dv[e] * ye[e]);
+                    Q *= nb[e];
+                    Pe[e] = Q; zv[e] = zz;
+                }
+            }
+            A = Pe[0]; B = zv[0];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double Ap = __shfl_down_sync(0xffffffffu, A, o);
+                const double Bp = __shfl_down_sync(0xffffffffu, B, o);
+                if (lane + o < 32) { B = fma(A, Bp, B); A *= Ap; }
+            }
+            Ax = __shfl_down_sync(0xffffffffu, A, 1); Bx = __shfl_down_sync(0xffffffffu, B, 1);
+            if (lane == 31) { Ax = 1.0; Bx = 0.0; }
+            carry = 0.0;
+            if constexpr (G::NW > 1) {
+                if (lane == 0) { s_bA[team_in_cta][wt] = A; s_bB[team_in_cta][wt] = B; }
+                team_barrier<TPL>(team_in_cta);
+                for (int w = G::NW - 1; w > wt; --w) carry = fma(s_bA[team_in_cta][w], carry, s_bB[team_in_cta][w]);
+            }
+            const double zafter = fma(Ax, carry, Bx);
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) zv[e] = fma(Pe[e], zafter, zv[e]);
+        }
+        store_row<EPT, VEC>(d.z + rb, i0, nr, zv);
+        if (need_diag) {
+            double dg[EPT];
+            load_row<EPT, VEC>(d.diag + rb, i0, nr, dg);
+#pragma unroll
+            for (int e = 0; e < EPT; ++e)
+                if (i0 + e < nr) acc[2] = fmax(acc[2], fabs(rv[e] / dg[e]));
+        } else {
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) acc[2] = fmax(acc[2], fabs(zv[e]));
+        }
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            acc[0] = fma(rv[e], zv[e], acc[0]);
+            acc[1] = fma(rv[e], rv[e], acc[1]);
+        }
+    }
+    double tot[3];
+    if (cta_publish<3>(acc, 4u, d.partials, &d.st->ticket, tot) && threadIdx.x == 0) {
+        HpState* s = d.st;
+        const double rz_new = tot[0], rr = tot[1], crit = tot[2];
+        int flags = s->flags;
+        int done = 0;
+        if (INIT) {
+            s->rz = rz_new;
+            s->parity = 0;
+            s->first = 1;
+        } else {
+            s->beta = (s->rz != 0.0) ? rz_new / s->rz : 0.0;
+            s->rz = rz_new;
+            s->iter += 1;
+            s->total_iters += 1;
+        }
+        s->rr = rr; s->crit = crit;
+        const bool nan_bad = !(isfinite(rz_new) && isfinite(crit));
+        if (converged(a, crit, rr, s->b2)) { done = 1; flags |= 1; }
+        else if (nan_bad || (flags & 4)) { done = 1; flags |= 4; }
+        else if (s->iter >= a.max_iter) { done = 1; flags |= 2; }
+        s->done = done; s->flags = flags;
+        hp_sweep_stat* stt = &d.stats[(s->sweep_count - 1) % HP_STATS_CAP];
+        stt->crit = (a.criterion == 2) ? sqrt(rr) : crit;
+        stt->iters = s->iter;
+        stt->flags = flags;
+        set_cond(a, !done);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// auxiliary kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_eval_property(hp_phys ph, int id, const double* __restrict__ T, double* __restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = hp::eval_property(ph, id, T[i]);
+}
+
+// rho, cp per owned cell; kavg = mean of k over the cell's 4 faces (main.py:243: k.value[cellFaceIDs] mean)
+__global__ void k_cell_fields(HpDev d, hp_phys ph, double* __restrict__ rho_o, double* __restrict__ cp_o,
+                              double* __restrict__ kavg_o) {
+    const long long n = (long long)d.nz * d.nr;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(c / d.nr), i = (int)(c - (long long)j * d.nr), g = j + 1;
+        const long long idx = c + d.nr;
+        const double Tc = d.T[idx];
+        double rho, cp;
+        hp::rho_cp_region(ph, d.cell_band[i], d.zc_flags[g], Tc, rho, cp);
+        if (rho_o) rho_o[c] = rho;
+        if (cp_o) cp_o[c] = cp;
+        if (kavg_o) {
+            // bottom / top axial faces (exterior ones: T_f = T_P, masked law at the face position)
+            double kb = d.axial_open[g - 1] ? k_zface(d, ph, g - 1, i, d.T[idx - d.nr], Tc)
+                                            : hp::k_region(ph, d.zface_band[i], d.zv_flags[g - 1], Tc);
+            double kt = d.axial_open[g] ? k_zface(d, ph, g, i, Tc, d.T[idx + d.nr])
+                                        : hp::k_region(ph, d.zface_band[i], d.zv_flags[g], Tc);
+            double kr = (i < d.nr - 1) ? k_rface(d, ph, g, i, Tc, d.T[idx + 1]) : k_outface(d, ph, g, Tc);
+            double kl = (i > 0) ? k_rface(d, ph, g, i - 1, d.T[idx - 1], Tc)
+                                : hp::k_region(ph, HP_BAND_VC, d.zc_flags[g], Tc);   // axis face r = 0 <= R_vc
+            if (ph.face_k != 0) {
+                // harmonic mode: exterior faces take the cell value
+                if (!d.axial_open[g - 1]) kb = hp::k_region(ph, d.cell_band[i], d.zc_flags[g], Tc);
+                if (!d.axial_open[g]) kt = hp::k_region(ph, d.cell_band[i], d.zc_flags[g], Tc);
+                if (i == 0) kl = hp::k_region(ph, d.cell_band[i], d.zc_flags[g], Tc);
+            }
+            kavg_o[c] = (kb + kr + kt + kl) / 4.0;
+        }
+    }
+}
+
+// rhs (owned rows, compact nz*nr) from a ghost-inclusive scratch array
+__global__ void k_copy_owned(const double* __restrict__ src_ghost, double* __restrict__ dst, int nr, long long n) {
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x)
+        dst[c] = src_ghost[c + nr];
+}
+
+// field[g,:] = Tamb_line[g] for all rows incl. ghosts  (main.py:34,152)
+__global__ void k_fill_rows(HpDev d, double* __restrict__ field) {
+    const long long n = (long long)(d.nz + 2) * d.nr;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x)
+        field[c] = d.Tamb_line[(int)(c / d.nr)];
+}
+
+// ---- instantiation table -----------------------------------------------------------------------
+template <int TPL, int EPT, bool VEC>
+const void* fn_A() { return (const void*)k_cg_A<TPL, EPT, VEC>; }
+template <int TPL, int EPT, bool VEC>
+const void* fn_B(int rline, int init) {
+    if (rline) return init ? (const void*)k_cg_B<TPL, EPT, VEC, true, true> : (const void*)k_cg_B<TPL, EPT, VEC, true, false>;
+    return init ? (const void*)k_cg_B<TPL, EPT, VEC, false, true> : (const void*)k_cg_B<TPL, EPT, VEC, false, false>;
+}
+
+#define HP_DISPATCH(cfg, EXPR_T)                                                          \
+    do {                                                                                  \
+        if (cfg.tpl == 32 && cfg.ept == 1) { EXPR_T(32, 1, false); }                      \
+        else if (cfg.tpl == 32 && cfg.ept == 4) { if (cfg.vec) { EXPR_T(32, 4, true); } else { EXPR_T(32, 4, false); } }       \
+        else if (cfg.tpl == 128 && cfg.ept == 4) { if (cfg.vec) { EXPR_T(128, 4, true); } else { EXPR_T(128, 4, false); } }    \
+        else if (cfg.tpl == 256 && cfg.ept == 4) { if (cfg.vec) { EXPR_T(256, 4, true); } else { EXPR_T(256, 4, false); } }    \
+        else if (cfg.tpl == 512 && cfg.ept == 8) { if (cfg.vec) { EXPR_T(512, 8, true); } else { EXPR_T(512, 8, false); } }    \
+        else if (cfg.tpl == 1024 && cfg.ept == 8) { if (cfg.vec) { EXPR_T(1024, 8, true); } else { EXPR_T(1024, 8, false); } } \
+    } while (0)
+
+}  // namespace
+
+// ================================================================================================
+// host side: configuration + launch descriptors
+// ================================================================================================
+namespace hpk {
+
+bool pick_config(int nr, int nz, int num_sms, HpLaunchCfg* cfg, const char** err) {
+    if (nr < 1 || nz < 1) { *err = "nr and nz must be >= 1"; return false; }
+    int tpl, ept;
+    if (nr <= 32) { tpl = 32; ept = 1; }
+    else if (nr <= 128) { tpl = 32; ept = 4; }
+    else if (nr <= 512) { tpl = 128; ept = 4; }
+    else if (nr <= 1024) { tpl = 256; ept = 4; }
+    else if (nr <= 4096) { tpl = 512; ept = 8; }
+    else if (nr <= 8192) { tpl = 1024; ept = 8; }
+    else { *err = "nr > 8192 radial cells per row is not supported"; return false; }
+    cfg->tpl = tpl; cfg->ept = ept;
+    cfg->vec = (ept >= 4) && (nr % ept == 0);
+    cfg->cta_threads = tpl < 256 ? 256 : tpl;
+    cfg->teams_per_cta = cfg->cta_threads / tpl;
+    // resident CTAs per SM (register bound ~ 64K regs): 256 thr -> 3, 512 -> 1 (128 regs), 1024 -> 1
+    int res = cfg->cta_threads == 256 ? 3 : 1;
+    long long max_teams = (long long)num_sms * res * cfg->teams_per_cta;
+    long long teams = nz < max_teams ? nz : max_teams;
+    // at least 2 rows per team when the problem is small (amortise halo rows)
+    if (teams > 1 && nz / teams < 2) teams = (nz + 1) / 2;
+    int grid = (int)((teams + cfg->teams_per_cta - 1) / cfg->teams_per_cta);
+    if (grid < 1) grid = 1;
+    if (grid > HP_MAX_PARTIALS) grid = HP_MAX_PARTIALS;
+    cfg->grid_team = grid;
+    cfg->cta_cell = 256;
+    long long ncell = (long long)(nz + 1) * nr;
+    long long gc = (ncell + 255) / 256;
+    long long cap = (long long)num_sms * 8;
+    cfg->grid_cell = (int)(gc < cap ? gc : cap);
+    if (cfg->grid_cell > HP_MAX_PARTIALS) cfg->grid_cell = HP_MAX_PARTIALS;
+    cfg->cta_factor = 32;
+    cfg->grid_factor = (nz + 31) / 32;
+    return true;
+}
+
+HpKernelLaunch desc_snapshot_kout(const HpLaunchCfg& c, const HpDev& d) {
+    return {(const void*)k_snapshot_kout, dim3((d.nz + 2 + 127) / 128), dim3(128), 0};
+}
+HpKernelLaunch desc_coef(const HpLaunchCfg& c, const HpDev& d) {
+    return {(const void*)k_coef, dim3(c.grid_cell), dim3(c.cta_cell), 0};
+}
+HpKernelLaunch desc_diag(const HpLaunchCfg& c, const HpDev& d) {
+    return {(const void*)k_diag, dim3(c.grid_cell), dim3(c.cta_cell), 0};
+}
+HpKernelLaunch desc_factor(const HpLaunchCfg& c, const HpDev& d) {
+    return {(const void*)k_factor_rline, dim3(c.grid_factor), dim3(c.cta_factor), 0};
+}
+HpKernelLaunch desc_cg_A(const HpLaunchCfg& c, const HpDev& d) {
+    const void* f = nullptr;
+#define HP_X(T, E, V) f = fn_A<T, E, V>()
+    HP_DISPATCH(c, HP_X);
+#undef HP_X
+    return {f, dim3(c.grid_team), dim3(c.cta_threads), 0};
+}
+static HpKernelLaunch desc_B(const HpLaunchCfg& c, int precond, int init) {
+    const void* f = nullptr;
+#define HP_X(T, E, V) f = fn_B<T, E, V>(precond, init)
+    HP_DISPATCH(c, HP_X);
+#undef HP_X
+    return {f, dim3(c.grid_team), dim3(c.cta_threads), 0};
+}
+HpKernelLaunch desc_cg_init(const HpLaunchCfg& c, const HpDev& d, int precond, int criterion) { return desc_B(c, precond, 1); }
+HpKernelLaunch desc_cg_B(const HpLaunchCfg& c, const HpDev& d, int precond, int criterion) { return desc_B(c, precond, 0); }
+
+cudaError_t launch_eval_property(const hp_phys& ph, int id, const double* T, double* out, long long n, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    long long g = (n + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    k_eval_property<<<(int)g, 256, 0, s>>>(ph, id, T, out, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_cell_fields(const HpDev& d, const hp_phys& ph, double* rho, double* cp, double* kavg, cudaStream_t s) {
+    long long n = (long long)d.nz * d.nr;
+    long long g = (n + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    k_cell_fields<<<(int)g, 256, 0, s>>>(d, ph, rho, cp, kavg);
+    return cudaGetLastError();
+}
+cudaError_t launch_copy_owned(const double* src_ghost, double* dst, int nr, long long n, cudaStream_t s) {
+    long long g = (n + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    k_copy_owned<<<(int)g, 256, 0, s>>>(src_ghost, dst, nr, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_fill_rows(const HpDev& d, double* field, cudaStream_t s) {
+    long long n = (long long)(d.nz + 2) * d.nr;
+    long long g = (n + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    k_fill_rows<<<(int)g, 256, 0, s>>>(d, field);
+    return cudaGetLastError();
+}
+
+}  // namespace hpk

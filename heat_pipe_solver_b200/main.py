@@ -1,0 +1,135 @@
+"""Time loop of the reference driver (`/root/reference/src/2d/main.py:14-339`) as a function.
+
+The reference is a module-level script that ends in blocking plot calls; here the same sequence --
+parameters, property tables, composite mesh, region masks, equation, implicit-Euler loop with
+optional ``T.updateOld()`` + sweeps, profile capture every ``measure_every`` seconds of loop time --
+is ``run(...)`` and returns the temperature field and the captured profiles.  ``python -m
+heat_pipe_solver_b200.main`` prints the reference's console lines (main.py:32,161,197,207,337-339)
+without plotting.
+
+All arithmetic of the loop body runs on the GPU (libhpsolver.so); steps between two capture times are
+enqueued back to back without host synchronisation.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import params as params_mod
+from .mesh import generate_composite_mesh
+from .solver import ConductionSolver
+from .regions import BAND_VC, BAND_WICK, BAND_WALL
+
+
+def measurement_schedule(t_end, dt, measure_times):
+    """Loop times, and for each captured profile (step index, loop time) -- the bookkeeping of main.py:200-259."""
+    times = np.arange(0, t_end, dt)                                        # main.py:200
+    captures = []
+    nxt = 0
+    last = None
+    for step, t in enumerate(times):
+        if nxt < len(measure_times) and t >= measure_times[nxt]:            # main.py:204
+            if last is None or last < t:                                    # main.py:206
+                captures.append((step, float(t)))
+                last = float(t)
+            nxt += 1
+            while nxt < len(measure_times) and measure_times[nxt] <= t:     # main.py:258-259
+                nxt += 1
+    return times, captures
+
+
+def run(config_file=None, *, t_end=101.0, dt=0.1, sweeps=1, has_old=False, h=5.0,
+        properties='temperature_dependent', gamma='snapshot', source='q_over_k', face_k='masked_at_Tface',
+        radiation=False, measure_every=5, measure_times=None, mesh_params=None, T0=None,
+        precond='rline', criterion='precond_inf', tol=1e-9, max_iter=5000, loop_mode='graph',
+        capture_properties=True, verbose=False, device=None):
+    """Transient conduction run.  Defaults = the reference's active code path (main.py:119-120,200-202:
+    t_end=101 s, dt=0.1 s, one sweep per step with hasOld=False, h=5 W/m2K, temperature-dependent laws).
+    The commented "sweep" variant (main.py:267-271) is ``sweeps=5, has_old=True``.
+
+    Returns a dict: ``T`` (nz, nr) final field, ``times`` / ``profiles`` (top-wall axial temperature profiles,
+    main.py:208-209), ``residuals`` (FiPy-style pre-solve residual at each capture), property profiles
+    (``rho_*``, ``cp_*``, ``k_*`` for top wall / wick mean / vapor core, main.py:212-254), ``n_steps``,
+    ``iterations`` (total PCG iterations), ``elapsed``.
+    """
+    cfg = params_mod.load_config(config_file)
+    parameters, dimensions, constants = dict(cfg['parameters']), dict(cfg['dimensions']), dict(cfg['constants'])
+    mparams = dict(cfg['mesh']) if mesh_params is None else dict(mesh_params)
+    mesh, _cell_types = generate_composite_mesh(mparams, dimensions)       # main.py:29
+    if verbose:
+        print(f"Number of cells: {mesh.numberOfCells}")                    # main.py:32
+    if measure_times is None:
+        measure_times = list(range(measure_every, int(t_end), measure_every))   # main.py:158-159
+    if verbose:
+        print(f"Measuring at: {measure_times} seconds")                    # main.py:161
+    times, captures = measurement_schedule(t_end, dt, measure_times)
+
+    solver = ConductionSolver(mesh, dimensions, parameters, constants, h=h, properties=properties, gamma=gamma,
+                              source=source, face_k=face_k, radiation=radiation, precond=precond,
+                              criterion=criterion, tol=tol, max_iter=max_iter, loop_mode=loop_mode, device=device)
+    try:
+        if T0 is not None:
+            solver.set_value(T0)
+        reg = solver.regions
+        top_is_wall = reg.cell_band[-1] == BAND_WALL                       # main.py:165-169
+        vc_cols = np.nonzero(reg.cell_band == BAND_VC)[0]
+        wick_cols = np.nonzero(reg.cell_band == BAND_WICK)[0]
+        out = dict(times=[], profiles=[], residuals=[],
+                   rho_top_wall=[], rho_wick=[], rho_vc=[], cp_top_wall=[], cp_wick=[], cp_vc=[],
+                   k_top_wall=[], k_wick=[], k_vc=[])
+
+        def capture(t):
+            T = solver.value_tensor()
+            st = solver.stats(1)[0]
+            if verbose:
+                print(f"Time {t:.2f}, Residual: {st['residual_l2']}")      # main.py:207
+            out['times'].append(t)
+            out['residuals'].append(st['residual_l2'])
+            out['profiles'].append(T[:, -1].cpu().numpy() if top_is_wall else np.empty(0))
+            if capture_properties:
+                f = solver.cell_fields()
+                for key, name in (('rho', 'rho'), ('cp', 'cp'), ('k', 'k')):
+                    a = f[key]
+                    out[f'{name}_top_wall'].append(a[:, -1].cpu().numpy() if top_is_wall else np.empty(0))
+                    out[f'{name}_vc'].append(a[:, vc_cols].reshape(-1).cpu().numpy())
+                    out[f'{name}_wick'].append(a[:, wick_cols].mean(dim=1).cpu().numpy() if wick_cols.size else np.empty(0))
+
+        if verbose:
+            print(f"Simulating for {t_end} seconds...")                    # main.py:197
+        start = time.time()
+        done = 0
+        for step, t in captures:
+            solver.run(dt, step + 1 - done, sweeps=sweeps, has_old=has_old)
+            done = step + 1
+            capture(t)
+        if done < len(times):
+            solver.run(dt, len(times) - done, sweeps=sweeps, has_old=has_old)
+        solver.synchronize()
+        elapsed = time.time() - start
+        if verbose:
+            print(f"Simulated time: {t_end} seconds")                      # main.py:337
+            print(f"Actual execution time: {elapsed:.2f} seconds")         # main.py:338
+            print("%d cells on processor %d of %d" % (mesh.numberOfCells, 0, 1))   # main.py:339
+        result = {k: (np.array(v) if k in ('times', 'residuals') else v) for k, v in out.items()}
+        result['profiles'] = np.array(out['profiles'])
+        result.update(T=solver.value.reshape(mesh.shape), n_steps=len(times), iterations=solver.total_iters,
+                      sweeps=solver.total_sweeps, elapsed=elapsed, mesh=mesh, kernel_launches=solver.kernel_launches)
+        return result
+    finally:
+        solver.close()
+
+
+if __name__ == '__main__':
+    import argparse
+    ap = argparse.ArgumentParser(description="heat-pipe transient conduction (B200)")
+    ap.add_argument('--config', default=None)
+    ap.add_argument('--t-end', type=float, default=101.0)
+    ap.add_argument('--dt', type=float, default=0.1)
+    ap.add_argument('--sweeps', type=int, default=1)
+    ap.add_argument('--has-old', action='store_true')
+    ap.add_argument('--simple', action='store_true')
+    a = ap.parse_args()
+    r = run(a.config, t_end=a.t_end, dt=a.dt, sweeps=a.sweeps, has_old=a.has_old,
+            properties='simple' if a.simple else 'temperature_dependent', verbose=True)
+    print(f"peak top-wall temperature: {r['profiles'][-1].max() if len(r['profiles']) else float('nan'):.3f} K")

@@ -1,0 +1,296 @@
+"""Host-side driver object of the conduction hot path.
+
+``ConductionSolver`` plays the role of the reference's ``(T, eq)`` pair
+(`/root/reference/src/2d/main.py:34,148-150`): ``sweep(dt)`` is ``eq.sweep(var=T, dt=dt)``
+(main.py:202), ``update_old()`` is ``T.updateOld()`` (main.py:269), ``value`` is ``T.value``.
+All arithmetic happens in libhpsolver.so (CUDA, sm_100a) through the C ABI of
+``include/hp_solver.h``; torch is only used for device buffers and the stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .regions import Regions
+
+PRECOND = {'jacobi': 0, 'rline': 1}
+CRITERION = {'precond_inf': 0, 'rowscaled_inf': 1, 'l2_rel_rhs': 2}
+LOOP_MODE = {'host': 0, 'graph': 1}
+PROPERTIES = {'temperature_dependent': 0, 'simple': 1}
+GAMMA = {'snapshot': 0, 'lazy': 1}
+SOURCE = {'q_over_k': 0, 'q': 1}
+FACE_K = {'masked_at_Tface': 0, 'harmonic': 1}
+
+# hp::PropId (csrc/hp_props.cuh)
+PROP_IDS = {n: i for i, n in enumerate([
+    'na_rho_s', 'na_rho_l', 'na_rho_v', 'na_h_vap', 'na_k_s', 'na_k_l', 'na_cp_s', 'na_cp_l', 'na_cp_v',
+    'na_cv_v', 'na_h_l', 'na_h_v', 'na_mu_v', 'na_psat', 'steel_rho_eff', 'steel_rho', 'steel_k', 'steel_cp',
+    'wick_k', 'wick_cp', 'wick_rho', 'vc_k_evap_cond', 'vc_k_adiabatic', 'na_k_i', 'na_cp_i', 'na_rho_i',
+    'na_dpdt'])}
+
+
+def _choice(table, key, what):
+    try:
+        return table[key]
+    except KeyError:
+        raise ValueError(f"{what} must be one of {sorted(table)}, got {key!r}")
+
+
+def make_phys(parameters, dimensions, constants, *, properties='temperature_dependent', gamma='snapshot',
+              source='q_over_k', face_k='masked_at_Tface', radiation=False,
+              simple_rho=7200.0, simple_cp=440.5, simple_k=55.0):
+    ph = _lib.HpPhys()
+    ph.R_vc = dimensions['R_vc']
+    ph.M_g = parameters['M_g_sodium']
+    ph.R_gas = constants['R']
+    ph.porosity = parameters['porosity_wick']
+    ph.T_melt = parameters['T_melting_sodium']
+    ph.dT_melt = parameters['delta_T_sodium']
+    ph.sigma = constants.get('sigma', 5.670374419e-8)
+    ph.simple_rho, ph.simple_cp, ph.simple_k = simple_rho, simple_cp, simple_k      # main.py:41-46
+    ph.properties = _choice(PROPERTIES, properties, 'properties')
+    ph.gamma = _choice(GAMMA, gamma, 'gamma')
+    ph.source = _choice(SOURCE, source, 'source')
+    ph.face_k = _choice(FACE_K, face_k, 'face_k')
+    ph.radiation = 1 if radiation else 0
+    return ph
+
+
+class SlabLayout:
+    """Ghost-inclusive 1-D arrays of the rows [j0, j1) of a global mesh (what hp_mesh_desc wants)."""
+
+    def __init__(self, mesh, regions, j0, j1, line_values, axial_break=None):
+        nzg = mesh.nz
+        if not (0 <= j0 < j1 <= nzg):
+            raise ValueError(f"bad slab rows [{j0},{j1}) of {nzg}")
+        self.j0, self.j1, self.nz, self.nr = j0, j1, j1 - j0, mesh.nr
+        zv = mesh.z_v
+        lo = zv[j0 - 1] if j0 > 0 else zv[j0] - (zv[j0 + 1] - zv[j0])
+        hi = zv[j1 + 1] if j1 < nzg else zv[j1] + (zv[j1] - zv[j1 - 1])
+        self.z_v = np.ascontiguousarray(np.concatenate(([lo], zv[j0:j1 + 1], [hi])), dtype=np.float64)
+        rows = np.clip(np.arange(j0 - 1, j1 + 1), 0, nzg - 1)              # ghost rows clamp at physical ends
+        self.zc_flags = np.ascontiguousarray(regions.zc_flags[rows], dtype=np.uint8)
+        # face between ghost-inclusive row g and g+1 is the global vertex j0+g
+        verts = np.arange(j0, j1 + 2)
+        self.zv_flags = np.ascontiguousarray(regions.zv_flags[np.clip(verts, 0, nzg)], dtype=np.uint8)
+        is_open = (verts > 0) & (verts < nzg)
+        if axial_break is not None:
+            ab = np.asarray(axial_break, dtype=bool)                       # [nzg-1]: break between row j and j+1
+            if ab.shape != (nzg - 1,):
+                raise ValueError("axial_break must have nz-1 entries")
+            inner = is_open.copy()
+            inner[is_open] &= ~ab[verts[is_open] - 1]
+            is_open = inner
+        self.axial_open = np.ascontiguousarray(is_open, dtype=np.uint8)
+        self.lines = {k: np.ascontiguousarray(np.asarray(v, dtype=np.float64)[rows]) for k, v in line_values.items()}
+
+
+def _as_line(value, nz, name):
+    arr = np.asarray(value, dtype=np.float64)
+    if arr.ndim == 0:
+        return np.full(nz, float(arr))
+    if arr.shape != (nz,):
+        raise ValueError(f"{name} must be a scalar or have one entry per axial row ({nz}), got shape {arr.shape}")
+    return arr.copy()
+
+
+class ConductionSolver:
+    def __init__(self, mesh, dimensions, parameters, constants, *, h=5.0, q=None, T_amb=None, emissivity=None,
+                 properties='temperature_dependent', gamma='snapshot', source='q_over_k',
+                 face_k='masked_at_Tface', radiation=False, axial_break=None, rows=None,
+                 precond='rline', criterion='precond_inf', tol=1e-9, max_iter=5000, loop_mode='graph',
+                 poll_chunk=8, refactor_every=1, device=None, simple=(7200.0, 440.5, 55.0)):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.HpError("ConductionSolver needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
+        self._torch = torch
+        self.lib = _lib.load()
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device) \
+            if not isinstance(device, torch.device) else device
+        self.mesh, self.dimensions, self.parameters, self.constants = mesh, dimensions, parameters, constants
+        self.regions = Regions(mesh, dimensions)
+        nzg = mesh.nz
+        j0, j1 = (0, nzg) if rows is None else rows
+        lines = dict(
+            q=_as_line(parameters['Q_input_flux'] if q is None else q, nzg, 'q'),               # main.py:130
+            h=_as_line(h, nzg, 'h'),                                                            # main.py:37
+            Tamb=_as_line(parameters['T_amb'] if T_amb is None else T_amb, nzg, 'T_amb'),       # main.py:36
+            eps=_as_line(parameters.get('emissivity', 0.0) if emissivity is None else emissivity, nzg, 'emissivity'))
+        self.layout = lay = SlabLayout(mesh, self.regions, j0, j1, lines, axial_break)
+        self.nr, self.nz = lay.nr, lay.nz
+        self.phys = make_phys(parameters, dimensions, constants, properties=properties, gamma=gamma, source=source,
+                              face_k=face_k, radiation=radiation, simple_rho=simple[0], simple_cp=simple[1],
+                              simple_k=simple[2])
+        r_v = np.ascontiguousarray(mesh.r_v, dtype=np.float64)
+        keep = [r_v, lay.z_v, np.ascontiguousarray(self.regions.cell_band, dtype=np.int8),
+                np.ascontiguousarray(self.regions.rface_band, dtype=np.int8),
+                np.ascontiguousarray(self.regions.zface_band, dtype=np.int8),
+                lay.zc_flags, lay.zv_flags, lay.axial_open, lay.lines['q'], lay.lines['h'], lay.lines['Tamb'], lay.lines['eps']]
+        md = _lib.HpMeshDesc()
+        md.nr, md.nz, md.cartesian = self.nr, self.nz, 0 if mesh.cylindrical else 1
+        md.r_v = keep[0].ctypes.data_as(_lib.c_double_p)
+        md.z_v = keep[1].ctypes.data_as(_lib.c_double_p)
+        md.cell_band = keep[2].ctypes.data_as(_lib.c_int8_p)
+        md.rface_band = keep[3].ctypes.data_as(_lib.c_int8_p)
+        md.zface_band = keep[4].ctypes.data_as(_lib.c_int8_p)
+        md.zc_flags = keep[5].ctypes.data_as(_lib.c_uint8_p)
+        md.zv_flags = keep[6].ctypes.data_as(_lib.c_uint8_p)
+        md.axial_open = keep[7].ctypes.data_as(_lib.c_uint8_p)
+        md.q_line = keep[8].ctypes.data_as(_lib.c_double_p)
+        md.h_line = keep[9].ctypes.data_as(_lib.c_double_p)
+        md.Tamb_line = keep[10].ctypes.data_as(_lib.c_double_p)
+        md.eps_line = keep[11].ctypes.data_as(_lib.c_double_p)
+        self._keep = keep
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            self._stream = torch.cuda.current_stream(self.device)
+            _lib.check(self.lib.hp_create(C.byref(self._h), C.byref(md), C.byref(self.phys),
+                                          C.c_void_p(self._stream.cuda_stream)), 'hp_create')
+        self.set_options(precond=precond, criterion=criterion, tol=tol, max_iter=max_iter, loop_mode=loop_mode,
+                         poll_chunk=poll_chunk, refactor_every=refactor_every)
+
+    # ------------------------------------------------------------------ options
+    def set_options(self, **kw):
+        cur = getattr(self, 'options', dict(precond='rline', criterion='precond_inf', tol=1e-9, max_iter=5000,
+                                            loop_mode='graph', poll_chunk=8, refactor_every=1))
+        cur = dict(cur)
+        for k, v in kw.items():
+            if k not in cur:
+                raise TypeError(f"unknown solver option {k!r}")
+            cur[k] = v
+        o = _lib.HpSolveOpts()
+        o.precond = _choice(PRECOND, cur['precond'], 'precond')
+        o.criterion = _choice(CRITERION, cur['criterion'], 'criterion')
+        o.tol, o.max_iter = float(cur['tol']), int(cur['max_iter'])
+        o.loop_mode = _choice(LOOP_MODE, cur['loop_mode'], 'loop_mode')
+        o.poll_chunk, o.refactor_every = int(cur['poll_chunk']), int(cur['refactor_every'])
+        _lib.check(self.lib.hp_set_opts(self._h, C.byref(o)), 'hp_set_opts')
+        self.options = cur
+
+    # ------------------------------------------------------------------ field access
+    @property
+    def n_cells(self):
+        return self.nr * self.nz
+
+    def set_value(self, T):
+        """`T.setValue(...)`: scalar, numpy array or torch tensor of nz*nr values (FiPy order)."""
+        torch = self._torch
+        if np.isscalar(T):
+            buf = torch.full((self.n_cells,), float(T), dtype=torch.float64, device=self.device)
+        elif isinstance(T, torch.Tensor):
+            buf = T.to(device=self.device, dtype=torch.float64).reshape(-1).contiguous()
+        else:
+            buf = torch.from_numpy(np.ascontiguousarray(T, dtype=np.float64).reshape(-1)).to(self.device)
+        if buf.numel() != self.n_cells:
+            raise ValueError(f"expected {self.n_cells} values, got {buf.numel()}")
+        _lib.check(self.lib.hp_set_T_dev(self._h, C.c_void_p(buf.data_ptr())), 'hp_set_T_dev')
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def value_tensor(self):
+        """Copy of the field as a torch.float64 CUDA tensor of shape (nz, nr)."""
+        out = self._torch.empty((self.nz, self.nr), dtype=self._torch.float64, device=self.device)
+        _lib.check(self.lib.hp_get_T_dev(self._h, C.c_void_p(out.data_ptr())), 'hp_get_T_dev')
+        return out
+
+    @property
+    def value(self):
+        """`T.value`: numpy array in FiPy cell order (main.py:208)."""
+        return self.value_tensor().cpu().numpy().ravel()
+
+    # ------------------------------------------------------------------ FiPy-like stepping
+    def update_old(self):
+        _lib.check(self.lib.hp_update_old(self._h), 'hp_update_old')
+
+    def sweep(self, dt, has_old=False, want_residual=True):
+        """`res = eq.sweep(var=T, dt=dt)`; returns FiPy's pre-solve L2 residual (None if not wanted: no sync)."""
+        if want_residual:
+            res = C.c_double()
+            _lib.check(self.lib.hp_sweep(self._h, float(dt), int(has_old), C.byref(res)), 'hp_sweep')
+            return res.value
+        _lib.check(self.lib.hp_sweep(self._h, float(dt), int(has_old), None), 'hp_sweep')
+        return None
+
+    def step(self, dt, sweeps=1, has_old=False):
+        _lib.check(self.lib.hp_step(self._h, float(dt), int(sweeps), int(has_old)), 'hp_step')
+
+    def run(self, dt, n_steps, sweeps=1, has_old=False):
+        _lib.check(self.lib.hp_run(self._h, float(dt), int(n_steps), int(sweeps), int(has_old)), 'hp_run')
+
+    def run_host(self, T_in_pinned, T_out_pinned, dt, n_steps, sweeps=1, has_old=False):
+        """End-to-end call with HOST buffers (pinned torch CPU tensors): H2D + steps + D2H + sync."""
+        for t in (T_in_pinned, T_out_pinned):
+            if t.device.type != 'cpu' or t.dtype != self._torch.float64 or t.numel() != self.n_cells or not t.is_contiguous():
+                raise ValueError("host buffers must be contiguous float64 CPU tensors of nz*nr elements")
+        _lib.check(self.lib.hp_run_host(self._h, C.c_void_p(T_in_pinned.data_ptr()), C.c_void_p(T_out_pinned.data_ptr()),
+                                        float(dt), int(n_steps), int(sweeps), int(has_old)), 'hp_run_host')
+
+    def synchronize(self):
+        self._stream.synchronize()
+
+    # ------------------------------------------------------------------ statistics / hooks
+    def stats(self, n=1):
+        arr = (_lib.HpSweepStat * n)()
+        got = self.lib.hp_get_stats(self._h, arr, n)
+        if got < 0:
+            _lib.check(got, 'hp_get_stats')
+        return [dict(residual_l2=a.residual_l2, rhs_l2=a.rhs_l2, crit=a.crit, iters=a.iters,
+                     converged=bool(a.flags & 1), hit_max_iter=bool(a.flags & 2), breakdown=bool(a.flags & 4))
+                for a in arr[:got]]
+
+    @property
+    def total_iters(self):
+        return int(self.lib.hp_total_iters(self._h))
+
+    @property
+    def total_sweeps(self):
+        return int(self.lib.hp_total_sweeps(self._h))
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.hp_kernel_launches(self._h))
+
+    def assemble_debug(self, dt, has_old=False):
+        """The assembled 5-point system at the current iterate, as (nz, nr) CUDA tensors."""
+        torch = self._torch
+        out = {k: torch.empty((self.nz, self.nr), dtype=torch.float64, device=self.device) for k in ('cR', 'cZ', 'diag', 'rhs')}
+        _lib.check(self.lib.hp_assemble_debug(self._h, float(dt), int(has_old), C.c_void_p(out['cR'].data_ptr()),
+                                              C.c_void_p(out['cZ'].data_ptr()), C.c_void_p(out['diag'].data_ptr()),
+                                              C.c_void_p(out['rhs'].data_ptr())), 'hp_assemble_debug')
+        return out
+
+    def cell_fields(self):
+        """rho, cp and face-averaged k per cell at the current iterate (main.py:212-254)."""
+        torch = self._torch
+        out = {k: torch.empty((self.nz, self.nr), dtype=torch.float64, device=self.device) for k in ('rho', 'cp', 'k')}
+        _lib.check(self.lib.hp_eval_cell_fields(self._h, C.c_void_p(out['rho'].data_ptr()), C.c_void_p(out['cp'].data_ptr()),
+                                                C.c_void_p(out['k'].data_ptr())), 'hp_eval_cell_fields')
+        return out
+
+    def eval_property(self, name, T):
+        """Elementwise material law on the device; T: torch CUDA float64 tensor."""
+        torch = self._torch
+        Tc = T.to(device=self.device, dtype=torch.float64).contiguous()
+        out = torch.empty_like(Tc)
+        _lib.check(self.lib.hp_eval_property(self._h, _choice(PROP_IDS, name, 'property'), C.c_void_p(Tc.data_ptr()),
+                                             C.c_void_p(out.data_ptr()), Tc.numel()), 'hp_eval_property')
+        return out
+
+    # ------------------------------------------------------------------ life cycle
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h:
+            self.lib.hp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

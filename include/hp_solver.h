@@ -1,0 +1,144 @@
+/* hp_solver.h -- C ABI of libhpsolver (B200 / sm_100a) : the transient r-z conduction hot path of
+ * kubaniak/heat-pipe-solver.
+ *
+ * The reference has no FFI: its hot path is the FiPy call `eq.sweep(var=T, dt=dt)` inside a module-level
+ * Python loop (reference src/2d/main.py:148-150, 200-202, 267-271).  This library is what a replacement
+ * of that call binds to (ctypes from Python; the binding a maintainer would add is in INTEGRATION.md).
+ * Each entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types.  `stream` arguments are `cudaStream_t` passed
+ *     as `void*` (0 = legacy default stream).
+ *   - one host thread per handle; one handle per GPU (the current CUDA device at hp_create time).
+ *   - all work is enqueued on the handle's stream; calls return without synchronising unless stated.
+ *   - return value 0 = success, negative = error (text via hp_last_error()).  Nothing throws; the
+ *     library never frees caller memory; the handle owns all scratch.
+ *   - fields are fp64, FiPy cell order: id = j*nr + i, radial index i fastest (CylindricalGrid2D with
+ *     dr->x, dz->y; reference src/2d/mesh.py:109, src/2d/main.py:30-31).
+ *   - "ghost-inclusive" per-row arrays have nz+2 entries: entry 0 / nz+1 describe the row below / above
+ *     the owned block (a neighbouring slab's row, or a dummy at a physical end).  Field pointers handed
+ *     to hp_set_T / hp_get_T cover the nz owned rows only.
+ */
+#ifndef HP_SOLVER_H
+#define HP_SOLVER_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hp_solver_s* hp_handle;
+
+/* physical constants + mode switches (reference config/faghri.json, main.py:37-46,103-150) */
+typedef struct hp_phys {
+    double R_vc, M_g, R_gas, porosity, T_melt, dT_melt, sigma;
+    double simple_rho, simple_cp, simple_k;      /* main.py:41-46 */
+    int32_t properties;   /* 0 temperature_dependent (main.py:103-117), 1 simple */
+    int32_t gamma;        /* 0 snapshot at create time (main.py:133,145), 1 lazy */
+    int32_t source;       /* 0 q/k (main.py:150), 1 q */
+    int32_t face_k;       /* 0 region law at arithmetic face T (main.py:103-106), 1 harmonic mean of cell k */
+    int32_t radiation;    /* 0 off, 1 on: g = h*T_amb + sigma*eps*(T_amb^4 - T_f^4) (verification_examples.py:81-91) */
+    int32_t _pad;
+} hp_phys;
+
+/* structured r-z grid + region codes.  Replaces the FiPy mesh object built by
+ * mesh.generate_composite_mesh (reference src/2d/mesh.py:42-149) and the position masks of
+ * main.py:64-72,86-90,123-124, which the host evaluates with the reference's float recipe. All HOST pointers. */
+typedef struct hp_mesh_desc {
+    int32_t nr;                 /* radial cells per row (fast index) */
+    int32_t nz;                 /* owned axial rows */
+    int32_t cartesian;          /* 0: CylindricalGrid2D (mesh.py:109), per-radian areas/volumes; 1: Grid2D (mesh.py:12-32) */
+    int32_t _pad;
+    const double* r_v;          /* [nr+1]   radial vertices */
+    const double* z_v;          /* [nz+3]   axial vertices, ghost-inclusive: row g spans z_v[g]..z_v[g+1] */
+    const int8_t* cell_band;    /* [nr]     0 vc, 1 wick, 2 wall, 3 none     (cells, main.py:64-70) */
+    const int8_t* rface_band;   /* [nr]     band of the radial face at r_v[i+1]; i=nr-1 is the outer surface (main.py:86-90) */
+    const int8_t* zface_band;   /* [nr]     band of axial faces (centre r_c[i], face inequalities) */
+    const uint8_t* zc_flags;    /* [nz+2]   HP_ZF_* bits at row centres */
+    const uint8_t* zv_flags;    /* [nz+2]   HP_ZF_* bits at the face between row g and g+1 */
+    const uint8_t* axial_open;  /* [nz+2]   1 if the face between row g and g+1 conducts (interior face) */
+    /* outer-surface boundary data per row (main.py:36-37,130; ensembles vary them per member) */
+    const double* q_line;       /* [nz+2]   evaporator heat flux  W/m^2 */
+    const double* h_line;       /* [nz+2]   condenser film coefficient W/m^2K */
+    const double* Tamb_line;    /* [nz+2]   ambient temperature K (also the snapshot temperature) */
+    const double* eps_line;     /* [nz+2]   emissivity (radiation mode) */
+} hp_mesh_desc;
+
+typedef struct hp_solve_opts {
+    int32_t precond;        /* 0 Jacobi, 1 radial-line tridiagonal */
+    int32_t criterion;      /* 0 max|M^-1 r| <= tol [K]; 1 max|r_i/a_ii| <= tol [K]; 2 ||r||_2 <= tol*||b||_2 */
+    double tol;
+    int32_t max_iter;
+    int32_t loop_mode;      /* 0 host-polled chunks of poll_chunk iterations; 1 CUDA graph, device-side WHILE */
+    int32_t poll_chunk;
+    int32_t refactor_every; /* re-factor the line preconditioner every k-th sweep (1 = every sweep) */
+} hp_solve_opts;
+
+typedef struct hp_sweep_stat {
+    double residual_l2;     /* FiPy's `res`: ||L(T) T - b(T)||_2 before the solve (main.py:202) */
+    double rhs_l2;          /* ||b||_2 */
+    double crit;            /* value of the stopping measure when the solve stopped */
+    int32_t iters;          /* PCG iterations */
+    int32_t flags;          /* bit0 converged, bit1 hit max_iter, bit2 breakdown (p.Ap <= 0 or NaN) */
+} hp_sweep_stat;
+
+const char* hp_last_error(void);
+int hp_version(void);
+
+/* life cycle.  Replaces mesh + CellVariable + equation construction, main.py:29-34,103-150.
+ * The initial field is Tamb_line broadcast over each row (main.py:34,152); Gamma / b snapshots are taken here. */
+int hp_create(hp_handle* out, const hp_mesh_desc* mesh, const hp_phys* phys, void* stream);
+int hp_destroy(hp_handle h);
+int hp_set_stream(hp_handle h, void* stream);
+int hp_set_opts(hp_handle h, const hp_solve_opts* opts);
+
+/* field access (`T.setValue`, `T.value`, main.py:152,208).  *_dev: device pointers, *_host: host pointers
+ * (pinned for true asynchrony).  nz*nr doubles. */
+int hp_set_T_dev(hp_handle h, const double* d_T);
+int hp_get_T_dev(hp_handle h, double* d_T);
+int hp_set_T_host(hp_handle h, const double* h_T);
+int hp_get_T_host(hp_handle h, double* h_T);        /* synchronises the stream */
+const double* hp_T_ptr(hp_handle h);                /* device pointer to owned row 0 of the live field */
+
+/* `T.updateOld()` (main.py:269) */
+int hp_update_old(hp_handle h);
+
+/* `res = eq.sweep(var=T, dt=dt)` (main.py:202,271).  has_old = 0 reproduces hasOld=False (main.py:34):
+ * the transient term uses the current iterate as old value.  If host_residual != NULL the stream is
+ * synchronised and the pre-solve residual returned (FiPy semantics); otherwise nothing is synchronised. */
+int hp_sweep(hp_handle h, double dt, int has_old, double* host_residual);
+
+/* one time step of the loop body: [updateOld] + `sweeps` sweeps (main.py:200-202 / 267-271), launched
+ * as one CUDA graph when loop_mode = 1 */
+int hp_step(hp_handle h, double dt, int sweeps, int has_old);
+/* n_steps steps back to back */
+int hp_run(hp_handle h, double dt, int n_steps, int sweeps, int has_old);
+/* end-to-end with HOST buffers: H2D(T_in) + n_steps steps + D2H(T_out) + stream sync */
+int hp_run_host(hp_handle h, const double* h_T_in, double* h_T_out, double dt, int n_steps, int sweeps, int has_old);
+
+/* statistics of the most recent sweeps (synchronises). Returns how many were written (<= max_n). */
+int hp_get_stats(hp_handle h, hp_sweep_stat* out, int max_n);
+int64_t hp_total_sweeps(hp_handle h);
+int64_t hp_total_iters(hp_handle h);        /* synchronises */
+int64_t hp_kernel_launches(hp_handle h);    /* kernels of this library launched so far (graph nodes counted per launch; WHILE bodies per executed iteration; synchronises) */
+
+/* parity hooks: assemble at the current iterate and copy out the 5-point system (device pointers,
+ * nz*nr doubles each; any may be NULL).  cR[j,i] couples (j,i)-(j,i+1), cZ[j,i] couples (j,i)-(j+1,i). */
+int hp_assemble_debug(hp_handle h, double dt, int has_old, double* d_cR, double* d_cZ, double* d_diag, double* d_rhs);
+/* elementwise property evaluation on the device (material_properties.py functions); id = hp::PropId */
+int hp_eval_property(hp_handle h, int prop_id, const double* d_T, double* d_out, int64_t n);
+/* same without a solver handle (material_properties.py called on CUDA tensors); stream = cudaStream_t */
+int hp_eval_property_raw(const hp_phys* phys, int prop_id, const double* d_T, double* d_out, int64_t n, void* stream);
+/* rho, cp per cell and face-averaged k per cell at the current iterate (profile capture, main.py:212-254) */
+int hp_eval_cell_fields(hp_handle h, double* d_rho, double* d_cp, double* d_kavg);
+
+/* axial-slab decomposition (FiPy parallelComm / PETSc ghost scatter + allreduce, main.py:11,339;
+ * tests/test_parallel.py).  hp_comm_unique_id fills 128 bytes on rank 0; every rank then calls hp_comm_init.
+ * After it, sweeps exchange one ghost row with each neighbour and all-reduce the CG scalars over NCCL. */
+int hp_comm_unique_id(void* id128);
+int hp_comm_init(hp_handle h, int rank, int nranks, const void* id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HP_SOLVER_H */
