@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- cell-timesteps/s (all sweeps and PCG iterations included) of the transient conduction hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NZxNR]
+
+One "step" = one implicit-Euler time step of the reference's sweep loop (main.py:267-271: updateOld + 5 sweeps)
+on a synthetic refined composite mesh with temperature-dependent properties (BASELINE.json configs[2] at N=1,
+configs[3] -- axial slabs -- at N>1).  Prints ONE JSON line (contract in the task statement):
+value = cells * K / device seconds (CUDA events, max over ranks); e2e = the same through the public API with
+pinned HOST buffers (H2D of the field before and D2H after every step inside the timed region);
+roofline = dominant kernel's algorithmic bytes / its CUDA-event duration vs the measured HBM copy peak;
+cpu_baseline = the oracle (numpy/scipy restatement of the FiPy sweep) timed on this box's host cores.
+
+--impl reference times that oracle alone (FiPy itself is not installable: DESIGN.md) and prints the same line
+with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RADIAL_SPLIT = {1024: (128, 256, 640), 4096: (512, 1024, 2560), 512: (64, 128, 320), 256: (32, 64, 160), 128: (16, 32, 80)}
+DT, SWEEPS, HAS_OLD = 0.1, 5, True
+# algorithmic bytes per cell and launch (fp64; DESIGN.md "Kernels"): reads + writes of full-size fields
+BYTES_PER_CELL = {'cg_A': 56, 'cg_B': 72, 'cg_init': 32, 'diag': 48, 'factor': 24, 'coef': 24}
+
+
+def parse_workload(s):
+    nz, nr = (int(v) for v in s.lower().split('x'))
+    if nr not in RADIAL_SPLIT:
+        raise SystemExit(f"unsupported radial size {nr}; choose from {sorted(RADIAL_SPLIT)}")
+    return nz, nr
+
+
+def mesh_params_for(nz, nr):
+    a, b, c = RADIAL_SPLIT[nr]
+    return dict(nx_wall=nz, nr_wall=c, nx_wick=nz, nr_wick=b, nx_vc=nz, nr_vc=a)
+
+
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.proc, self.index = None, index
+        self.path = f'/tmp/hp_clocks_{os.getpid()}.csv'
+
+    def start(self):
+        exe = shutil.which('nvidia-smi')
+        if not exe:
+            return
+        self.fh = open(self.path, 'w')
+        self.proc = subprocess.Popen([exe, '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                      '-lms', '100'], stdout=self.fh, stderr=subprocess.DEVNULL)
+
+    def stop(self):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        os.unlink(self.path)
+        if not sm:
+            return None
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ------------------------------------------------------------------------------------------------------------
+# oracle timing (cpu_baseline leg and --impl reference)
+# ------------------------------------------------------------------------------------------------------------
+def oracle_steps(nz, nr, n_steps, warmup=0):
+    """Time n_steps implicit-Euler steps (updateOld + 5 sweeps, line-PCG at the GPU's tolerance) of the oracle."""
+    from oracle import fv_oracle as fo
+    cfg = fo.load_config()
+    grid = fo.build_grid(mesh_params_for(nz, nr), cfg['dimensions'])
+    o = fo.Oracle(grid, fo.case_from_config(), has_old=HAS_OLD)
+    solver = 'banded' if nr <= 64 else 'pcg_rline'
+
+    def one():
+        o.update_old()
+        for _ in range(SWEEPS):
+            o.sweep(DT, solver=solver, tol=1e-9, criterion='precond_inf') if solver != 'banded' else o.sweep(DT, solver=solver)
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        one()
+    dt = time.perf_counter() - t0
+    return grid.n_cells * n_steps / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    nz, nr = parse_workload(args.workload or ('4096x1024' if world == 1 else '16384x4096'))
+    snz, snr = 1024, 256      # bounded sample: same mesh recipe and physics, 1/16 (or 1/256) of the cells per step
+    value, secs = oracle_steps(snz, snr, args.steps, args.warmup)
+    sample = (f"{args.steps} steps (after {args.warmup} warm-up) of the oracle on a synthetic composite mesh {snz}x{snr} "
+              f"(same recipe as {nz}x{nr}, T-dependent, updateOld + {SWEEPS} sweeps, line-PCG tol 1e-9 K); FiPy itself is not installable")
+    line = {
+        'impl': 'reference', 'metric': 'cell-timesteps/s (incl. sweeps)', 'value': value, 'unit': 'cell-timesteps/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * secs / max(args.steps, 1),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': f'synthetic composite mesh {nz}x{nr} (axial x radial), T-dependent properties, dt={DT}s, '
+                               f'updateOld + {SWEEPS} sweeps/step', 'sample_mesh': f'{snz}x{snr}'},
+        'cpu_baseline': {'value': value, 'unit': 'cell-timesteps/s', 'cores': 1, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'cell-timesteps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the conduction path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from heat_pipe_solver_b200 import generate_composite_mesh, params
+    from heat_pipe_solver_b200.distributed import make_solver_for_rank
+    cfg = params.load_config()
+    nz, nr = parse_workload(args.workload or ('4096x1024' if world == 1 else '16384x4096'))
+    mesh, _ = generate_composite_mesh(mesh_params_for(nz, nr), cfg['dimensions'])
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        solver = make_solver_for_rank(mesh, cfg, rank, world, tol=args.tol, loop_mode=args.loop_mode)
+
+        def barrier():
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        # ---- device-resident throughput ------------------------------------------------------------
+        solver.run(DT, args.warmup, sweeps=SWEEPS, has_old=HAS_OLD)
+        barrier()
+        it0, l0 = solver.total_iters, solver.kernel_launches
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        solver.run(DT, args.steps, sweeps=SWEEPS, has_old=HAS_OLD)
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        clk = clocks.stop() if rank == 0 else None
+        iters, launches = solver.total_iters - it0, solver.kernel_launches - l0
+        stats = solver.stats(min(SWEEPS * args.steps, 64))
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        n_cells = mesh.numberOfCells
+        value = n_cells * args.steps / (ms * 1e-3)
+
+        # ---- end to end through the public API with host buffers ---------------------------------------
+        n_own = solver.n_cells
+        a = torch.empty(n_own, dtype=torch.float64).pin_memory()
+        b = torch.empty(n_own, dtype=torch.float64).pin_memory()
+        a.copy_(solver.value_tensor().reshape(-1).cpu())
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(args.steps):
+            solver.run_host(a, b, DT, 1, sweeps=SWEEPS, has_old=HAS_OLD)     # H2D + step + D2H + sync
+            a, b = b, a
+        e1.record(stream)
+        barrier()
+        e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
+        if world > 1:
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        e2e_value = n_cells * args.steps / (e2e_ms * 1e-3)
+
+        # ---- per-kernel CUDA-event times (stream-launch mode, same workload continuing) ----------------------
+        roof = None
+        if world == 1:
+            solver.profile_begin(16384)
+            solver.run(DT, max(1, min(3, args.steps)), sweeps=SWEEPS, has_old=HAS_OLD)
+            kt = solver.profile_end()
+            peak, peak_src = measured_peak()
+            tot_ms = sum(v[1] for v in kt.values())
+            dom = max(kt, key=lambda k: kt[k][1])
+            cnt, tms = kt[dom]
+            bytes_per_launch = BYTES_PER_CELL.get(dom, 0) * n_cells
+            achieved = bytes_per_launch / (tms / cnt * 1e-3) / 1e9 if cnt else 0.0
+            traffic = None
+            tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+            if os.path.exists(tp):
+                try:
+                    traffic = json.load(open(tp)).get(dom)
+                except Exception:
+                    traffic = None
+            roof = {'bound': 'hbm', 'kernel': 'k_' + dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                    'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                    'algorithmic_bytes_per_launch': bytes_per_launch, 'avg_launch_ms': tms / cnt if cnt else None,
+                    'share_of_step': tms / tot_ms if tot_ms else None,
+                    'all_kernels': {k: {'launches': c, 'avg_ms': (m / c if c else None),
+                                        'GBps': (BYTES_PER_CELL.get(k, 0) * n_cells / (m / c * 1e-3) / 1e9 if c else None)}
+                                    for k, (c, m) in kt.items() if c}}
+        solver.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        snz, snr = 2048, 512
+        v, secs = oracle_steps(snz, snr, 2)
+        cpu = {'value': v, 'unit': 'cell-timesteps/s', 'cores': 1, 'kind': 'port',
+               'sample': f'2 steps of the numpy/scipy oracle (FiPy restatement, line-PCG tol 1e-9 K) on a {snz}x{snr} synthetic '
+                         f'composite mesh, same physics and sweeps ({secs:.1f} s); host has {os.cpu_count()} cores, the port uses 1'}
+    if rank == 0:
+        line = {
+            'metric': 'cell-timesteps/s (incl. sweeps)', 'value': value, 'unit': 'cell-timesteps/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak' if world == 1 else 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': f'synthetic composite mesh {nz}x{nr} (axial x radial), T-dependent properties, literal mode, '
+                                   f'dt={DT}s, updateOld + {SWEEPS} sweeps/step, radial-line PCG tol {args.tol:g} K',
+                       'parallelism': 'single GPU' if world == 1 else f'axial slabs x{world} (NCCL halo + scalar all-gather)',
+                       'l2': 'working set (11 fp64 fields) exceeds the 126 MB L2; no flush needed',
+                       'pcg_iterations_per_step': iters / args.steps, 'loop_mode': args.loop_mode},
+            'e2e': {'value': e2e_value, 'unit': 'cell-timesteps/s', 'h2d_bytes_per_step': 8 * n_cells,
+                    'd2h_bytes_per_step': 8 * n_cells, 'ms_per_step': e2e_ms / args.steps},
+            'gpu_launches': int(launches), 'clocks': clk,
+            'roofline': roof, 'cpu_baseline': cpu,
+            'last_sweep_stats': stats[-SWEEPS:],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default=None, help='NZxNR, e.g. 4096x1024 (default) or 16384x4096')
+    ap.add_argument('--tol', type=float, default=1e-9)
+    ap.add_argument('--loop-mode', default='graph', choices=['graph', 'host'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.warmup < 3 and args.impl != 'reference':
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

@@ -41,6 +41,12 @@ class HpSweepStat(C.Structure):
                 ('iters', C.c_int32), ('flags', C.c_int32)]
 
 
+class HpKernelTimes(C.Structure):
+    _fields_ = [('count', C.c_int64 * 8), ('total_ms', C.c_double * 8)]
+
+
+KERNEL_KINDS = ('other', 'coef', 'diag', 'factor', 'cg_init', 'cg_A', 'cg_B')
+
 # every symbol include/hp_solver.h declares: name -> (restype, argtypes)
 _H = C.c_void_p
 SIGNATURES = {
@@ -68,6 +74,8 @@ SIGNATURES = {
     'hp_eval_property': (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]),
     'hp_eval_property_raw': (C.c_int, [C.POINTER(HpPhys), C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'hp_eval_cell_fields': (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'hp_profile_begin': (C.c_int, [_H, C.c_int]),
+    'hp_profile_end': (C.c_int, [_H, C.POINTER(HpKernelTimes)]),
     'hp_comm_unique_id': (C.c_int, [C.c_void_p]),
     'hp_comm_init': (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
 }

@@ -92,6 +92,11 @@ struct hp_solver_s {
     ncclComm_t comm = nullptr;
     double* red_local = nullptr;    // [HP_NRED]
     double* red_all = nullptr;      // [nranks*HP_NRED]
+    // per-kernel event timing (hp_profile_begin / hp_profile_end; stream-launch mode only)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_kind;
+    size_t prof_used = 0;
 };
 
 static int dev_alloc(hp_solver_s* h, void** p, size_t bytes) {
@@ -115,8 +120,17 @@ static HpKArgs make_args(const hp_solver_s* h, double dt, int has_old) {
     return a;
 }
 
-static int launch(hp_solver_s* h, const HpKernelLaunch& k, void** params) {
+enum { KIND_OTHER = 0, KIND_COEF, KIND_DIAG, KIND_FACTOR, KIND_INIT, KIND_A, KIND_B, KIND_COUNT };
+
+static int launch(hp_solver_s* h, const HpKernelLaunch& k, void** params, int kind = KIND_OTHER) {
+    const bool prof = h->prof_on && h->prof_used < h->prof_ev.size() / 2;
+    if (prof) CK(cudaEventRecord(h->prof_ev[2 * h->prof_used], h->stream));
     CK(cudaLaunchKernel(k.func, k.grid, k.block, params, k.smem, h->stream));
+    if (prof) {
+        CK(cudaEventRecord(h->prof_ev[2 * h->prof_used + 1], h->stream));
+        h->prof_kind.push_back(kind);
+        h->prof_used++;
+    }
     h->launches_host++;
     return 0;
 }
@@ -225,6 +239,7 @@ int hp_destroy(hp_handle h) {
     cudaStreamSynchronize(h->stream);
     destroy_graphs(h);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_state) cudaFreeHost(h->h_state);
     delete h;
@@ -306,17 +321,17 @@ static int sweep_stream(hp_solver_s* h, double dt, int has_old, bool refactor) {
     a.rhs_out = h->rhs_dbg;
     void* params[] = {&d, &h->phys, &a};
     if (h->phys.gamma == 1) {
-        if (launch(h, hpk::desc_coef(h->cfg, d), params)) return -1;
+        if (launch(h, hpk::desc_coef(h->cfg, d), params, KIND_COEF)) return -1;
     }
     {
         int write_dinv = (h->opts.precond == 0) ? 1 : 0;
         void* p4[] = {&d, &h->phys, &a, &write_dinv};
-        if (launch(h, hpk::desc_diag(h->cfg, d), p4)) return -1;
+        if (launch(h, hpk::desc_diag(h->cfg, d), p4, KIND_DIAG)) return -1;
     }
     if (h->opts.precond == 1 && refactor) {
-        if (launch(h, hpk::desc_factor(h->cfg, d), params)) return -1;
+        if (launch(h, hpk::desc_factor(h->cfg, d), params, KIND_FACTOR)) return -1;
     }
-    if (launch(h, hpk::desc_cg_init(h->cfg, d, h->opts.precond, h->opts.criterion), params)) return -1;
+    if (launch(h, hpk::desc_cg_init(h->cfg, d, h->opts.precond, h->opts.criterion), params, KIND_INIT)) return -1;
     const HpKernelLaunch kA = hpk::desc_cg_A(h->cfg, d);
     const HpKernelLaunch kB = hpk::desc_cg_B(h->cfg, d, h->opts.precond, h->opts.criterion);
     int launched = 0;
@@ -326,8 +341,8 @@ static int sweep_stream(hp_solver_s* h, double dt, int has_old, bool refactor) {
         if (h->h_state->done) break;
         if (launched >= h->opts.max_iter + h->opts.poll_chunk) return fail("sweep_stream: PCG loop did not terminate");
         for (int k = 0; k < h->opts.poll_chunk; ++k) {
-            if (launch(h, kA, params)) return -1;
-            if (launch(h, kB, params)) return -1;
+            if (launch(h, kA, params, KIND_A)) return -1;
+            if (launch(h, kB, params, KIND_B)) return -1;
             launched++;
         }
     }
@@ -408,7 +423,7 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
 static int run_steps(hp_solver_s* h, double dt, int n_steps, int sweeps, int has_old, int update_old) {
     if (!(dt > 0.0)) return fail("dt must be > 0");
     if (sweeps < 1) return fail("sweeps must be >= 1");
-    if (h->opts.loop_mode == 1 && h->nranks == 1 && !h->rhs_dbg) {
+    if (h->opts.loop_mode == 1 && h->nranks == 1 && !h->rhs_dbg && !h->prof_on) {
         GraphEntry* g = nullptr;
         if (get_graph(h, dt, sweeps, has_old, update_old, &g)) return -1;
         for (int s = 0; s < n_steps; ++s) {
@@ -535,6 +550,35 @@ int hp_eval_cell_fields(hp_handle h, double* d_rho, double* d_cp, double* d_kavg
     if (!h) return fail("null handle");
     CK(hpk::launch_cell_fields(h->d, h->phys, d_rho, d_cp, d_kavg, h->stream));
     h->launches_host++;
+    return 0;
+}
+
+int hp_profile_begin(hp_handle h, int max_launches) {
+    if (!h) return fail("null handle");
+    if (max_launches < 1) max_launches = 1;
+    while (h->prof_ev.size() < (size_t)2 * max_launches) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        h->prof_ev.push_back(e);
+    }
+    h->prof_kind.clear();
+    h->prof_used = 0;
+    h->prof_on = true;
+    return 0;
+}
+
+int hp_profile_end(hp_handle h, hp_kernel_times* out) {
+    if (!h || !out) return fail("hp_profile_end: null argument");
+    h->prof_on = false;
+    CK(cudaStreamSynchronize(h->stream));
+    memset(out, 0, sizeof(*out));
+    for (size_t k = 0; k < h->prof_used; ++k) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->prof_ev[2 * k], h->prof_ev[2 * k + 1]));
+        int kind = h->prof_kind[k];
+        out->count[kind] += 1;
+        out->total_ms[kind] += ms;
+    }
     return 0;
 }
 

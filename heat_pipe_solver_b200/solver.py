@@ -101,7 +101,8 @@ class ConductionSolver:
                  properties='temperature_dependent', gamma='snapshot', source='q_over_k',
                  face_k='masked_at_Tface', radiation=False, axial_break=None, rows=None,
                  precond='rline', criterion='precond_inf', tol=1e-9, max_iter=5000, loop_mode='graph',
-                 poll_chunk=8, refactor_every=1, device=None, simple=(7200.0, 440.5, 55.0)):
+                 poll_chunk=8, refactor_every=1, device=None, simple=(7200.0, 440.5, 55.0),
+                 layout=None, regions=None):
         import torch
         if not torch.cuda.is_available():
             raise _lib.HpError("ConductionSolver needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
@@ -110,15 +111,17 @@ class ConductionSolver:
         self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device) \
             if not isinstance(device, torch.device) else device
         self.mesh, self.dimensions, self.parameters, self.constants = mesh, dimensions, parameters, constants
-        self.regions = Regions(mesh, dimensions)
+        self.regions = Regions(mesh, dimensions) if regions is None else regions
         nzg = mesh.nz
         j0, j1 = (0, nzg) if rows is None else rows
-        lines = dict(
-            q=_as_line(parameters['Q_input_flux'] if q is None else q, nzg, 'q'),               # main.py:130
-            h=_as_line(h, nzg, 'h'),                                                            # main.py:37
-            Tamb=_as_line(parameters['T_amb'] if T_amb is None else T_amb, nzg, 'T_amb'),       # main.py:36
-            eps=_as_line(parameters.get('emissivity', 0.0) if emissivity is None else emissivity, nzg, 'emissivity'))
-        self.layout = lay = SlabLayout(mesh, self.regions, j0, j1, lines, axial_break)
+        if layout is None:
+            lines = dict(
+                q=_as_line(parameters['Q_input_flux'] if q is None else q, nzg, 'q'),               # main.py:130
+                h=_as_line(h, nzg, 'h'),                                                            # main.py:37
+                Tamb=_as_line(parameters['T_amb'] if T_amb is None else T_amb, nzg, 'T_amb'),       # main.py:36
+                eps=_as_line(parameters.get('emissivity', 0.0) if emissivity is None else emissivity, nzg, 'emissivity'))
+            layout = SlabLayout(mesh, self.regions, j0, j1, lines, axial_break)
+        self.layout = lay = layout
         self.nr, self.nz = lay.nr, lay.nz
         self.phys = make_phys(parameters, dimensions, constants, properties=properties, gamma=gamma, source=source,
                               face_k=face_k, radiation=radiation, simple_rho=simple[0], simple_cp=simple[1],
@@ -250,6 +253,22 @@ class ConductionSolver:
     @property
     def kernel_launches(self):
         return int(self.lib.hp_kernel_launches(self._h))
+
+    def init_comm(self, rank, world, unique_id: bytes):
+        """Join the library's NCCL communicator (axial slabs); `unique_id` = 128 bytes from rank 0."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _lib.check(self.lib.hp_comm_init(self._h, int(rank), int(world), buf), 'hp_comm_init')
+        self.rank, self.world = rank, world
+
+    def profile_begin(self, max_launches=8192):
+        """Start per-kernel CUDA-event timing; sweeps run in stream-launch mode until profile_end()."""
+        _lib.check(self.lib.hp_profile_begin(self._h, int(max_launches)), 'hp_profile_begin')
+
+    def profile_end(self):
+        """-> {kind: (launches, total_ms)}"""
+        kt = _lib.HpKernelTimes()
+        _lib.check(self.lib.hp_profile_end(self._h, C.byref(kt)), 'hp_profile_end')
+        return {name: (int(kt.count[i]), float(kt.total_ms[i])) for i, name in enumerate(_lib.KERNEL_KINDS)}
 
     def assemble_debug(self, dt, has_old=False):
         """The assembled 5-point system at the current iterate, as (nz, nr) CUDA tensors."""

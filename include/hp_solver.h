@@ -132,6 +132,16 @@ int hp_eval_property_raw(const hp_phys* phys, int prop_id, const double* d_T, do
 /* rho, cp per cell and face-averaged k per cell at the current iterate (profile capture, main.py:212-254) */
 int hp_eval_cell_fields(hp_handle h, double* d_rho, double* d_cp, double* d_kavg);
 
+/* per-kernel device times by CUDA events (bench.py roofline).  Between begin and end every sweep runs in
+ * stream-launch mode with an event pair around each kernel launch (at most max_launches are recorded).
+ * kinds: 0 other, 1 coef, 2 diag, 3 factor, 4 cg_init, 5 cg_A, 6 cg_B */
+typedef struct hp_kernel_times {
+    int64_t count[8];
+    double total_ms[8];
+} hp_kernel_times;
+int hp_profile_begin(hp_handle h, int max_launches);
+int hp_profile_end(hp_handle h, hp_kernel_times* out);
+
 /* axial-slab decomposition (FiPy parallelComm / PETSc ghost scatter + allreduce, main.py:11,339;
  * tests/test_parallel.py).  hp_comm_unique_id fills 128 bytes on rank 0; every rank then calls hp_comm_init.
  * After it, sweeps exchange one ghost row with each neighbour and all-reduce the CG scalars over NCCL. */

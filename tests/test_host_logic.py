@@ -1,0 +1,127 @@
+"""Host-side logic that needs no GPU: loop bookkeeping, slab layouts, member sharding, and the slab partition
+under a real 2-process gloo group."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from heat_pipe_solver_b200 import generate_composite_mesh
+from heat_pipe_solver_b200.distributed import neighbours, slab_rows
+from heat_pipe_solver_b200.ensemble import _StackedLayout, shard_members
+from heat_pipe_solver_b200.main import measurement_schedule
+from heat_pipe_solver_b200.regions import Regions
+from heat_pipe_solver_b200.solver import SlabLayout
+
+
+def test_measurement_schedule_matches_reference_loop():
+    times, caps = measurement_schedule(101.0, 0.1, list(range(5, 101, 5)))       # main.py:119-120,158-159
+    assert len(times) == 1010
+    assert [t for _, t in caps][:3] == [5.0, 10.0, 15.0] and len(caps) == 20
+    assert all(times[s] == t for s, t in caps)
+    # a capture happens on the first loop time >= the scheduled time, once
+    times, caps = measurement_schedule(12.0, 0.7, [1, 2, 3, 10])
+    assert [round(t, 10) for _, t in caps] == [1.4, 2.1, 3.5, 10.5]
+    assert measurement_schedule(3.0, 1.0, [])[1] == []
+
+
+def test_slab_rows_cover_and_balance():
+    for nz, world in ((16384, 8), (4096, 3), (500, 7), (5, 5)):
+        rows = [slab_rows(nz, r, world) for r in range(world)]
+        assert rows[0][0] == 0 and rows[-1][1] == nz
+        assert all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+        sizes = [b - a for a, b in rows]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        slab_rows(3, 0, 4)
+    assert neighbours(0, 4) == (None, 1) and neighbours(3, 4) == (2, None) and neighbours(0, 1) == (None, None)
+
+
+def test_slab_layout_is_a_window_of_the_global_arrays(cfg):
+    mesh, _ = generate_composite_mesh(dict(cfg['mesh']), cfg['dimensions'])
+    reg = Regions(mesh, cfg['dimensions'])
+    lines = dict(q=np.arange(500.0), h=np.full(500, 5.0), Tamb=np.full(500, 290.0), eps=np.zeros(500))
+    whole = SlabLayout(mesh, reg, 0, 500, lines)
+    assert whole.z_v.size == 503 and np.array_equal(whole.z_v[1:-1], mesh.z_v)
+    assert whole.axial_open[0] == 0 and whole.axial_open[500] == 0 and whole.axial_open[1:500].all()
+    a, b = SlabLayout(mesh, reg, 0, 250, lines), SlabLayout(mesh, reg, 250, 500, lines)
+    assert a.axial_open[250] == 1 and b.axial_open[0] == 1 and b.axial_open[250] == 0
+    # ghost rows are the neighbour's rows
+    assert np.array_equal(a.z_v[-3:], mesh.z_v[249:252]) and np.array_equal(b.z_v[:3], mesh.z_v[249:252])
+    assert a.zc_flags[-1] == reg.zc_flags[250] and b.zc_flags[0] == reg.zc_flags[249]
+    assert a.lines['q'][-1] == 250.0 and b.lines['q'][0] == 249.0 and b.lines['q'][-1] == 499.0
+    # the face between the two slabs carries the same flags on both sides
+    assert a.zv_flags[250] == b.zv_flags[0] == reg.zv_flags[250]
+    ab = np.zeros(499, dtype=bool)
+    ab[99] = True
+    cut = SlabLayout(mesh, reg, 0, 500, lines, axial_break=ab)
+    assert cut.axial_open[100] == 0 and cut.axial_open[99] == 1 and cut.axial_open[101] == 1
+
+
+def test_member_sharding_and_stacked_layout(cfg):
+    parts = [shard_members(1024, r, 8) for r in range(8)]
+    assert parts[0] == (0, 128) and parts[-1] == (896, 1024)
+    parts = [shard_members(10, r, 4) for r in range(4)]
+    assert [b - a for a, b in parts] == [3, 3, 2, 2] and parts[-1][1] == 10
+    mesh, _ = generate_composite_mesh(dict(cfg['mesh']), cfg['dimensions'])
+    reg = Regions(mesh, cfg['dimensions'])
+    lay = _StackedLayout(mesh, reg, 3, dict(q=[1.0, 2.0, 3.0], h=[5.0] * 3, Tamb=[290.0] * 3, eps=[0.0] * 3))
+    assert lay.nz == 1500 and lay.z_v.size == 1503 and np.all(np.diff(lay.z_v) > 0)
+    assert list(np.nonzero(lay.axial_open == 0)[0]) == [0, 500, 1000, 1500, 1501]
+    assert np.array_equal(lay.zc_flags[1:501], reg.zc_flags) and np.array_equal(lay.zc_flags[501:1001], reg.zc_flags)
+    assert lay.lines['q'][1] == 1.0 and lay.lines['q'][501] == 2.0 and lay.lines['q'][1500] == 3.0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, nz, nr, out):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from heat_pipe_solver_b200.distributed import gather_field, slab_rows
+    j0, j1 = slab_rows(nz, rank, world)
+    full = torch.arange(nz * nr, dtype=torch.float64).reshape(nz, nr)
+    got = gather_field(full[j0:j1].clone())
+    # halo exchange pattern of the slab solver: my first row goes down, my last row goes up
+    lo, hi = (rank - 1 if rank > 0 else None), (rank + 1 if rank < world - 1 else None)
+    recv_lo, recv_hi = torch.zeros(nr, dtype=torch.float64), torch.zeros(nr, dtype=torch.float64)
+    reqs = []
+    if lo is not None:
+        reqs += [dist.isend(full[j0].clone(), lo), dist.irecv(recv_lo, lo)]
+    if hi is not None:
+        reqs += [dist.isend(full[j1 - 1].clone(), hi), dist.irecv(recv_hi, hi)]
+    for r in reqs:
+        r.wait()
+    ok = bool(torch.equal(got, full))
+    if lo is not None:
+        ok &= bool(torch.equal(recv_lo, full[j0 - 1]))
+    if hi is not None:
+        ok &= bool(torch.equal(recv_hi, full[j1]))
+    # CG scalars: sum / max over ranks
+    v = torch.tensor([float(rank + 1), 10.0 * (rank + 1)], dtype=torch.float64)
+    dist.all_reduce(v)
+    ok &= bool(v[0].item() == world * (world + 1) / 2)
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_slab_partition_under_gloo_world_size_2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    mgr = ctx.Manager()
+    out = mgr.dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, 11, 4, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert dict(out) == {0: True, 1: True}

@@ -1,0 +1,126 @@
+"""The oracle (numpy/scipy restatement of the reference's FiPy sweep) against what can pin it:
+coarse read-offs of the reference's committed plots, analytic known answers, and
+internal consistency (direct vs iterative solvers, symmetry, conservation).  FiPy cannot run here, so the
+assembled solve itself stays "parity unpinned" (see oracle/fv_oracle.py header)."""
+import numpy as np
+import pytest
+from scipy import optimize, special
+
+from oracle import fv_oracle as fo
+
+
+@pytest.fixture(scope='module')
+def native(cfg):
+    return fo.build_grid(cfg['mesh'], cfg['dimensions'])
+
+
+def test_plot_readoffs_101s_run(native):
+    """plots/top_wall_axial_profiles.png: plateau ~290.72 K at loop time 5 s; the tight-solve peak at 100 s is
+    300.93 K (the plot's 300.54 K comes from a loosely converged iterative solve)."""
+    out = fo.run_transient(native, fo.case_from_config(), t_end=101.0, dt=0.1)
+    assert out['n_steps'] == 1010 and list(out['profile_times'][:3]) == [5.0, 10.0, 15.0]
+    assert abs(out['profiles'][0].max() - 290.72) <= 0.05
+    assert abs(out['profiles'][0].max() - 290.744) <= 2e-3         # survey's independent restatement
+    assert abs(out['profiles'][-1].max() - 300.934) <= 2e-3
+    assert 300.54 - 0.1 <= out['profiles'][-1].max() <= 301.0
+
+
+def test_plot_readoffs_3000s_run(native):
+    """plots/12000s/top_wall_axial_profiles.png (+-2 K): T(z~0) = 350 / 387 / 419 K and peak 355 / 390 / 421 K at
+    1038 / 1998 / 2958 s (dt = 1 s run)."""
+    out = fo.run_transient(native, fo.case_from_config(), t_end=2960.0, dt=1.0, measure_times=[1038, 1998, 2958])
+    z0 = out['profiles'][:, 0]
+    peak = out['profiles'].max(axis=1)
+    assert np.all(np.abs(z0 - [350.0, 387.0, 419.0]) <= 2.0), z0
+    assert np.all(np.abs(peak - [355.0, 390.0, 421.0]) <= 2.0), peak
+    assert np.allclose(z0, [349.9, 386.7, 418.6], atol=0.15)       # survey's restatement (P8)
+
+
+def test_direct_solvers_agree_and_pcg_reaches_them(cfg):
+    grid = fo.build_grid(fo.synthetic_mesh_params(48, 4, 8, 20), cfg['dimensions'])
+    T0 = 290 + 200 * np.exp(-((grid.z_c[:, None] - 0.1) / 0.3) ** 2) * np.ones((1, grid.nr))
+    sols = {}
+    for solver, kw in (('banded', {}), ('splu', {}), ('pcg_rline', dict(tol=1e-10)), ('pcg_jacobi', dict(tol=1e-10)),
+                       ('pcg_rline', dict(tol=1e-10, criterion='rowscaled_inf'))):
+        o = fo.Oracle(grid, fo.case_from_config(), T0=T0)
+        o.sweep(0.1, solver=solver, **kw)
+        sols[(solver, tuple(kw))] = o.T
+    ref = sols[('banded', ())]
+    for k, v in sols.items():
+        assert np.max(np.abs(v - ref)) <= 5e-8, k
+
+
+def test_operator_is_symmetric_positive(cfg):
+    grid = fo.build_grid(fo.synthetic_mesh_params(20, 2, 3, 5), cfg['dimensions'])
+    o = fo.Oracle(grid, fo.case_from_config(gamma='lazy'), T0=300.0)
+    S = o.assemble(0.1)
+    A = S.to_csr().toarray()
+    assert np.allclose(A, A.T, rtol=0, atol=0)
+    x = np.random.default_rng(0).standard_normal(A.shape[0])
+    assert np.allclose(S.matvec(x).ravel(), A @ x, rtol=1e-12, atol=1e-12 * np.abs(A).max())
+    assert np.all(np.linalg.eigvalsh(A) > 0)
+    assert np.all(S.cR >= 0) and np.all(S.cZ >= 0) and np.all(S.cR[:, -1] == 0) and np.all(S.cZ[-1, :] == 0)
+
+
+def test_energy_conservation_constant_properties(native, cfg):
+    """Implicit Euler with constant properties and no condenser loss stores exactly the heat put in."""
+    case = fo.case_from_config(properties='simple', h=0.0, source='q')
+    o = fo.Oracle(native, case)
+    for _ in range(40):
+        o.sweep(0.1, solver='banded')
+    stored = (7200.0 * 440.5 * o.vol * (o.T - 290.0)).sum()
+    evap = (o.masks.zc_flags & fo.ZF_BC_EVAP) != 0
+    assert evap.sum() == 27
+    put_in = cfg['parameters']['Q_input_flux'] * o.A_out[evap].sum() * 4.0
+    assert abs(stored - put_in) <= 1e-9 * put_in
+
+
+def test_transient_cylinder_convective_cooling_bessel(cfg):
+    """Known answer independent of FiPy: infinite solid cylinder, uniform T0, convective surface (Robin) --
+    theta(r,t) = sum C_n exp(-l_n^2 Fo) J0(l_n r/R),  l_n J1(l_n) = Bi J0(l_n).  Exercises the cylindrical
+    volumes/areas, the Robin algebra of main.py:133-149 and the transient term."""
+    R, L = 0.01335, 0.982
+    k, rho, cp, h, Ta, T0 = 55.0, 7200.0, 440.5, 4000.0, 290.0, 600.0
+    dims = dict(cfg['dimensions'])
+    dims.update(L_e=1e-9, L_a=1e-9, L_c=L - 2e-9, L_input_left=-2.0, L_input_right=-1.0)   # condenser everywhere, no flux
+    grid = fo.build_grid(fo.synthetic_mesh_params(4, 40, 40, 40), dims)
+    case = fo.Case(dimensions=dims, parameters=dict(cfg['parameters']), constants=dict(cfg['constants']),
+                   h=h, properties='simple')
+    o = fo.Oracle(grid, case, T0=T0)
+    dt, n = 2e-3, 500
+    for _ in range(n):
+        o.sweep(dt, solver='banded')
+    Bi, Fo = h * R / k, k / (rho * cp) * dt * n / R ** 2
+    roots = [optimize.brentq(lambda x: x * special.j1(x) - Bi * special.j0(x), a + 1e-9, a + np.pi - 1e-9)
+             for a in np.arange(0, 40) * np.pi if (lambda f, lo, hi: f(lo) * f(hi) < 0)(
+                 lambda x: x * special.j1(x) - Bi * special.j0(x), a + 1e-9, a + np.pi - 1e-9)]
+    lam = np.array(roots)
+    Cn = 2 / lam * special.j1(lam) / (special.j0(lam) ** 2 + special.j1(lam) ** 2)
+    theta = (Cn[None, :] * np.exp(-lam[None, :] ** 2 * Fo) * special.j0(lam[None, :] * grid.r_c[:, None] / R)).sum(axis=1)
+    exact = Ta + (T0 - Ta) * theta
+    assert np.max(np.abs(o.T[2] - exact)) <= 0.3            # O(dt) + O(dr^2) on a 310 K drop
+    assert np.max(np.abs(o.T[2] - exact)) / (T0 - Ta) <= 1e-3
+
+
+def test_mode_switches_change_the_right_terms(cfg):
+    grid = fo.build_grid(fo.synthetic_mesh_params(32, 2, 4, 8), cfg['dimensions'])
+    T0 = 290 + 300 * np.exp(-((grid.z_c[:, None] - 0.1) / 0.3) ** 2) * np.ones((1, grid.nr))
+    base = fo.Oracle(grid, fo.case_from_config(), T0=T0).assemble(0.1)
+    lazy = fo.Oracle(grid, fo.case_from_config(gamma='lazy'), T0=T0).assemble(0.1)
+    srcq = fo.Oracle(grid, fo.case_from_config(source='q'), T0=T0).assemble(0.1)
+    rad = fo.Oracle(grid, fo.case_from_config(radiation=True), T0=T0).assemble(0.1)
+    assert not np.allclose(base.cR, lazy.cR) and np.array_equal(base.cR, srcq.cR) and np.array_equal(base.cR, rad.cR)
+    evap = (fo.build_masks(grid, cfg['dimensions']).zc_flags & fo.ZF_BC_EVAP) != 0
+    k_out = fo.P.steel_k(T0[:, -1])
+    assert np.allclose((srcq.rhs - base.rhs)[evap, -1], ((1 - 1 / k_out) * cfg['parameters']['Q_input_flux'] * grid.r_v[-1] * grid.dz)[evap])
+    assert np.array_equal(base.rhs[:, :-1], rad.rhs[:, :-1]) and np.all(rad.rhs[:, -1] <= base.rhs[:, -1])
+
+
+def test_pcg_iteration_counts_are_modest_with_line_preconditioner(cfg):
+    """SURVEY probe P6: the radial-line preconditioner needs far fewer iterations than Jacobi on refined meshes."""
+    grid = fo.build_grid(fo.synthetic_mesh_params(256, 16, 32, 80), cfg['dimensions'])
+    o1, o2 = fo.Oracle(grid, fo.case_from_config()), fo.Oracle(grid, fo.case_from_config())
+    o1.sweep(0.1, solver='pcg_rline')
+    o2.sweep(0.1, solver='pcg_jacobi')
+    assert o1.last_solver_info['iterations'] < 40 < 400 < o2.last_solver_info['iterations']
+    assert np.max(np.abs(o1.T - o2.T)) <= 1e-7
