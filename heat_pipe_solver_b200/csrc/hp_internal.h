@@ -64,7 +64,8 @@ struct HpKArgs {
 
 struct HpLaunchCfg {
     int tpl, ept, vec;       // team kernels: threads per line, elements per thread, vector loads ok
-    int cta_threads, teams_per_cta, grid_team;   // grid for the marching kernels
+    int cta_threads, teams_per_cta;              // marching kernels; their grid = one resident wave (team_grid)
+    int num_sms, nz;
     int grid_cell, cta_cell;                     // grid for thread-per-cell kernels
     int grid_factor, cta_factor;
 };

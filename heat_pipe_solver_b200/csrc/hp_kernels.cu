@@ -332,6 +332,7 @@ __global__ void __launch_bounds__(32) k_factor_rline(HpDev d, hp_phys ph, HpKArg
 template <int TPL>
 struct TeamGeom {
     static constexpr int CTA = (TPL < 256) ? 256 : TPL;
+    static constexpr int MIN_CTAS = (TPL <= 256) ? 3 : 1;   // register budget: 3 x 256 threads x <= 85 regs
     static constexpr int LPC = CTA / TPL;
     static constexpr int NW = TPL / 32;       // warps per team
 };
@@ -351,7 +352,7 @@ __device__ __forceinline__ void team_barrier(int team_in_cta) {
 //   pq    = sum p_new*q
 // last CTA: alpha = rz/pq, parity ^= 1, first = 0
 template <int TPL, int EPT, bool VEC>
-__global__ void __launch_bounds__(TeamGeom<TPL>::CTA) k_cg_A(HpDev d, hp_phys ph, HpKArgs a) {
+__global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::MIN_CTAS) k_cg_A(HpDev d, hp_phys ph, HpKArgs a) {
     using G = TeamGeom<TPL>;
     const HpState s0 = *d.st;
     if (s0.done) return;
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA) k_cg_A(HpDev d, hp_phys ph
 //   rz = sum r z ; rr = sum r r ; crit = max|z| (criterion 0) or max|r/diag| (criterion 1)
 // last CTA: beta = rz_new/rz, iter++, convergence flag, sweep statistics, WHILE condition
 template <int TPL, int EPT, bool VEC, bool RLINE, bool INIT>
-__global__ void __launch_bounds__(TeamGeom<TPL>::CTA) k_cg_B(HpDev d, hp_phys ph, HpKArgs a) {
+__global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::MIN_CTAS) k_cg_B(HpDev d, hp_phys ph, HpKArgs a) {
     using G = TeamGeom<TPL>;
     const HpState s0 = *d.st;
     if (!INIT && s0.done) return;
@@ -697,16 +698,7 @@ bool pick_config(int nr, int nz, int num_sms, HpLaunchCfg* cfg, const char** err
     cfg->vec = (ept >= 4) && (nr % ept == 0);
     cfg->cta_threads = tpl < 256 ? 256 : tpl;
     cfg->teams_per_cta = cfg->cta_threads / tpl;
-    // resident CTAs per SM (register bound ~ 64K regs): 256 thr -> 3, 512 -> 1 (128 regs), 1024 -> 1
-    int res = cfg->cta_threads == 256 ? 3 : 1;
-    long long max_teams = (long long)num_sms * res * cfg->teams_per_cta;
-    long long teams = nz < max_teams ? nz : max_teams;
-    // at least 2 rows per team when the problem is small (amortise halo rows)
-    if (teams > 1 && nz / teams < 2) teams = (nz + 1) / 2;
-    int grid = (int)((teams + cfg->teams_per_cta - 1) / cfg->teams_per_cta);
-    if (grid < 1) grid = 1;
-    if (grid > HP_MAX_PARTIALS) grid = HP_MAX_PARTIALS;
-    cfg->grid_team = grid;
+    cfg->num_sms = num_sms; cfg->nz = nz;
     cfg->cta_cell = 256;
     long long ncell = (long long)(nz + 1) * nr;
     long long gc = (ncell + 255) / 256;
@@ -716,6 +708,20 @@ bool pick_config(int nr, int nz, int num_sms, HpLaunchCfg* cfg, const char** err
     cfg->cta_factor = 32;
     cfg->grid_factor = (nz + 31) / 32;
     return true;
+}
+
+// Grid of a marching kernel: exactly one resident wave (occupancy of THIS instantiation x SM count) so that no
+// partially filled second wave appears; fewer CTAs when the mesh has too few rows (>= 2 rows per team).
+static int team_grid(const void* func, const HpLaunchCfg& c) {
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, c.cta_threads, 0) != cudaSuccess || occ < 1) occ = 1;
+    long long max_teams = (long long)c.num_sms * occ * c.teams_per_cta;
+    long long teams = c.nz < max_teams ? c.nz : max_teams;
+    if (teams > 1 && c.nz / teams < 2) teams = (c.nz + 1) / 2;
+    long long grid = (teams + c.teams_per_cta - 1) / c.teams_per_cta;
+    if (grid < 1) grid = 1;
+    if (grid > HP_MAX_PARTIALS) grid = HP_MAX_PARTIALS;
+    return (int)grid;
 }
 
 HpKernelLaunch desc_snapshot_kout(const HpLaunchCfg& c, const HpDev& d) {
@@ -735,14 +741,14 @@ HpKernelLaunch desc_cg_A(const HpLaunchCfg& c, const HpDev& d) {
 #define HP_X(T, E, V) f = fn_A<T, E, V>()
     HP_DISPATCH(c, HP_X);
 #undef HP_X
-    return {f, dim3(c.grid_team), dim3(c.cta_threads), 0};
+    return {f, dim3(team_grid(f, c)), dim3(c.cta_threads), 0};
 }
 static HpKernelLaunch desc_B(const HpLaunchCfg& c, int precond, int init) {
     const void* f = nullptr;
 #define HP_X(T, E, V) f = fn_B<T, E, V>(precond, init)
     HP_DISPATCH(c, HP_X);
 #undef HP_X
-    return {f, dim3(c.grid_team), dim3(c.cta_threads), 0};
+    return {f, dim3(team_grid(f, c)), dim3(c.cta_threads), 0};
 }
 HpKernelLaunch desc_cg_init(const HpLaunchCfg& c, const HpDev& d, int precond, int criterion) { return desc_B(c, precond, 1); }
 HpKernelLaunch desc_cg_B(const HpLaunchCfg& c, const HpDev& d, int precond, int criterion) { return desc_B(c, precond, 0); }
