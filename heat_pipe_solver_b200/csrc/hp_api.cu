@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -90,8 +91,11 @@ struct hp_solver_s {
     // slabs
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
-    double* red_local = nullptr;    // [HP_NRED]
-    double* red_all = nullptr;      // [nranks*HP_NRED]
+    // L2 access-policy window over the contiguous (q, z) block
+    bool l2_on = false;
+    void* l2_base = nullptr;
+    size_t l2_bytes = 0;
+    cudaAccessPolicyWindow l2_window{};
     // per-kernel event timing (hp_profile_begin / hp_profile_end; stream-launch mode only)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -113,10 +117,42 @@ static int upload(hp_solver_s* h, const T** dst, const std::vector<T>& v) {
     return 0;
 }
 
+// L2 residency of the producer->consumer vectors of the PCG iteration (q: k_cg_A -> k_cg_B, z: k_cg_B -> k_cg_A).
+// The window is attached to every PCG kernel launch (stream attribute in stream mode, kernel-node attribute in
+// graphs).  HP_L2_PERSIST=0 disables it (A/B measurements).
+static void setup_l2_window(hp_solver_s* h, const cudaDeviceProp& prop) {
+    h->l2_on = false;
+    const char* env = getenv("HP_L2_PERSIST");
+    if (env && env[0] == '0') return;
+    if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
+    size_t want = h->l2_bytes;
+    size_t win = want < (size_t)prop.accessPolicyMaxWindowSize ? want : (size_t)prop.accessPolicyMaxWindowSize;
+    size_t carve = win < (size_t)prop.persistingL2CacheMaxSize ? win : (size_t)prop.persistingL2CacheMaxSize;
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
+    memset(&h->l2_window, 0, sizeof(h->l2_window));
+    h->l2_window.base_ptr = h->l2_base;
+    h->l2_window.num_bytes = win;
+    h->l2_window.hitRatio = (float)((double)carve / (double)win);
+    h->l2_window.hitProp = cudaAccessPropertyPersisting;
+    h->l2_window.missProp = cudaAccessPropertyStreaming;
+    h->l2_on = true;
+}
+
+static int apply_l2_to_stream(hp_solver_s* h) {
+    if (!h->l2_on) return 0;
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof(v));
+    v.accessPolicyWindow = h->l2_window;
+    CK(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &v));
+    return 0;
+}
+
 static HpKArgs make_args(const hp_solver_s* h, double dt, int has_old) {
     HpKArgs a{};
     a.dt = dt; a.tol = h->opts.tol; a.has_old = has_old; a.max_iter = h->opts.max_iter;
     a.criterion = h->opts.criterion; a.use_cond = 0; a.cond = 0; a.rhs_out = nullptr;
+    static const int pf = [] { const char* e = getenv("HP_PREFETCH"); return e ? atoi(e) : 0; }();
+    a.prefetch = pf;   // measured slower on B200 (profiles/): off unless asked for
     return a;
 }
 
@@ -164,7 +200,7 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
         if (!(m->z_v[g + 1] > m->z_v[g])) { delete h; return fail("hp_create: z_v must be strictly increasing"); }
 
     HpDev& d = h->d;
-    d.nr = nr; d.nz = nz;
+    d.nr = nr; d.nz = nz; d.ncolA = h->cfg.ncolA; d.nranks = 1; d.rank = 0; d.red_local = nullptr; d.red_all = nullptr;
     std::vector<double> r_v(m->r_v, m->r_v + nr + 1), r_c(nr), dr(nr), ar(nr, 0.0), dcr(nr, 1.0);
     for (int i = 0; i < nr; ++i) { r_c[i] = 0.5 * (r_v[i] + r_v[i + 1]); dr[i] = r_v[i + 1] - r_v[i]; }
     for (int i = 0; i + 1 < nr; ++i) { dcr[i] = r_c[i + 1] - r_c[i]; ar[i] = (r_v[i + 1] - r_c[i]) / dcr[i]; }
@@ -190,11 +226,21 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
     UP(eps_line, std::vector<double>(m->eps_line, m->eps_line + nz + 2));
 #undef UP
     h->field_elems = (size_t)(nz + 2) * nr + 64;
-    double** fields[] = {&d.T, &d.Told, &d.cR, &d.cZ, &d.diag, &d.dinv, &d.r, &d.q, &d.z, &d.p0, &d.p1};
+    double** fields[] = {&d.T, &d.Told, &d.cR, &d.cZ, &d.diag, &d.dinv, &d.r, &d.p0, &d.p1};
     for (double** f : fields) {
         if (dev_alloc(h, (void**)f, h->field_elems * sizeof(double))) { hp_destroy(h); return -1; }
         CK(cudaMemsetAsync(*f, 0, h->field_elems * sizeof(double), h->stream));
     }
+    // q and z are produced by one PCG kernel and consumed by the next one: one contiguous block so that a single
+    // L2 access-policy window can keep both resident across kernel boundaries (setup_l2_window)
+    {
+        double* qz = nullptr;
+        if (dev_alloc(h, (void**)&qz, 2 * h->field_elems * sizeof(double))) { hp_destroy(h); return -1; }
+        CK(cudaMemsetAsync(qz, 0, 2 * h->field_elems * sizeof(double), h->stream));
+        d.q = qz; d.z = qz + h->field_elems;
+        h->l2_base = qz; h->l2_bytes = 2 * h->field_elems * sizeof(double);
+    }
+    setup_l2_window(h, prop);
     void* p = nullptr;
     if (dev_alloc(h, &p, sizeof(double) * (nz + 2))) { hp_destroy(h); return -1; }
     d.k0_out = (const double*)p;
@@ -314,12 +360,24 @@ static int exchange_rows(hp_solver_s* h, double* field) {
     return 0;
 }
 
+// all ranks' per-kernel sums -> every rank, then one thread advances the scalar recurrences identically everywhere
+static int combine(hp_solver_s* h, HpKArgs& a, int kind) {
+    if (h->nranks == 1) return 0;
+    NK(g_nccl.AllGather(h->d.red_local, h->d.red_all, HP_NRED, ncclFloat64, h->comm, h->stream));
+    void* p4[] = {&h->d, &h->phys, &a, &kind};
+    return launch(h, hpk::desc_finalize(), p4, KIND_OTHER);
+}
+
 // ---- one sweep with plain stream launches, host-polled PCG loop ------------------------------------------
+// Under axial slabs (nranks > 1): ghost rows of T before assembly, ghost rows of z before every direction
+// update, and the CG scalars combined over ranks after every reducing kernel (FIN_* kinds of k_finalize).
 static int sweep_stream(hp_solver_s* h, double dt, int has_old, bool refactor) {
     HpDev& d = h->d;
     HpKArgs a = make_args(h, dt, has_old);
     a.rhs_out = h->rhs_dbg;
     void* params[] = {&d, &h->phys, &a};
+    if (apply_l2_to_stream(h)) return -1;
+    if (exchange_rows(h, d.T)) return -1;
     if (h->phys.gamma == 1) {
         if (launch(h, hpk::desc_coef(h->cfg, d), params, KIND_COEF)) return -1;
     }
@@ -327,11 +385,13 @@ static int sweep_stream(hp_solver_s* h, double dt, int has_old, bool refactor) {
         int write_dinv = (h->opts.precond == 0) ? 1 : 0;
         void* p4[] = {&d, &h->phys, &a, &write_dinv};
         if (launch(h, hpk::desc_diag(h->cfg, d), p4, KIND_DIAG)) return -1;
+        if (combine(h, a, 0)) return -1;
     }
     if (h->opts.precond == 1 && refactor) {
         if (launch(h, hpk::desc_factor(h->cfg, d), params, KIND_FACTOR)) return -1;
     }
     if (launch(h, hpk::desc_cg_init(h->cfg, d, h->opts.precond, h->opts.criterion), params, KIND_INIT)) return -1;
+    if (combine(h, a, 3)) return -1;
     const HpKernelLaunch kA = hpk::desc_cg_A(h->cfg, d);
     const HpKernelLaunch kB = hpk::desc_cg_B(h->cfg, d, h->opts.precond, h->opts.criterion);
     int launched = 0;
@@ -341,8 +401,11 @@ static int sweep_stream(hp_solver_s* h, double dt, int has_old, bool refactor) {
         if (h->h_state->done) break;
         if (launched >= h->opts.max_iter + h->opts.poll_chunk) return fail("sweep_stream: PCG loop did not terminate");
         for (int k = 0; k < h->opts.poll_chunk; ++k) {
+            if (exchange_rows(h, d.z)) return -1;
             if (launch(h, kA, params, KIND_A)) return -1;
+            if (combine(h, a, 1)) return -1;
             if (launch(h, kB, params, KIND_B)) return -1;
+            if (combine(h, a, 2)) return -1;
             launched++;
         }
     }
@@ -355,12 +418,18 @@ static int sweep_stream(hp_solver_s* h, double dt, int has_old, bool refactor) {
 struct NodeChain {
     cudaGraph_t g; cudaGraphNode_t last = nullptr; int count = 0;
 };
-static int chain_kernel(NodeChain& c, const HpKernelLaunch& k, void** params) {
+static int chain_kernel(NodeChain& c, const HpKernelLaunch& k, void** params, const hp_solver_s* h = nullptr) {
     cudaKernelNodeParams np{};
     np.func = (void*)k.func; np.gridDim = k.grid; np.blockDim = k.block; np.sharedMemBytes = (unsigned)k.smem;
     np.kernelParams = params; np.extra = nullptr;
     cudaGraphNode_t n;
     CK(cudaGraphAddKernelNode(&n, c.g, c.last ? &c.last : nullptr, c.last ? 1 : 0, &np));
+    if (h && h->l2_on) {
+        cudaKernelNodeAttrValue v;
+        memset(&v, 0, sizeof(v));
+        v.accessPolicyWindow = h->l2_window;
+        CK(cudaGraphKernelNodeSetAttribute(n, cudaKernelNodeAttributeAccessPolicyWindow, &v));
+    }
     c.last = n; c.count++;
     return 0;
 }
@@ -400,7 +469,7 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
         cudaGraphConditionalHandle cond;
         CK(cudaGraphConditionalHandleCreate(&cond, e.graph, 0, cudaGraphCondAssignDefault));
         a.use_cond = 1; a.cond = (unsigned long long)cond;
-        if (chain_kernel(c, hpk::desc_cg_init(h->cfg, d, h->opts.precond, h->opts.criterion), params)) return -1;
+        if (chain_kernel(c, hpk::desc_cg_init(h->cfg, d, h->opts.precond, h->opts.criterion), params, h)) return -1;
         cudaGraphNodeParams cp{};
         cp.type = cudaGraphNodeTypeConditional;
         cp.conditional.handle = cond;
@@ -410,8 +479,8 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
         CK(cudaGraphAddNode(&wn, e.graph, c.last ? &c.last : nullptr, c.last ? 1 : 0, &cp));
         c.last = wn;
         NodeChain body{cp.conditional.phGraph_out[0]};
-        if (chain_kernel(body, hpk::desc_cg_A(h->cfg, d), params)) return -1;
-        if (chain_kernel(body, hpk::desc_cg_B(h->cfg, d, h->opts.precond, h->opts.criterion), params)) return -1;
+        if (chain_kernel(body, hpk::desc_cg_A(h->cfg, d), params, h)) return -1;
+        if (chain_kernel(body, hpk::desc_cg_B(h->cfg, d, h->opts.precond, h->opts.criterion), params, h)) return -1;
     }
     e.static_nodes = c.count;
     CK(cudaGraphInstantiate(&e.exec, e.graph, 0));
@@ -433,7 +502,6 @@ static int run_steps(hp_solver_s* h, double dt, int n_steps, int sweeps, int has
         }
         return 0;
     }
-    if (h->nranks > 1) return fail("slab mode: use hp_sweep_slab path (not built in this call)");
     for (int s = 0; s < n_steps; ++s) {
         if (update_old && hp_update_old(h)) return -1;
         for (int k = 0; k < sweeps; ++k)
@@ -599,9 +667,13 @@ int hp_comm_init(hp_handle h, int rank, int nranks, const void* id128) {
     memcpy(&id, id128, sizeof(id));
     NK(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
     h->rank = rank; h->nranks = nranks;
-    if (dev_alloc(h, (void**)&h->red_local, sizeof(double) * HP_NRED)) return -1;
-    if (dev_alloc(h, (void**)&h->red_all, sizeof(double) * HP_NRED * nranks)) return -1;
-    (void)exchange_rows;
+    if (dev_alloc(h, (void**)&h->d.red_local, sizeof(double) * HP_NRED)) return -1;
+    if (dev_alloc(h, (void**)&h->d.red_all, sizeof(double) * HP_NRED * nranks)) return -1;
+    CK(cudaMemsetAsync(h->d.red_local, 0, sizeof(double) * HP_NRED, h->stream));
+    h->d.nranks = nranks; h->d.rank = rank;
+    destroy_graphs(h);
+    // the snapshot couplings across slab interfaces were assembled from the T_amb-filled ghost rows at create
+    // time (both neighbours compute the same value); nothing to exchange here.
     return 0;
 }
 

@@ -48,6 +48,11 @@ struct HpDev {
     HpState* st;
     hp_sweep_stat* stats;    // ring of HP_STATS_CAP
     double* partials;        // [HP_NRED * HP_MAX_PARTIALS]
+    // axial slabs (nranks > 1): per-rank sums and their all-gathered copies
+    int nranks, rank;
+    int ncolA;               // column tiles of k_cg_A
+    double* red_local;       // [HP_NRED]
+    double* red_all;         // [nranks * HP_NRED]
 };
 
 // Per-launch scalar arguments shared by all kernels: signature (HpDev, hp_phys, HpKArgs [, extra]).
@@ -58,13 +63,18 @@ struct HpKArgs {
     int32_t max_iter;
     int32_t criterion;
     int32_t use_cond;
+    int32_t prefetch;          // bit0: k_cg_A, bit1: k_cg_B issue bulk L2 prefetches of the next row
+    int32_t _pad;
     unsigned long long cond;   // cudaGraphConditionalHandle of the enclosing WHILE node (use_cond != 0)
     double* rhs_out;           // optional (debug): full rhs, ghost-inclusive layout
 };
 
 struct HpLaunchCfg {
-    int tpl, ept, vec;       // team kernels: threads per line, elements per thread, vector loads ok
+    // k_cg_B / k_cg_init (whole rows per team: the line solve scans along the row)
+    int tpl, ept, vec;       // threads per line, elements per thread, vector loads ok
     int cta_threads, teams_per_cta;              // marching kernels; their grid = one resident wave (team_grid)
+    // k_cg_A (no row-wide dependency: rows wider than tplA*eptA are cut into ncolA column tiles)
+    int tplA, eptA, vecA, ctaA, teams_per_ctaA, ncolA;
     int num_sms, nz;
     int grid_cell, cta_cell;                     // grid for thread-per-cell kernels
     int grid_factor, cta_factor;
@@ -88,6 +98,7 @@ HpKernelLaunch desc_diag(const HpLaunchCfg&, const HpDev&);
 HpKernelLaunch desc_factor(const HpLaunchCfg&, const HpDev&);
 HpKernelLaunch desc_cg_init(const HpLaunchCfg&, const HpDev&, int precond, int criterion);
 HpKernelLaunch desc_cg_A(const HpLaunchCfg&, const HpDev&);
+HpKernelLaunch desc_finalize();   // args: (HpDev, hp_phys, HpKArgs, int kind) kind: 0 diag, 1 A, 2 B, 3 init
 HpKernelLaunch desc_cg_B(const HpLaunchCfg&, const HpDev&, int precond, int criterion);
 
 cudaError_t launch_eval_property(const hp_phys& ph, int id, const double* T, double* out, long long n, cudaStream_t s);

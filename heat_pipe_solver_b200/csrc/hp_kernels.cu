@@ -15,6 +15,8 @@
 // CTA (ticket), which also advances the PCG scalar recurrences on the device -- no host round trip.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include "hp_internal.h"
 #include "hp_props.cuh"
 
@@ -29,6 +31,12 @@ __device__ __forceinline__ void ld256(const double* p, double* v) {
 }
 __device__ __forceinline__ void st256(double* p, const double* v) {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+
+// TMA-class bulk prefetch of one contiguous row into L2 (one instruction, no registers, no smem):
+// the next row of every streamed field is requested while the current row is being processed.
+__device__ __forceinline__ void prefetch_row_l2(const double* row, int nr) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"(nr * 8) : "memory");
 }
 
 template <int EPT, bool VEC>
@@ -132,6 +140,87 @@ __device__ __forceinline__ void set_cond(const HpKArgs& a, int keep_going) {
 __device__ __forceinline__ bool converged(const HpKArgs& a, double crit, double rr, double b2) {
     if (a.criterion == 2) return rr <= a.tol * a.tol * b2;
     return crit <= a.tol;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scalar recurrences of the sweep / PCG, executed by ONE thread per kernel: the last CTA of the producing
+// kernel (single GPU) or k_finalize after the all-gather of the per-rank sums (axial slabs).
+// ------------------------------------------------------------------------------------------------
+enum { FIN_DIAG = 0, FIN_A = 1, FIN_B = 2, FIN_INIT = 3 };
+
+__device__ __forceinline__ void finalize_diag(const HpDev& d, const HpKArgs& a, double res2, double b2) {
+    HpState* s = d.st;
+    s->res2 = res2;
+    s->b2 = b2;
+    s->iter = 0; s->done = 0; s->first = 1; s->flags = 0;
+    hp_sweep_stat* stt = &d.stats[s->sweep_count % HP_STATS_CAP];
+    stt->residual_l2 = sqrt(res2);
+    stt->rhs_l2 = sqrt(b2);
+    stt->crit = 0.0; stt->iters = 0; stt->flags = 0;
+    s->sweep_count += 1;
+}
+
+__device__ __forceinline__ void finalize_A(const HpDev& d, const HpKArgs& a, double pq) {
+    HpState* s = d.st;
+    s->pq = pq;
+    if (pq > 0.0 && isfinite(pq)) {
+        s->alpha = s->rz / pq;
+    } else {
+        s->alpha = 0.0;
+        s->flags |= 4;          // breakdown
+    }
+    s->parity ^= 1;
+    s->first = 0;
+}
+
+__device__ __forceinline__ void finalize_B(const HpDev& d, const HpKArgs& a, bool init, double rz_new, double rr, double crit) {
+    HpState* s = d.st;
+    int flags = s->flags;
+    int done = 0;
+    if (init) {
+        s->rz = rz_new;
+        s->parity = 0;
+        s->first = 1;
+    } else {
+        s->beta = (s->rz != 0.0) ? rz_new / s->rz : 0.0;
+        s->rz = rz_new;
+        s->iter += 1;
+        s->total_iters += 1;
+    }
+    s->rr = rr; s->crit = crit;
+    const bool nan_bad = !(isfinite(rz_new) && isfinite(crit));
+    if (converged(a, crit, rr, s->b2)) { done = 1; flags |= 1; }
+    else if (nan_bad || (flags & 4)) { done = 1; flags |= 4; }
+    else if (s->iter >= a.max_iter) { done = 1; flags |= 2; }
+    s->done = done; s->flags = flags;
+    hp_sweep_stat* stt = &d.stats[(s->sweep_count - 1) % HP_STATS_CAP];
+    stt->crit = (a.criterion == 2) ? sqrt(rr) : crit;
+    stt->iters = s->iter;
+    stt->flags = flags;
+    set_cond(a, !done);
+}
+
+// slabs: this rank's sums go to red_local; k_finalize combines all ranks' after the all-gather
+template <int NV>
+__device__ __forceinline__ void stash_local(const HpDev& d, const double (&tot)[NV]) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) d.red_local[k] = tot[k];
+}
+
+__global__ void k_finalize(HpDev d, hp_phys ph, HpKArgs a, int kind) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if ((kind == FIN_A || kind == FIN_B) && d.st->done) return;
+    double v[HP_NRED];
+    for (int k = 0; k < HP_NRED; ++k) v[k] = 0.0;
+    for (int r = 0; r < d.nranks; ++r) {           // fixed rank order: every rank computes identical scalars
+        const double* p = d.red_all + r * HP_NRED;
+        if (kind == FIN_DIAG) { v[0] += p[0]; v[1] += p[1]; }
+        else if (kind == FIN_A) { v[0] += p[0]; }
+        else { v[0] += p[0]; v[1] += p[1]; v[2] = fmax(v[2], p[2]); }
+    }
+    if (kind == FIN_DIAG) finalize_diag(d, a, v[0], v[1]);
+    else if (kind == FIN_A) finalize_A(d, a, v[0]);
+    else finalize_B(d, a, kind == FIN_INIT, v[0], v[1], v[2]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -259,15 +348,8 @@ __global__ void __launch_bounds__(256) k_diag(HpDev d, hp_phys ph, HpKArgs a, in
     }
     double tot[2];
     if (cta_publish<2>(acc, 0u, d.partials, &d.st->ticket, tot) && threadIdx.x == 0) {
-        HpState* s = d.st;
-        s->res2 = tot[0];
-        s->b2 = tot[1];
-        s->iter = 0; s->done = 0; s->first = 1; s->flags = 0;
-        hp_sweep_stat* stt = &d.stats[s->sweep_count % HP_STATS_CAP];
-        stt->residual_l2 = sqrt(tot[0]);
-        stt->rhs_l2 = sqrt(tot[1]);
-        stt->crit = 0.0; stt->iters = 0; stt->flags = 0;
-        s->sweep_count += 1;
+        if (d.nranks > 1) stash_local<2>(d, tot);
+        else finalize_diag(d, a, tot[0], tot[1]);
     }
 }
 
@@ -333,6 +415,10 @@ template <int TPL>
 struct TeamGeom {
     static constexpr int CTA = (TPL < 256) ? 256 : TPL;
     static constexpr int MIN_CTAS = (TPL <= 256) ? 3 : 1;   // register budget: 3 x 256 threads x <= 85 regs
+    // resident CTAs the register budget is tuned for: kernel A keeps three rows of the direction in registers
+    // (2 CTAs of 256 threads, <= 128 regs); EPT = 8 doubles the per-thread state of both kernels
+    static constexpr int minb_A(int ept) { return TPL <= 256 ? 2 : 1; }
+    static constexpr int minb_B(int ept) { return TPL <= 256 ? (ept >= 8 ? 2 : 3) : 1; }
     static constexpr int LPC = CTA / TPL;
     static constexpr int NW = TPL / 32;       // warps per team
 };
@@ -351,16 +437,21 @@ __device__ __forceinline__ void team_barrier(int team_in_cta) {
 //   q     = L p_new                             5-point, couplings cR / cZ, diagonal diag
 //   pq    = sum p_new*q
 // last CTA: alpha = rz/pq, parity ^= 1, first = 0
-template <int TPL, int EPT, bool VEC>
-__global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::MIN_CTAS) k_cg_A(HpDev d, hp_phys ph, HpKArgs a) {
+template <int TPL, int EPT, bool VEC, int MINB = TeamGeom<TPL>::minb_A(EPT)>
+__global__ void __launch_bounds__(TeamGeom<TPL>::CTA, MINB) k_cg_A(HpDev d, hp_phys ph, HpKArgs a) {
     using G = TeamGeom<TPL>;
     const HpState s0 = *d.st;
     if (s0.done) return;
     const int nr = d.nr, nz = d.nz;
     const int team_in_cta = threadIdx.x / TPL, tl = threadIdx.x % TPL, lane = threadIdx.x & 31;
-    const int i0 = tl * EPT;
+    // teams tile the mesh as (row chunk) x (column tile); neighbours in another tile / warp come from global memory
     const long long team = (long long)blockIdx.x * G::LPC + team_in_cta, nteams = (long long)gridDim.x * G::LPC;
-    const int ja = (int)(team * nz / nteams), jb = (int)((team + 1) * nz / nteams);
+    const int ncol = d.ncolA;
+    const long long nchunks = nteams / ncol;
+    const long long chunk = team / ncol;
+    const int i0 = ((int)(team % ncol) * TPL + tl) * EPT;
+    int ja = 0, jb = 0;
+    if (chunk < nchunks) { ja = (int)(chunk * nz / nchunks); jb = (int)((chunk + 1) * nz / nchunks); }
     const double beta = s0.beta;
     const bool first = s0.first != 0;
     const double* __restrict__ pin = s0.parity ? d.p1 : d.p0;
@@ -384,30 +475,50 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::MIN_CTAS) k
         const double zz = zf[idx];
         return first ? zz : fma(beta, pin[idx], zz);
     };
+    // radial neighbours that live in another warp: only lane 0 / lane 31 fetch them, one row AHEAD, together with
+    // the row's vector loads (a dependent second round trip to DRAM per row would halve the streaming rate)
+    const bool has_l = (lane == 0) && (i0 != 0) && (i0 < nr);
+    const bool has_r = (lane == 31) && (i0 + EPT < nr);
 
     double acc[1] = {0.0};
     if (jb > ja) {
         double pm[EPT], pc[EPT], pn[EPT], czm[EPT];
+        double pc_l = 0.0, pc_r = 0.0;
         pnew_row(ja, pm);          // row g = ja  (the row below the first owned row of this team)
         pnew_row(ja + 1, pc);
+        if (has_l) pc_l = pnew_at((long long)(ja + 1) * nr + i0 - 1);
+        if (has_r) pc_r = pnew_at((long long)(ja + 1) * nr + i0 + EPT);
         load_row<EPT, VEC>(d.cZ + (long long)ja * nr, i0, nr, czm);
         if (ja == 0) store_row<EPT, VEC>(pout, i0, nr, pm);                      // lower ghost row
         for (int g = ja + 1; g <= jb; ++g) {
             const long long rb = (long long)g * nr;
-            pnew_row(g + 1, pn);
-            double cr[EPT], cz[EPT], dg[EPT];
+            if (VEC && tl == 0 && g < jb && (a.prefetch & 1)) {
+                prefetch_row_l2(zf + rb + 2 * (long long)nr, nr);
+                if (!first) prefetch_row_l2(pin + rb + 2 * (long long)nr, nr);
+                prefetch_row_l2(d.cR + rb + nr, nr);
+                prefetch_row_l2(d.cZ + rb + nr, nr);
+                prefetch_row_l2(d.diag + rb + nr, nr);
+            }
+            // ---- every load of this row is issued before the first use ----
+            double zz[EPT], pp[EPT], cr[EPT], cz[EPT], dg[EPT];
+            load_row<EPT, VEC>(zf + rb + nr, i0, nr, zz);
+            if (!first) load_row<EPT, VEC>(pin + rb + nr, i0, nr, pp);
             load_row<EPT, VEC>(d.cR + rb, i0, nr, cr);
             load_row<EPT, VEC>(d.cZ + rb, i0, nr, cz);
             load_row<EPT, VEC>(d.diag + rb, i0, nr, dg);
+            double zl = 0.0, plo = 0.0, zr = 0.0, pro = 0.0, crl_e = 0.0;
+            if (has_l) { zl = zf[rb + nr + i0 - 1]; if (!first) plo = pin[rb + nr + i0 - 1]; crl_e = d.cR[rb + i0 - 1]; }
+            if (has_r) { zr = zf[rb + nr + i0 + EPT]; if (!first) pro = pin[rb + nr + i0 + EPT]; }
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) pn[e] = first ? zz[e] : fma(beta, pp[e], zz[e]);
+            const double pn_l = first ? zl : fma(beta, plo, zl);
+            const double pn_r = first ? zr : fma(beta, pro, zr);
             // radial neighbours across thread boundaries
             double pl = __shfl_up_sync(0xffffffffu, pc[EPT - 1], 1);
             double crl = __shfl_up_sync(0xffffffffu, cr[EPT - 1], 1);
             double pr = __shfl_down_sync(0xffffffffu, pc[0], 1);
-            if (lane == 0) {
-                if (tl == 0 || i0 >= nr) { pl = 0.0; crl = 0.0; }
-                else { pl = pnew_at(rb + i0 - 1); crl = d.cR[rb + i0 - 1]; }
-            }
-            if (lane == 31) pr = (i0 + EPT < nr) ? pnew_at(rb + i0 + EPT) : 0.0;
+            if (lane == 0) { pl = pc_l; crl = crl_e; }      // zero when there is no left neighbour
+            if (lane == 31) pr = pc_r;
             double qv[EPT];
 #pragma unroll
             for (int e = 0; e < EPT; ++e) {
@@ -426,22 +537,14 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::MIN_CTAS) k
             store_row<EPT, VEC>(pout + rb, i0, nr, pc);
 #pragma unroll
             for (int e = 0; e < EPT; ++e) { pm[e] = pc[e]; pc[e] = pn[e]; czm[e] = cz[e]; }
+            pc_l = pn_l; pc_r = pn_r;
         }
         if (jb == nz) store_row<EPT, VEC>(pout + (long long)(nz + 1) * nr, i0, nr, pc);   // upper ghost row
     }
     double tot[1];
     if (cta_publish<1>(acc, 0u, d.partials, &d.st->ticket, tot) && threadIdx.x == 0) {
-        HpState* s = d.st;
-        const double pq = tot[0];
-        s->pq = pq;
-        if (pq > 0.0 && isfinite(pq)) {
-            s->alpha = s->rz / pq;
-        } else {
-            s->alpha = 0.0;
-            s->flags |= 4;          // breakdown
-        }
-        s->parity ^= 1;
-        s->first = 0;
+        if (d.nranks > 1) stash_local<1>(d, tot);
+        else finalize_A(d, a, tot[0]);
     }
 }
 
@@ -453,7 +556,7 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::MIN_CTAS) k
 //   rz = sum r z ; rr = sum r r ; crit = max|z| (criterion 0) or max|r/diag| (criterion 1)
 // last CTA: beta = rz_new/rz, iter++, convergence flag, sweep statistics, WHILE condition
 template <int TPL, int EPT, bool VEC, bool RLINE, bool INIT>
-__global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::MIN_CTAS) k_cg_B(HpDev d, hp_phys ph, HpKArgs a) {
+__global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT)) k_cg_B(HpDev d, hp_phys ph, HpKArgs a) {
     using G = TeamGeom<TPL>;
     const HpState s0 = *d.st;
     if (!INIT && s0.done) return;
@@ -471,13 +574,35 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::MIN_CTAS) k
     double acc[3] = {0.0, 0.0, 0.0};   // rz, rr, crit(max)
     for (int g = ja + 1; g <= jb; ++g) {
         const long long rb = (long long)g * nr;
-        double rv[EPT];
+        if (VEC && tl == 0 && g < jb && (a.prefetch & 2)) {             // next row of every streamed field -> L2
+            prefetch_row_l2(d.r + rb + nr, nr);
+            prefetch_row_l2(d.dinv + rb + nr, nr);
+            if constexpr (RLINE) prefetch_row_l2(d.cR + rb + nr, nr);
+            if constexpr (!INIT) {
+                prefetch_row_l2(d.T + rb + nr, nr);
+                prefetch_row_l2(pcur + rb + nr, nr);
+                prefetch_row_l2(d.q + rb + nr, nr);
+            }
+        }
+        // ---- every load of this row is issued before the first store / use (the vector loads and stores are
+        //      volatile asm and keep program order: a load placed after a store would wait for a full extra
+        //      DRAM round trip) ----
+        double rv[EPT], dv[EPT], zv[EPT];
+        [[maybe_unused]] double xv[EPT], pv[EPT], qv[EPT], cr[EPT], dgv[EPT];
         load_row<EPT, VEC>(d.r + rb, i0, nr, rv);
         if constexpr (!INIT) {
-            double xv[EPT], pv[EPT], qv[EPT];
             load_row<EPT, VEC>(d.T + rb, i0, nr, xv);
             load_row<EPT, VEC>(pcur + rb, i0, nr, pv);
             load_row<EPT, VEC>(d.q + rb, i0, nr, qv);
+        }
+        load_row<EPT, VEC>(d.dinv + rb, i0, nr, dv);
+        if constexpr (RLINE) load_row<EPT, VEC>(d.cR + rb, i0, nr, cr);
+        if (need_diag) load_row<EPT, VEC>(d.diag + rb, i0, nr, dgv);
+        [[maybe_unused]] double m0_edge = 0.0;      // forward multiplier entering this warp from the previous one
+        if constexpr (RLINE) {
+            if (lane == 0 && tl != 0 && i0 < nr) m0_edge = d.cR[rb + i0 - 1] * d.dinv[rb + i0 - 1];
+        }
+        if constexpr (!INIT) {
 #pragma unroll
             for (int e = 0; e < EPT; ++e) {
                 xv[e] = fma(alpha, pv[e], xv[e]);
@@ -486,20 +611,16 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::MIN_CTAS) k
             store_row<EPT, VEC>(d.T + rb, i0, nr, xv);
             store_row<EPT, VEC>(d.r + rb, i0, nr, rv);
         }
-        double dv[EPT], zv[EPT];
-        load_row<EPT, VEC>(d.dinv + rb, i0, nr, dv);
         if constexpr (!RLINE) {
 #pragma unroll
             for (int e = 0; e < EPT; ++e) zv[e] = rv[e] * dv[e];
         } else {
-            double cr[EPT];
-            load_row<EPT, VEC>(d.cR + rb, i0, nr, cr);
             // ---------------- forward scan ----------------
             double nb[EPT];     // cR_i * dinv_i : backward multiplier of cell i, forward multiplier of cell i+1
 #pragma unroll
             for (int e = 0; e < EPT; ++e) nb[e] = cr[e] * dv[e];
             double m0 = __shfl_up_sync(0xffffffffu, nb[EPT - 1], 1);
-            if (lane == 0) m0 = (tl == 0 || i0 >= nr) ? 0.0 : d.cR[rb + i0 - 1] * d.dinv[rb + i0 - 1];
+            if (lane == 0) m0 = m0_edge;
             double Pe[EPT], ye[EPT];
             {
                 double P = 1.0, y = 0.0;
@@ -560,11 +681,9 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::MIN_CTAS) k
         }
         store_row<EPT, VEC>(d.z + rb, i0, nr, zv);
         if (need_diag) {
-            double dg[EPT];
-            load_row<EPT, VEC>(d.diag + rb, i0, nr, dg);
 #pragma unroll
             for (int e = 0; e < EPT; ++e)
-                if (i0 + e < nr) acc[2] = fmax(acc[2], fabs(rv[e] / dg[e]));
+                if (i0 + e < nr) acc[2] = fmax(acc[2], fabs(rv[e] / dgv[e]));
         } else {
 #pragma unroll
             for (int e = 0; e < EPT; ++e) acc[2] = fmax(acc[2], fabs(zv[e]));
@@ -577,31 +696,8 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::MIN_CTAS) k
     }
     double tot[3];
     if (cta_publish<3>(acc, 4u, d.partials, &d.st->ticket, tot) && threadIdx.x == 0) {
-        HpState* s = d.st;
-        const double rz_new = tot[0], rr = tot[1], crit = tot[2];
-        int flags = s->flags;
-        int done = 0;
-        if (INIT) {
-            s->rz = rz_new;
-            s->parity = 0;
-            s->first = 1;
-        } else {
-            s->beta = (s->rz != 0.0) ? rz_new / s->rz : 0.0;
-            s->rz = rz_new;
-            s->iter += 1;
-            s->total_iters += 1;
-        }
-        s->rr = rr; s->crit = crit;
-        const bool nan_bad = !(isfinite(rz_new) && isfinite(crit));
-        if (converged(a, crit, rr, s->b2)) { done = 1; flags |= 1; }
-        else if (nan_bad || (flags & 4)) { done = 1; flags |= 4; }
-        else if (s->iter >= a.max_iter) { done = 1; flags |= 2; }
-        s->done = done; s->flags = flags;
-        hp_sweep_stat* stt = &d.stats[(s->sweep_count - 1) % HP_STATS_CAP];
-        stt->crit = (a.criterion == 2) ? sqrt(rr) : crit;
-        stt->iters = s->iter;
-        stt->flags = flags;
-        set_cond(a, !done);
+        if (d.nranks > 1) stash_local<3>(d, tot);
+        else finalize_B(d, a, INIT, tot[0], tot[1], tot[2]);
     }
 }
 
@@ -673,8 +769,18 @@ const void* fn_B(int rline, int init) {
         else if (cfg.tpl == 32 && cfg.ept == 4) { if (cfg.vec) { EXPR_T(32, 4, true); } else { EXPR_T(32, 4, false); } }       \
         else if (cfg.tpl == 128 && cfg.ept == 4) { if (cfg.vec) { EXPR_T(128, 4, true); } else { EXPR_T(128, 4, false); } }    \
         else if (cfg.tpl == 256 && cfg.ept == 4) { if (cfg.vec) { EXPR_T(256, 4, true); } else { EXPR_T(256, 4, false); } }    \
+        else if (cfg.tpl == 128 && cfg.ept == 8) { if (cfg.vec) { EXPR_T(128, 8, true); } else { EXPR_T(128, 8, false); } }    \
+        else if (cfg.tpl == 256 && cfg.ept == 8) { if (cfg.vec) { EXPR_T(256, 8, true); } else { EXPR_T(256, 8, false); } }    \
         else if (cfg.tpl == 512 && cfg.ept == 8) { if (cfg.vec) { EXPR_T(512, 8, true); } else { EXPR_T(512, 8, false); } }    \
         else if (cfg.tpl == 1024 && cfg.ept == 8) { if (cfg.vec) { EXPR_T(1024, 8, true); } else { EXPR_T(1024, 8, false); } } \
+    } while (0)
+
+#define HP_DISPATCH_A(cfg, EXPR_T)                                                        \
+    do {                                                                                  \
+        if (cfg.tplA == 32 && cfg.eptA == 1) { EXPR_T(32, 1, false); }                    \
+        else if (cfg.tplA == 32 && cfg.eptA == 4) { if (cfg.vecA) { EXPR_T(32, 4, true); } else { EXPR_T(32, 4, false); } }    \
+        else if (cfg.tplA == 128 && cfg.eptA == 4) { if (cfg.vecA) { EXPR_T(128, 4, true); } else { EXPR_T(128, 4, false); } } \
+        else if (cfg.tplA == 256 && cfg.eptA == 4) { if (cfg.vecA) { EXPR_T(256, 4, true); } else { EXPR_T(256, 4, false); } } \
     } while (0)
 
 }  // namespace
@@ -694,10 +800,26 @@ bool pick_config(int nr, int nz, int num_sms, HpLaunchCfg* cfg, const char** err
     else if (nr <= 4096) { tpl = 512; ept = 8; }
     else if (nr <= 8192) { tpl = 1024; ept = 8; }
     else { *err = "nr > 8192 radial cells per row is not supported"; return false; }
+    // experiment hook: HP_TEAM=TPLxEPT overrides the table when the pair is instantiated and covers the row
+    if (const char* e = getenv("HP_TEAM")) {
+        int t = 0, p = 0;
+        if (sscanf(e, "%dx%d", &t, &p) == 2 && (long long)t * p >= nr &&
+            ((t == 32 && (p == 1 || p == 4)) || (t == 128 && (p == 4 || p == 8)) || (t == 256 && (p == 4 || p == 8)) ||
+             ((t == 512 || t == 1024) && p == 8))) { tpl = t; ept = p; }
+    }
     cfg->tpl = tpl; cfg->ept = ept;
     cfg->vec = (ept >= 4) && (nr % ept == 0);
     cfg->cta_threads = tpl < 256 ? 256 : tpl;
     cfg->teams_per_cta = cfg->cta_threads / tpl;
+    // k_cg_A: at most 256 threads x 4 cells per tile (three rows of the direction + five streams stay in <= 128 regs)
+    if (nr <= 32) { cfg->tplA = 32; cfg->eptA = 1; }
+    else if (nr <= 128) { cfg->tplA = 32; cfg->eptA = 4; }
+    else if (nr <= 512) { cfg->tplA = 128; cfg->eptA = 4; }
+    else { cfg->tplA = 256; cfg->eptA = 4; }
+    cfg->vecA = (cfg->eptA >= 4) && (nr % cfg->eptA == 0);
+    cfg->ctaA = 256;
+    cfg->teams_per_ctaA = 256 / cfg->tplA;
+    cfg->ncolA = (nr + cfg->tplA * cfg->eptA - 1) / (cfg->tplA * cfg->eptA);
     cfg->num_sms = num_sms; cfg->nz = nz;
     cfg->cta_cell = 256;
     long long ncell = (long long)(nz + 1) * nr;
@@ -712,13 +834,16 @@ bool pick_config(int nr, int nz, int num_sms, HpLaunchCfg* cfg, const char** err
 
 // Grid of a marching kernel: exactly one resident wave (occupancy of THIS instantiation x SM count) so that no
 // partially filled second wave appears; fewer CTAs when the mesh has too few rows (>= 2 rows per team).
-static int team_grid(const void* func, const HpLaunchCfg& c) {
+static int team_grid(const void* func, const HpLaunchCfg& c, int cta_threads, int teams_per_cta, int ncol) {
     int occ = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, c.cta_threads, 0) != cudaSuccess || occ < 1) occ = 1;
-    long long max_teams = (long long)c.num_sms * occ * c.teams_per_cta;
-    long long teams = c.nz < max_teams ? c.nz : max_teams;
-    if (teams > 1 && c.nz / teams < 2) teams = (c.nz + 1) / 2;
-    long long grid = (teams + c.teams_per_cta - 1) / c.teams_per_cta;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, cta_threads, 0) != cudaSuccess || occ < 1) occ = 1;
+    long long max_teams = (long long)c.num_sms * occ * teams_per_cta;
+    long long chunks = max_teams / ncol;                 // row chunks; each is served by ncol column-tile teams
+    if (chunks < 1) chunks = 1;
+    if (chunks > c.nz) chunks = c.nz;
+    if (chunks > 1 && c.nz / chunks < 2) chunks = (c.nz + 1) / 2;
+    long long teams = chunks * ncol;
+    long long grid = (teams + teams_per_cta - 1) / teams_per_cta;
     if (grid < 1) grid = 1;
     if (grid > HP_MAX_PARTIALS) grid = HP_MAX_PARTIALS;
     return (int)grid;
@@ -736,19 +861,20 @@ HpKernelLaunch desc_diag(const HpLaunchCfg& c, const HpDev& d) {
 HpKernelLaunch desc_factor(const HpLaunchCfg& c, const HpDev& d) {
     return {(const void*)k_factor_rline, dim3(c.grid_factor), dim3(c.cta_factor), 0};
 }
+HpKernelLaunch desc_finalize() { return {(const void*)k_finalize, dim3(1), dim3(32), 0}; }
 HpKernelLaunch desc_cg_A(const HpLaunchCfg& c, const HpDev& d) {
     const void* f = nullptr;
 #define HP_X(T, E, V) f = fn_A<T, E, V>()
-    HP_DISPATCH(c, HP_X);
+    HP_DISPATCH_A(c, HP_X);
 #undef HP_X
-    return {f, dim3(team_grid(f, c)), dim3(c.cta_threads), 0};
+    return {f, dim3(team_grid(f, c, c.ctaA, c.teams_per_ctaA, c.ncolA)), dim3(c.ctaA), 0};
 }
 static HpKernelLaunch desc_B(const HpLaunchCfg& c, int precond, int init) {
     const void* f = nullptr;
 #define HP_X(T, E, V) f = fn_B<T, E, V>(precond, init)
     HP_DISPATCH(c, HP_X);
 #undef HP_X
-    return {f, dim3(team_grid(f, c)), dim3(c.cta_threads), 0};
+    return {f, dim3(team_grid(f, c, c.cta_threads, c.teams_per_cta, 1)), dim3(c.cta_threads), 0};
 }
 HpKernelLaunch desc_cg_init(const HpLaunchCfg& c, const HpDev& d, int precond, int criterion) { return desc_B(c, precond, 1); }
 HpKernelLaunch desc_cg_B(const HpLaunchCfg& c, const HpDev& d, int precond, int criterion) { return desc_B(c, precond, 0); }
