@@ -162,7 +162,8 @@ def run_gpu(args, rank, world, local_rank):
     mesh, _ = generate_composite_mesh(mesh_params_for(nz, nr), cfg['dimensions'])
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
-        solver = make_solver_for_rank(mesh, cfg, rank, world, tol=args.tol, loop_mode=args.loop_mode)
+        loop_mode = 'host' if (world > 1 and args.comm == 'nccl') else args.loop_mode
+        solver = make_solver_for_rank(mesh, cfg, rank, world, comm=args.comm, tol=args.tol, loop_mode=loop_mode)
 
         def barrier():
             stream.synchronize()
@@ -257,9 +258,9 @@ def run_gpu(args, rank, world, local_rank):
             'scaling': 'weak' if world == 1 else 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': f'synthetic composite mesh {nz}x{nr} (axial x radial), T-dependent properties, literal mode, '
                                    f'dt={DT}s, updateOld + {SWEEPS} sweeps/step, radial-line PCG tol {args.tol:g} K',
-                       'parallelism': 'single GPU' if world == 1 else f'axial slabs x{world} (NCCL halo + scalar all-gather)',
+                       'parallelism': 'single GPU' if world == 1 else (f'axial slabs x{world}, ' + ('NVLink peer-memory halo rows + CG scalars fused into the PCG kernels, one CUDA graph per step' if args.comm == 'p2p' else 'NCCL send/recv halo + all-gathered CG scalars, host-driven loop')),
                        'l2': 'working set (11 fp64 fields) exceeds the 126 MB L2; no flush needed',
-                       'pcg_iterations_per_step': iters / args.steps, 'loop_mode': args.loop_mode},
+                       'pcg_iterations_per_step': iters / args.steps, 'loop_mode': loop_mode},
             'e2e': {'value': e2e_value, 'unit': 'cell-timesteps/s', 'h2d_bytes_per_step': 8 * n_cells,
                     'd2h_bytes_per_step': 8 * n_cells, 'ms_per_step': e2e_ms / args.steps},
             'gpu_launches': int(launches), 'clocks': clk,
@@ -282,6 +283,7 @@ def main():
     ap.add_argument('--tol', type=float, default=1e-9)
     ap.add_argument('--loop-mode', default='graph', choices=['graph', 'host'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--comm', default='p2p', choices=['p2p', 'nccl'], help='slab exchange: NVLink peer stores fused into the kernels, or NCCL calls')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

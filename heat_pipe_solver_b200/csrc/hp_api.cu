@@ -70,6 +70,7 @@ struct GraphEntry {
     double dt; int sweeps; int has_old; int update_old; hp_solve_opts opts;
     cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
     int static_nodes = 0;
+    int body_nodes = 2;
 };
 
 struct hp_solver_s {
@@ -87,10 +88,16 @@ struct hp_solver_s {
     long long launches_host = 0;    // kernels launched by the host + static graph nodes per graph launch
     long long stream_mode_iters = 0;
     long long sweeps_host = 0;
+    int graph_body_nodes = 2;
     std::vector<GraphEntry> graphs;
     // slabs
     int rank = 0, nranks = 1;
-    ncclComm_t comm = nullptr;
+    ncclComm_t nccl = nullptr;
+    // peer-memory exchange (hp_peer_export / hp_peer_import)
+    HpComm* comm = nullptr;          // my mailbox
+    double* qz_block = nullptr;      // base of the (q, z) allocation (IPC handle is per allocation)
+    std::vector<void*> ipc_opened;
+    bool ghost_dirty = true;         // ghost rows of T must be refreshed by an explicit exchange before the next sweep
     // L2 access-policy window over the contiguous (q, z) block
     bool l2_on = false;
     void* l2_base = nullptr;
@@ -123,16 +130,23 @@ static int upload(hp_solver_s* h, const T** dst, const std::vector<T>& v) {
 static void setup_l2_window(hp_solver_s* h, const cudaDeviceProp& prop) {
     h->l2_on = false;
     const char* env = getenv("HP_L2_PERSIST");
-    if (env && env[0] == '0') return;
+    const int mode = env ? atoi(env) : 1;
+    if (mode == 0) return;
     if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
-    size_t want = h->l2_bytes;
-    size_t win = want < (size_t)prop.accessPolicyMaxWindowSize ? want : (size_t)prop.accessPolicyMaxWindowSize;
-    size_t carve = win < (size_t)prop.persistingL2CacheMaxSize ? win : (size_t)prop.persistingL2CacheMaxSize;
-    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
+    // Only when the whole window fits the persisting carve-out: a partially persisting window (hitRatio < 1) over
+    // vectors larger than L2 halves the streaming rate of both PCG kernels (measured on 16384x4096, profiles/).
+    size_t win = h->l2_bytes;                                   // q and z
+    const size_t cap = (size_t)prop.persistingL2CacheMaxSize < (size_t)prop.accessPolicyMaxWindowSize
+                           ? (size_t)prop.persistingL2CacheMaxSize : (size_t)prop.accessPolicyMaxWindowSize;
+    if (win > cap) {
+        if (mode == 2 && win / 2 <= cap) win = win / 2;        // experiment: q alone
+        else return;
+    }
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, win) != cudaSuccess) { cudaGetLastError(); return; }
     memset(&h->l2_window, 0, sizeof(h->l2_window));
     h->l2_window.base_ptr = h->l2_base;
     h->l2_window.num_bytes = win;
-    h->l2_window.hitRatio = (float)((double)carve / (double)win);
+    h->l2_window.hitRatio = 1.0f;
     h->l2_window.hitProp = cudaAccessPropertyPersisting;
     h->l2_window.missProp = cudaAccessPropertyStreaming;
     h->l2_on = true;
@@ -200,7 +214,9 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
         if (!(m->z_v[g + 1] > m->z_v[g])) { delete h; return fail("hp_create: z_v must be strictly increasing"); }
 
     HpDev& d = h->d;
-    d.nr = nr; d.nz = nz; d.ncolA = h->cfg.ncolA; d.nranks = 1; d.rank = 0; d.red_local = nullptr; d.red_all = nullptr;
+    d.nr = nr; d.nz = nz; d.ncolA = h->cfg.ncolA; d.p2p = 0; d.seq = nullptr; d.z_lo = d.z_hi = d.T_lo = d.T_hi = nullptr;
+    for (int r = 0; r < HP_MAX_RANKS; ++r) d.comm_peer[r] = nullptr;
+    d.nranks = 1; d.rank = 0; d.red_local = nullptr; d.red_all = nullptr;
     std::vector<double> r_v(m->r_v, m->r_v + nr + 1), r_c(nr), dr(nr), ar(nr, 0.0), dcr(nr, 1.0);
     for (int i = 0; i < nr; ++i) { r_c[i] = 0.5 * (r_v[i] + r_v[i + 1]); dr[i] = r_v[i + 1] - r_v[i]; }
     for (int i = 0; i + 1 < nr; ++i) { dcr[i] = r_c[i + 1] - r_c[i]; ar[i] = (r_v[i + 1] - r_c[i]) / dcr[i]; }
@@ -238,6 +254,7 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
         if (dev_alloc(h, (void**)&qz, 2 * h->field_elems * sizeof(double))) { hp_destroy(h); return -1; }
         CK(cudaMemsetAsync(qz, 0, 2 * h->field_elems * sizeof(double), h->stream));
         d.q = qz; d.z = qz + h->field_elems;
+        h->qz_block = qz;
         h->l2_base = qz; h->l2_bytes = 2 * h->field_elems * sizeof(double);
     }
     setup_l2_window(h, prop);
@@ -284,7 +301,8 @@ int hp_destroy(hp_handle h) {
     if (!h) return 0;
     cudaStreamSynchronize(h->stream);
     destroy_graphs(h);
-    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    if (h->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_state) cudaFreeHost(h->h_state);
@@ -317,6 +335,7 @@ static size_t owned_bytes(hp_handle h) { return (size_t)h->d.nz * h->d.nr * size
 int hp_set_T_dev(hp_handle h, const double* d_T) {
     if (!h || !d_T) return fail("hp_set_T_dev: null argument");
     CK(cudaMemcpyAsync(h->d.T + h->d.nr, d_T, owned_bytes(h), cudaMemcpyDeviceToDevice, h->stream));
+    h->ghost_dirty = true;
     return 0;
 }
 int hp_get_T_dev(hp_handle h, double* d_T) {
@@ -327,6 +346,7 @@ int hp_get_T_dev(hp_handle h, double* d_T) {
 int hp_set_T_host(hp_handle h, const double* h_T) {
     if (!h || !h_T) return fail("hp_set_T_host: null argument");
     CK(cudaMemcpyAsync(h->d.T + h->d.nr, h_T, owned_bytes(h), cudaMemcpyHostToDevice, h->stream));
+    h->ghost_dirty = true;
     return 0;
 }
 int hp_get_T_host(hp_handle h, double* h_T) {
@@ -349,12 +369,12 @@ static int exchange_rows(hp_solver_s* h, double* field) {
     const int nr = h->d.nr, nz = h->d.nz;
     NK(g_nccl.GroupStart());
     if (h->rank > 0) {
-        NK(g_nccl.Send(field + (size_t)1 * nr, nr, ncclFloat64, h->rank - 1, h->comm, h->stream));
-        NK(g_nccl.Recv(field, nr, ncclFloat64, h->rank - 1, h->comm, h->stream));
+        NK(g_nccl.Send(field + (size_t)1 * nr, nr, ncclFloat64, h->rank - 1, h->nccl, h->stream));
+        NK(g_nccl.Recv(field, nr, ncclFloat64, h->rank - 1, h->nccl, h->stream));
     }
     if (h->rank < h->nranks - 1) {
-        NK(g_nccl.Send(field + (size_t)nz * nr, nr, ncclFloat64, h->rank + 1, h->comm, h->stream));
-        NK(g_nccl.Recv(field + (size_t)(nz + 1) * nr, nr, ncclFloat64, h->rank + 1, h->comm, h->stream));
+        NK(g_nccl.Send(field + (size_t)nz * nr, nr, ncclFloat64, h->rank + 1, h->nccl, h->stream));
+        NK(g_nccl.Recv(field + (size_t)(nz + 1) * nr, nr, ncclFloat64, h->rank + 1, h->nccl, h->stream));
     }
     NK(g_nccl.GroupEnd());
     return 0;
@@ -363,7 +383,11 @@ static int exchange_rows(hp_solver_s* h, double* field) {
 // all ranks' per-kernel sums -> every rank, then one thread advances the scalar recurrences identically everywhere
 static int combine(hp_solver_s* h, HpKArgs& a, int kind) {
     if (h->nranks == 1) return 0;
-    NK(g_nccl.AllGather(h->d.red_local, h->d.red_all, HP_NRED, ncclFloat64, h->comm, h->stream));
+    if (h->d.p2p) {                  // sums already travelled by peer stores of the producing kernel
+        void* p4[] = {&h->d, &h->phys, &a, &kind};
+        return launch(h, hpk::desc_wait(), p4, KIND_OTHER);
+    }
+    NK(g_nccl.AllGather(h->d.red_local, h->d.red_all, HP_NRED, ncclFloat64, h->nccl, h->stream));
     void* p4[] = {&h->d, &h->phys, &a, &kind};
     return launch(h, hpk::desc_finalize(), p4, KIND_OTHER);
 }
@@ -377,7 +401,7 @@ static int sweep_stream(hp_solver_s* h, double dt, int has_old, bool refactor) {
     a.rhs_out = h->rhs_dbg;
     void* params[] = {&d, &h->phys, &a};
     if (apply_l2_to_stream(h)) return -1;
-    if (exchange_rows(h, d.T)) return -1;
+    if (!d.p2p || h->ghost_dirty) { if (exchange_rows(h, d.T)) return -1; h->ghost_dirty = false; }
     if (h->phys.gamma == 1) {
         if (launch(h, hpk::desc_coef(h->cfg, d), params, KIND_COEF)) return -1;
     }
@@ -401,7 +425,7 @@ static int sweep_stream(hp_solver_s* h, double dt, int has_old, bool refactor) {
         if (h->h_state->done) break;
         if (launched >= h->opts.max_iter + h->opts.poll_chunk) return fail("sweep_stream: PCG loop did not terminate");
         for (int k = 0; k < h->opts.poll_chunk; ++k) {
-            if (exchange_rows(h, d.z)) return -1;
+            if (!d.p2p && exchange_rows(h, d.z)) return -1;      // p2p: k_cg_B stored the rows into the ghosts itself
             if (launch(h, kA, params, KIND_A)) return -1;
             if (combine(h, a, 1)) return -1;
             if (launch(h, kB, params, KIND_B)) return -1;
@@ -464,12 +488,17 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
         int write_dinv = (h->opts.precond == 0) ? 1 : 0;
         void* p4[] = {&d, &h->phys, &a, &write_dinv};
         if (chain_kernel(c, hpk::desc_diag(h->cfg, d), p4)) return -1;
+        int kd = 0, ka = 1, kb = 2, ki = 3;          // FIN_* kinds of k_wait
+        void* pwd[] = {&d, &h->phys, &a, &kd};
+        if (h->nranks > 1 && chain_kernel(c, hpk::desc_wait(), pwd)) return -1;
         if (h->opts.precond == 1 && (s % h->opts.refactor_every) == 0)
             if (chain_kernel(c, hpk::desc_factor(h->cfg, d), params)) return -1;
         cudaGraphConditionalHandle cond;
         CK(cudaGraphConditionalHandleCreate(&cond, e.graph, 0, cudaGraphCondAssignDefault));
         a.use_cond = 1; a.cond = (unsigned long long)cond;
         if (chain_kernel(c, hpk::desc_cg_init(h->cfg, d, h->opts.precond, h->opts.criterion), params, h)) return -1;
+        void* pwi[] = {&d, &h->phys, &a, &ki};
+        if (h->nranks > 1 && chain_kernel(c, hpk::desc_wait(), pwi)) return -1;
         cudaGraphNodeParams cp{};
         cp.type = cudaGraphNodeTypeConditional;
         cp.conditional.handle = cond;
@@ -479,8 +508,13 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
         CK(cudaGraphAddNode(&wn, e.graph, c.last ? &c.last : nullptr, c.last ? 1 : 0, &cp));
         c.last = wn;
         NodeChain body{cp.conditional.phGraph_out[0]};
+        void* pwa[] = {&d, &h->phys, &a, &ka};
+        void* pwb[] = {&d, &h->phys, &a, &kb};
         if (chain_kernel(body, hpk::desc_cg_A(h->cfg, d), params, h)) return -1;
+        if (h->nranks > 1 && chain_kernel(body, hpk::desc_wait(), pwa)) return -1;
         if (chain_kernel(body, hpk::desc_cg_B(h->cfg, d, h->opts.precond, h->opts.criterion), params, h)) return -1;
+        if (h->nranks > 1 && chain_kernel(body, hpk::desc_wait(), pwb)) return -1;
+        e.body_nodes = body.count;
     }
     e.static_nodes = c.count;
     CK(cudaGraphInstantiate(&e.exec, e.graph, 0));
@@ -492,12 +526,14 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
 static int run_steps(hp_solver_s* h, double dt, int n_steps, int sweeps, int has_old, int update_old) {
     if (!(dt > 0.0)) return fail("dt must be > 0");
     if (sweeps < 1) return fail("sweeps must be >= 1");
-    if (h->opts.loop_mode == 1 && h->nranks == 1 && !h->rhs_dbg && !h->prof_on) {
+    if (h->opts.loop_mode == 1 && (h->nranks == 1 || h->d.p2p) && !h->rhs_dbg && !h->prof_on) {
+        if (h->nranks > 1 && h->ghost_dirty) { if (exchange_rows(h, h->d.T)) return -1; h->ghost_dirty = false; }
         GraphEntry* g = nullptr;
         if (get_graph(h, dt, sweeps, has_old, update_old, &g)) return -1;
         for (int s = 0; s < n_steps; ++s) {
             CK(cudaGraphLaunch(g->exec, h->stream));
             h->launches_host += g->static_nodes;
+            h->graph_body_nodes = g->body_nodes;
             h->sweeps_host += sweeps;
         }
         return 0;
@@ -569,7 +605,7 @@ int64_t hp_total_iters(hp_handle h) {
 int64_t hp_kernel_launches(hp_handle h) {
     if (!h || fetch_state(h)) return -1;
     long long graph_iters = h->h_state->total_iters - h->stream_mode_iters;
-    return h->launches_host + 2 * graph_iters;
+    return h->launches_host + (long long)h->graph_body_nodes * graph_iters;
 }
 
 int hp_assemble_debug(hp_handle h, double dt, int has_old, double* d_cR, double* d_cZ, double* d_diag, double* d_rhs) {
@@ -621,6 +657,71 @@ int hp_eval_cell_fields(hp_handle h, double* d_rho, double* d_cp, double* d_kavg
     return 0;
 }
 
+// ---- peer memory over NVLink: every rank maps every other rank's mailbox, and its neighbours' z / T arrays -------
+int hp_peer_export(hp_handle h, void* out192) {
+    if (!h || !out192) return fail("hp_peer_export: null argument");
+    if (!h->comm) {
+        if (dev_alloc(h, (void**)&h->comm, sizeof(HpComm))) return -1;
+        CK(cudaMemset(h->comm, 0, sizeof(HpComm)));
+        if (dev_alloc(h, (void**)&h->d.seq, sizeof(unsigned long long) * HP_COMM_KINDS)) return -1;
+        CK(cudaMemset(h->d.seq, 0, sizeof(unsigned long long) * HP_COMM_KINDS));
+    }
+    cudaIpcMemHandle_t hd[3];
+    CK(cudaIpcGetMemHandle(&hd[0], h->comm));
+    CK(cudaIpcGetMemHandle(&hd[1], h->qz_block));
+    CK(cudaIpcGetMemHandle(&hd[2], h->d.T));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(out192, hd, sizeof(hd));
+    return 0;
+}
+
+int hp_peer_import(hp_handle h, const void* all_handles, const int32_t* nz_of_rank) {
+    if (!h || !all_handles || !nz_of_rank) return fail("hp_peer_import: null argument");
+    if (h->nranks < 2) return fail("hp_peer_import: call hp_comm_init first");
+    if (h->nranks > HP_MAX_RANKS) return fail("hp_peer_import: too many ranks");
+    if (!h->comm) return fail("hp_peer_import: call hp_peer_export first");
+    CK(cudaStreamSynchronize(h->stream));
+    const cudaIpcMemHandle_t* hd = (const cudaIpcMemHandle_t*)all_handles;
+    HpDev& d = h->d;
+    const size_t nr = d.nr;
+    for (int r = 0; r < h->nranks; ++r) {
+        if (r == h->rank) { d.comm_peer[r] = h->comm; continue; }
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, hd[3 * r + 0], cudaIpcMemLazyEnablePeerAccess));
+        h->ipc_opened.push_back(p);
+        d.comm_peer[r] = (HpComm*)p;
+    }
+    d.z_lo = d.z_hi = d.T_lo = d.T_hi = nullptr;
+    auto open_nb = [&](int r, double** qz, double** T) -> int {
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, hd[3 * r + 1], cudaIpcMemLazyEnablePeerAccess));
+        h->ipc_opened.push_back(p); *qz = (double*)p;
+        CK(cudaIpcOpenMemHandle(&p, hd[3 * r + 2], cudaIpcMemLazyEnablePeerAccess));
+        h->ipc_opened.push_back(p); *T = (double*)p;
+        return 0;
+    };
+    if (h->rank > 0) {                       // lower neighbour: its UPPER ghost row (nz_lo + 1) mirrors my row 1
+        const int r = h->rank - 1;
+        double *qz, *T;
+        if (open_nb(r, &qz, &T)) return -1;
+        const size_t felems = (size_t)(nz_of_rank[r] + 2) * nr + 64;
+        d.z_lo = qz + felems + (size_t)(nz_of_rank[r] + 1) * nr;
+        d.T_lo = T + (size_t)(nz_of_rank[r] + 1) * nr;
+    }
+    if (h->rank < h->nranks - 1) {           // upper neighbour: its LOWER ghost row (0) mirrors my row nz
+        const int r = h->rank + 1;
+        double *qz, *T;
+        if (open_nb(r, &qz, &T)) return -1;
+        const size_t felems = (size_t)(nz_of_rank[r] + 2) * nr + 64;
+        d.z_hi = qz + felems;
+        d.T_hi = T;
+    }
+    d.p2p = 1;
+    h->ghost_dirty = true;
+    destroy_graphs(h);
+    return 0;
+}
+
 int hp_profile_begin(hp_handle h, int max_launches) {
     if (!h) return fail("null handle");
     if (max_launches < 1) max_launches = 1;
@@ -665,7 +766,7 @@ int hp_comm_init(hp_handle h, int rank, int nranks, const void* id128) {
     if (!load_nccl()) return fail("hp_comm_init: libnccl.so.2 not found");
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
-    NK(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+    NK(g_nccl.CommInitRank(&h->nccl, nranks, id, rank));
     h->rank = rank; h->nranks = nranks;
     if (dev_alloc(h, (void**)&h->d.red_local, sizeof(double) * HP_NRED)) return -1;
     if (dev_alloc(h, (void**)&h->d.red_all, sizeof(double) * HP_NRED * nranks)) return -1;

@@ -8,6 +8,16 @@
 #define HP_MAX_PARTIALS 4096     // max CTAs of any reducing kernel
 #define HP_NRED 4                // reduced values per kernel
 
+#define HP_MAX_RANKS 16
+enum { HP_COMM_DIAG = 0, HP_COMM_A = 1, HP_COMM_B = 2, HP_COMM_KINDS = 3 };
+
+// Peer-memory mailbox of one rank (cudaMalloc'ed, IPC-mapped into every peer of the box over NVLink).
+// red[kind][src] / flag[kind][src] are WRITTEN BY rank `src` (remote stores from its reducing kernel) and read locally.
+struct HpComm {
+    double red[HP_COMM_KINDS][HP_MAX_RANKS][HP_NRED];
+    unsigned long long flag[HP_COMM_KINDS][HP_MAX_RANKS];
+};
+
 // Device-resident scalar state of the running solve (one per handle).
 struct HpState {
     double alpha, beta, rz, pq, crit, rr, res2, b2;
@@ -51,6 +61,12 @@ struct HpDev {
     // axial slabs (nranks > 1): per-rank sums and their all-gathered copies
     int nranks, rank;
     int ncolA;               // column tiles of k_cg_A
+    // peer-memory (NVLink) exchange fused into the kernels (p2p != 0): no NCCL call inside a sweep
+    int p2p;
+    HpComm* comm_peer[HP_MAX_RANKS];   // every rank's mailbox (own one included) as seen from this GPU
+    unsigned long long* seq;           // [HP_COMM_KINDS] how many times this rank has produced each kind
+    double *z_lo, *z_hi;               // neighbour's z ghost row that mirrors my first / last owned row (or null)
+    double *T_lo, *T_hi;               // same for the field T
     double* red_local;       // [HP_NRED]
     double* red_all;         // [nranks * HP_NRED]
 };
@@ -98,6 +114,7 @@ HpKernelLaunch desc_diag(const HpLaunchCfg&, const HpDev&);
 HpKernelLaunch desc_factor(const HpLaunchCfg&, const HpDev&);
 HpKernelLaunch desc_cg_init(const HpLaunchCfg&, const HpDev&, int precond, int criterion);
 HpKernelLaunch desc_cg_A(const HpLaunchCfg&, const HpDev&);
+HpKernelLaunch desc_wait();       // args: (HpDev, hp_phys, HpKArgs, int kind): peer-memory variant of finalize
 HpKernelLaunch desc_finalize();   // args: (HpDev, hp_phys, HpKArgs, int kind) kind: 0 diag, 1 A, 2 B, 3 init
 HpKernelLaunch desc_cg_B(const HpLaunchCfg&, const HpDev&, int precond, int criterion);
 

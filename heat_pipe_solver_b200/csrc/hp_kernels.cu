@@ -84,7 +84,7 @@ __device__ __forceinline__ double warp_max(double v) {
 // thread of the last CTA; tot[] is valid on thread 0 of it.  All threads of the CTA must call.
 template <int NV>
 __device__ bool cta_publish(double (&v)[NV], unsigned max_mask, double* __restrict__ partials, unsigned int* ticket,
-                            double (&tot)[NV]) {
+                            double (&tot)[NV], bool sys_scope = false) {
     __shared__ double s_red[NV][32];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
@@ -103,7 +103,8 @@ __device__ bool cta_publish(double (&v)[NV], unsigned max_mask, double* __restri
             if (lane == 0) partials[k * HP_MAX_PARTIALS + blockIdx.x] = w;
         }
         if (lane == 0) {
-            __threadfence();
+            if (sys_scope) __threadfence_system();      // remote (peer) stores of this CTA before the ticket
+            else __threadfence();
             unsigned t = atomicAdd(ticket, 1u);
             s_last = (t == gridDim.x - 1);
         }
@@ -152,7 +153,7 @@ __device__ __forceinline__ void finalize_diag(const HpDev& d, const HpKArgs& a, 
     HpState* s = d.st;
     s->res2 = res2;
     s->b2 = b2;
-    s->iter = 0; s->done = 0; s->first = 1; s->flags = 0;
+    s->iter = 0; s->done = 0; s->first = 1; s->flags &= 8;      // bit3 (a peer never arrived) is sticky
     hp_sweep_stat* stt = &d.stats[s->sweep_count % HP_STATS_CAP];
     stt->residual_l2 = sqrt(res2);
     stt->rhs_l2 = sqrt(b2);
@@ -202,9 +203,75 @@ __device__ __forceinline__ void finalize_B(const HpDev& d, const HpKArgs& a, boo
 
 // slabs: this rank's sums go to red_local; k_finalize combines all ranks' after the all-gather
 template <int NV>
-__device__ __forceinline__ void stash_local(const HpDev& d, const double (&tot)[NV]) {
+__device__ __forceinline__ void stash_local(const HpDev& d, const double (&tot)[NV], int kind) {
+    if (!d.p2p) {
 #pragma unroll
-    for (int k = 0; k < NV; ++k) d.red_local[k] = tot[k];
+        for (int k = 0; k < NV; ++k) d.red_local[k] = tot[k];
+        return;
+    }
+    // peer-memory path: my sums into slot [kind][me] of EVERY rank's mailbox, then the sequence flag (release, system
+    // scope).  The boundary rows other CTAs of this kernel stored into the neighbours' ghost rows are ordered before
+    // the flag through their system fence + ticket (cta_publish) and this fence.
+    const unsigned long long sq = d.seq[kind] + 1ull;
+    d.seq[kind] = sq;
+    for (int r = 0; r < d.nranks; ++r) {
+        HpComm* c = d.comm_peer[r];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) c->red[kind][d.rank][k] = tot[k];
+    }
+    __threadfence_system();
+    for (int r = 0; r < d.nranks; ++r) {
+        unsigned long long* f = &d.comm_peer[r]->flag[kind][d.rank];
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(sq) : "memory");
+    }
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// k_wait: one warp; lane r waits until rank r's flag of `kind` reaches this rank's own production count (all ranks run
+// the same kernel sequence), then lane 0 combines the sums in rank order and advances the scalar recurrences.
+// A bounded wait (2 s): on timeout the sweep is aborted with flags bit3 instead of hanging the GPU.
+__global__ void k_wait(HpDev d, hp_phys ph, HpKArgs a, int fin_kind) {
+    const int kind = (fin_kind == FIN_DIAG) ? HP_COMM_DIAG : (fin_kind == FIN_A ? HP_COMM_A : HP_COMM_B);
+    HpState* s = d.st;
+    if ((fin_kind == FIN_A || fin_kind == FIN_B) && s->done) return;
+    const int lane = threadIdx.x;
+    const HpComm* mine = d.comm_peer[d.rank];
+    const unsigned long long want = d.seq[kind];
+    bool ok = true;
+    if (lane < d.nranks && !(s->flags & 8)) {
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(&mine->flag[kind][lane]) < want) {
+            if (global_ns() - t0 > 2000000000ull) { ok = false; break; }
+            __nanosleep(64);
+        }
+    }
+    const unsigned bad = __ballot_sync(0xffffffffu, !ok);
+    if (lane != 0) return;
+    double v[HP_NRED] = {0.0, 0.0, 0.0, 0.0};
+    for (int r = 0; r < d.nranks; ++r) {
+        const volatile double* p = mine->red[kind][r];
+        if (fin_kind == FIN_DIAG) { v[0] += p[0]; v[1] += p[1]; }
+        else if (fin_kind == FIN_A) { v[0] += p[0]; }
+        else { v[0] += p[0]; v[1] += p[1]; v[2] = fmax(v[2], p[2]); }
+    }
+    if (fin_kind == FIN_DIAG) finalize_diag(d, a, v[0], v[1]);
+    else if (fin_kind == FIN_A) finalize_A(d, a, v[0]);
+    else finalize_B(d, a, fin_kind == FIN_INIT, v[0], v[1], v[2]);
+    if (bad || (s->flags & 8)) {          // a peer never arrived: stop this sweep, make the failure sticky
+        s->flags |= 8; s->done = 1;
+        d.stats[(s->sweep_count - 1) % HP_STATS_CAP].flags |= 8;
+        set_cond(a, 0);
+    }
 }
 
 __global__ void k_finalize(HpDev d, hp_phys ph, HpKArgs a, int kind) {
@@ -347,8 +414,8 @@ __global__ void __launch_bounds__(256) k_diag(HpDev d, hp_phys ph, HpKArgs a, in
         acc[1] += rhs * rhs;
     }
     double tot[2];
-    if (cta_publish<2>(acc, 0u, d.partials, &d.st->ticket, tot) && threadIdx.x == 0) {
-        if (d.nranks > 1) stash_local<2>(d, tot);
+    if (cta_publish<2>(acc, 0u, d.partials, &d.st->ticket, tot, d.p2p != 0) && threadIdx.x == 0) {
+        if (d.nranks > 1) stash_local<2>(d, tot, HP_COMM_DIAG);
         else finalize_diag(d, a, tot[0], tot[1]);
     }
 }
@@ -414,7 +481,6 @@ __global__ void __launch_bounds__(32) k_factor_rline(HpDev d, hp_phys ph, HpKArg
 template <int TPL>
 struct TeamGeom {
     static constexpr int CTA = (TPL < 256) ? 256 : TPL;
-    static constexpr int MIN_CTAS = (TPL <= 256) ? 3 : 1;   // register budget: 3 x 256 threads x <= 85 regs
     // resident CTAs the register budget is tuned for: kernel A keeps three rows of the direction in registers
     // (2 CTAs of 256 threads, <= 128 regs); EPT = 8 doubles the per-thread state of both kernels
     static constexpr int minb_A(int ept) { return TPL <= 256 ? 2 : 1; }
@@ -542,8 +608,8 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, MINB) k_cg_A(HpDev d, hp_p
         if (jb == nz) store_row<EPT, VEC>(pout + (long long)(nz + 1) * nr, i0, nr, pc);   // upper ghost row
     }
     double tot[1];
-    if (cta_publish<1>(acc, 0u, d.partials, &d.st->ticket, tot) && threadIdx.x == 0) {
-        if (d.nranks > 1) stash_local<1>(d, tot);
+    if (cta_publish<1>(acc, 0u, d.partials, &d.st->ticket, tot, d.p2p != 0) && threadIdx.x == 0) {
+        if (d.nranks > 1) stash_local<1>(d, tot, HP_COMM_A);
         else finalize_A(d, a, tot[0]);
     }
 }
@@ -610,6 +676,10 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT)
             }
             store_row<EPT, VEC>(d.T + rb, i0, nr, xv);
             store_row<EPT, VEC>(d.r + rb, i0, nr, rv);
+            if (d.p2p) {        // my boundary rows of the iterate -> the neighbours' ghost rows (NVLink stores)
+                if (g == 1 && d.T_lo) store_row<EPT, VEC>(d.T_lo, i0, nr, xv);
+                if (g == nz && d.T_hi) store_row<EPT, VEC>(d.T_hi, i0, nr, xv);
+            }
         }
         if constexpr (!RLINE) {
 #pragma unroll
@@ -680,6 +750,10 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT)
             for (int e = 0; e < EPT; ++e) zv[e] = fma(Pe[e], zafter, zv[e]);
         }
         store_row<EPT, VEC>(d.z + rb, i0, nr, zv);
+        if (d.p2p) {            // halo of the preconditioned residual, fused into its producer
+            if (g == 1 && d.z_lo) store_row<EPT, VEC>(d.z_lo, i0, nr, zv);
+            if (g == nz && d.z_hi) store_row<EPT, VEC>(d.z_hi, i0, nr, zv);
+        }
         if (need_diag) {
 #pragma unroll
             for (int e = 0; e < EPT; ++e)
@@ -695,8 +769,8 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT)
         }
     }
     double tot[3];
-    if (cta_publish<3>(acc, 4u, d.partials, &d.st->ticket, tot) && threadIdx.x == 0) {
-        if (d.nranks > 1) stash_local<3>(d, tot);
+    if (cta_publish<3>(acc, 4u, d.partials, &d.st->ticket, tot, d.p2p != 0) && threadIdx.x == 0) {
+        if (d.nranks > 1) stash_local<3>(d, tot, HP_COMM_B);
         else finalize_B(d, a, INIT, tot[0], tot[1], tot[2]);
     }
 }
@@ -862,6 +936,7 @@ HpKernelLaunch desc_factor(const HpLaunchCfg& c, const HpDev& d) {
     return {(const void*)k_factor_rline, dim3(c.grid_factor), dim3(c.cta_factor), 0};
 }
 HpKernelLaunch desc_finalize() { return {(const void*)k_finalize, dim3(1), dim3(32), 0}; }
+HpKernelLaunch desc_wait() { return {(const void*)k_wait, dim3(1), dim3(32), 0}; }
 HpKernelLaunch desc_cg_A(const HpLaunchCfg& c, const HpDev& d) {
     const void* f = nullptr;
 #define HP_X(T, E, V) f = fn_A<T, E, V>()

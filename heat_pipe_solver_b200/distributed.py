@@ -46,8 +46,13 @@ def gather_field(local, group=None):
     return torch.cat([p[:n] for p, n in zip(parts, rows)], dim=0)
 
 
-def make_solver_for_rank(mesh, cfg, rank, world, **solver_kw):
-    """ConductionSolver for this rank's slab of `mesh` (the whole mesh when world == 1)."""
+def make_solver_for_rank(mesh, cfg, rank, world, comm='p2p', **solver_kw):
+    """ConductionSolver for this rank's slab of `mesh` (the whole mesh when world == 1).
+
+    comm = 'nccl': ghost rows by ncclSend/Recv and CG scalars by ncclAllGather between the kernels (host-driven loop).
+    comm = 'p2p' : the same exchange as NVLink peer-memory stores fused into the PCG kernels (CUDA-IPC mapped
+                   buffers); the time step is one CUDA graph per rank.  NCCL is then only used for the first ghost
+                   refresh after a field upload."""
     from .solver import ConductionSolver
     if world == 1:
         return ConductionSolver(mesh, cfg['dimensions'], cfg['parameters'], cfg['constants'], **solver_kw)
@@ -65,4 +70,14 @@ def make_solver_for_rank(mesh, cfg, rank, world, **solver_kw):
     ident = ident.cuda()
     dist.broadcast(ident, src=0)
     solver.init_comm(rank, world, bytes(ident.cpu().numpy().tobytes()))
+    if comm == 'p2p':
+        mine = torch.frombuffer(bytearray(solver.peer_export()), dtype=torch.uint8).cuda()
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        handles = b''.join(bytes(g.cpu().numpy().tobytes()) for g in gathered)
+        nzs = [slab_rows(mesh.nz, r, world) for r in range(world)]
+        solver.init_peer(handles, [b - a for a, b in nzs])
+        dist.barrier()
+    elif comm != 'nccl':
+        raise ValueError("comm must be 'p2p' or 'nccl'")
     return solver

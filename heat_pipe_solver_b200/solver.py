@@ -239,7 +239,8 @@ class ConductionSolver:
         if got < 0:
             _lib.check(got, 'hp_get_stats')
         return [dict(residual_l2=a.residual_l2, rhs_l2=a.rhs_l2, crit=a.crit, iters=a.iters,
-                     converged=bool(a.flags & 1), hit_max_iter=bool(a.flags & 2), breakdown=bool(a.flags & 4))
+                     converged=bool(a.flags & 1), hit_max_iter=bool(a.flags & 2), breakdown=bool(a.flags & 4),
+                     peer_timeout=bool(a.flags & 8))
                 for a in arr[:got]]
 
     @property
@@ -259,6 +260,21 @@ class ConductionSolver:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         _lib.check(self.lib.hp_comm_init(self._h, int(rank), int(world), buf), 'hp_comm_init')
         self.rank, self.world = rank, world
+
+    def peer_export(self) -> bytes:
+        """192 bytes of CUDA-IPC handles (mailbox, (q,z) block, T) for `init_peer` on the other ranks."""
+        buf = (C.c_uint8 * 192)()
+        _lib.check(self.lib.hp_peer_export(self._h, buf), 'hp_peer_export')
+        return bytes(buf)
+
+    def init_peer(self, all_handles: bytes, nz_of_rank):
+        """Switch the slab exchange from NCCL calls to peer-memory stores fused into the kernels."""
+        n = len(nz_of_rank)
+        if len(all_handles) != 192 * n:
+            raise ValueError("need 192 bytes of handles per rank")
+        buf = (C.c_uint8 * len(all_handles)).from_buffer_copy(all_handles)
+        nzs = (C.c_int32 * n)(*[int(v) for v in nz_of_rank])
+        _lib.check(self.lib.hp_peer_import(self._h, buf, nzs), 'hp_peer_import')
 
     def profile_begin(self, max_launches=8192):
         """Start per-kernel CUDA-event timing; sweeps run in stream-launch mode until profile_end()."""

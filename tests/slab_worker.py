@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main(rank, world, port, shape, n_steps, sweeps, out_path):
+def main(rank, world, port, shape, n_steps, sweeps, out_path, comm='nccl', loop_mode='host'):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -20,7 +20,7 @@ def main(rank, world, port, shape, n_steps, sweeps, out_path):
     from oracle import fv_oracle as fo
     cfg = params.load_config()
     mesh, _ = generate_composite_mesh(fo.synthetic_mesh_params(*shape), cfg['dimensions'])
-    solver = make_solver_for_rank(mesh, cfg, rank, world, loop_mode='host', poll_chunk=4)
+    solver = make_solver_for_rank(mesh, cfg, rank, world, comm=comm, loop_mode=loop_mode, poll_chunk=4)
     j0, j1 = solver.layout.j0, solver.layout.j1
     z = mesh.z_c[:, None] / mesh.z_v[-1]
     T0 = 290.0 + 250.0 * np.exp(-((z - 0.45) / 0.3) ** 2) * np.ones((1, mesh.nr))     # hot spot across the slab cut
@@ -28,6 +28,7 @@ def main(rank, world, port, shape, n_steps, sweeps, out_path):
     solver.run(0.1, n_steps, sweeps=sweeps, has_old=True)
     full = gather_field(solver.value_tensor())
     stats = solver.stats(sweeps * n_steps)
+    assert not any(s.get('peer_timeout') for s in stats), stats
     if rank == 0:
         np.save(out_path, full.cpu().numpy())
         np.save(out_path + '.iters.npy', np.array([s['iters'] for s in stats]))
@@ -38,4 +39,4 @@ def main(rank, world, port, shape, n_steps, sweeps, out_path):
 
 if __name__ == '__main__':
     main(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), tuple(int(v) for v in sys.argv[4].split(',')),
-         int(sys.argv[5]), int(sys.argv[6]), sys.argv[7])
+         int(sys.argv[5]), int(sys.argv[6]), sys.argv[7], *(sys.argv[8:10]))
