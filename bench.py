@@ -25,6 +25,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; stdout must carry exactly one JSON line
+if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+    os.environ['NCCL_DEBUG'] = 'WARN'
 
 RADIAL_SPLIT = {1024: (128, 256, 640), 4096: (512, 1024, 2560), 512: (64, 128, 320), 256: (32, 64, 160), 128: (16, 32, 80)}
 DT, SWEEPS, HAS_OLD = 0.1, 5, True
@@ -163,7 +166,8 @@ def run_gpu(args, rank, world, local_rank):
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
         loop_mode = 'host' if (world > 1 and args.comm == 'nccl') else args.loop_mode
-        solver = make_solver_for_rank(mesh, cfg, rank, world, comm=args.comm, tol=args.tol, loop_mode=loop_mode)
+        solver = make_solver_for_rank(mesh, cfg, rank, world, comm=args.comm, tol=args.tol, loop_mode=loop_mode,
+                                      extrapolate=os.environ.get('HP_EXTRAP', '1') != '0')
 
         def barrier():
             stream.synchronize()

@@ -97,6 +97,7 @@ struct hp_solver_s {
     HpComm* comm = nullptr;          // my mailbox
     double* qz_block = nullptr;      // base of the (q, z) allocation (IPC handle is per allocation)
     std::vector<void*> ipc_opened;
+    bool have_prev = false;          // Told holds the field of the previous step start (extrapolated PCG start)
     bool ghost_dirty = true;         // ghost rows of T must be refreshed by an explicit exchange before the next sweep
     // L2 access-policy window over the contiguous (q, z) block
     bool l2_on = false;
@@ -269,7 +270,7 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
     CK(cudaMallocHost((void**)&h->h_state, sizeof(HpState)));
 
     h->opts.precond = 1; h->opts.criterion = 0; h->opts.tol = 1e-9; h->opts.max_iter = 5000;
-    h->opts.loop_mode = 1; h->opts.poll_chunk = 8; h->opts.refactor_every = 1;
+    h->opts.loop_mode = 1; h->opts.poll_chunk = 8; h->opts.refactor_every = 1; h->opts.extrapolate = 1;
 
     // initial field + snapshots (main.py:34,133,145,152)
     CK(hpk::launch_fill_rows(d, d.T, h->stream));
@@ -336,6 +337,7 @@ int hp_set_T_dev(hp_handle h, const double* d_T) {
     if (!h || !d_T) return fail("hp_set_T_dev: null argument");
     CK(cudaMemcpyAsync(h->d.T + h->d.nr, d_T, owned_bytes(h), cudaMemcpyDeviceToDevice, h->stream));
     h->ghost_dirty = true;
+    h->have_prev = false;
     return 0;
 }
 int hp_get_T_dev(hp_handle h, double* d_T) {
@@ -347,6 +349,7 @@ int hp_set_T_host(hp_handle h, const double* h_T) {
     if (!h || !h_T) return fail("hp_set_T_host: null argument");
     CK(cudaMemcpyAsync(h->d.T + h->d.nr, h_T, owned_bytes(h), cudaMemcpyHostToDevice, h->stream));
     h->ghost_dirty = true;
+    h->have_prev = false;
     return 0;
 }
 int hp_get_T_host(hp_handle h, double* h_T) {
@@ -395,7 +398,7 @@ static int combine(hp_solver_s* h, HpKArgs& a, int kind) {
 // ---- one sweep with plain stream launches, host-polled PCG loop ------------------------------------------
 // Under axial slabs (nranks > 1): ghost rows of T before assembly, ghost rows of z before every direction
 // update, and the CG scalars combined over ranks after every reducing kernel (FIN_* kinds of k_finalize).
-static int sweep_stream(hp_solver_s* h, double dt, int has_old, bool refactor) {
+static int sweep_stream(hp_solver_s* h, double dt, int has_old, bool refactor, bool shift = false) {
     HpDev& d = h->d;
     HpKArgs a = make_args(h, dt, has_old);
     a.rhs_out = h->rhs_dbg;
@@ -414,10 +417,23 @@ static int sweep_stream(hp_solver_s* h, double dt, int has_old, bool refactor) {
     if (h->opts.precond == 1 && refactor) {
         if (launch(h, hpk::desc_factor(h->cfg, d), params, KIND_FACTOR)) return -1;
     }
-    if (launch(h, hpk::desc_cg_init(h->cfg, d, h->opts.precond, h->opts.criterion), params, KIND_INIT)) return -1;
-    if (combine(h, a, 3)) return -1;
     const HpKernelLaunch kA = hpk::desc_cg_A(h->cfg, d);
     const HpKernelLaunch kB = hpk::desc_cg_B(h->cfg, d, h->opts.precond, h->opts.criterion);
+    if (shift) {
+        // z holds T - T_prev (k_delta): one (A, B) pair with alpha := 1 moves the start of the solve to the extrapolated
+        // field, r0 -> r0 - L z, and finalises like the INIT kernel
+        HpKArgs as = a;
+        as.shift = 1;
+        void* ps[] = {&d, &h->phys, &as};
+        if (!d.p2p && exchange_rows(h, d.z)) return -1;
+        if (launch(h, kA, ps, KIND_A)) return -1;
+        if (combine(h, as, 1)) return -1;
+        if (launch(h, kB, ps, KIND_B)) return -1;
+        if (combine(h, as, 3)) return -1;
+    } else {
+        if (launch(h, hpk::desc_cg_init(h->cfg, d, h->opts.precond, h->opts.criterion), params, KIND_INIT)) return -1;
+        if (combine(h, a, 3)) return -1;
+    }
     int launched = 0;
     while (true) {
         CK(cudaMemcpyAsync(h->h_state, d.st, sizeof(HpState), cudaMemcpyDeviceToHost, h->stream));
@@ -460,7 +476,7 @@ static int chain_kernel(NodeChain& c, const HpKernelLaunch& k, void** params, co
 
 static bool same_opts(const hp_solve_opts& a, const hp_solve_opts& b) {
     return a.precond == b.precond && a.criterion == b.criterion && a.tol == b.tol && a.max_iter == b.max_iter &&
-           a.loop_mode == b.loop_mode && a.refactor_every == b.refactor_every;
+           a.loop_mode == b.loop_mode && a.refactor_every == b.refactor_every && a.extrapolate == b.extrapolate;
 }
 
 static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int update_old, GraphEntry** out) {
@@ -475,10 +491,16 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
     CK(cudaGraphCreate(&e.graph, 0));
     NodeChain c{e.graph};
     HpDev& d = h->d;
+    // update_old: 0 nothing, 1 Told <- T, 2 z <- T - Told (extrapolated start of the first solve) then Told <- T
+    if (update_old == 2) {
+        HpKArgs a0 = make_args(h, dt, has_old);
+        void* p0[] = {&d, &h->phys, &a0};
+        if (chain_kernel(c, hpk::desc_delta(h->cfg, d), p0)) return -1;
+    }
     if (update_old) {
         cudaGraphNode_t n;
-        CK(cudaGraphAddMemcpyNode1D(&n, e.graph, nullptr, 0, d.Told, d.T, (size_t)(d.nz + 2) * d.nr * sizeof(double),
-                                    cudaMemcpyDeviceToDevice));
+        CK(cudaGraphAddMemcpyNode1D(&n, e.graph, c.last ? &c.last : nullptr, c.last ? 1 : 0, d.Told, d.T,
+                                    (size_t)(d.nz + 2) * d.nr * sizeof(double), cudaMemcpyDeviceToDevice));
         c.last = n;
     }
     for (int s = 0; s < sweeps; ++s) {
@@ -496,9 +518,21 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
         cudaGraphConditionalHandle cond;
         CK(cudaGraphConditionalHandleCreate(&cond, e.graph, 0, cudaGraphCondAssignDefault));
         a.use_cond = 1; a.cond = (unsigned long long)cond;
-        if (chain_kernel(c, hpk::desc_cg_init(h->cfg, d, h->opts.precond, h->opts.criterion), params, h)) return -1;
-        void* pwi[] = {&d, &h->phys, &a, &ki};
-        if (h->nranks > 1 && chain_kernel(c, hpk::desc_wait(), pwi)) return -1;
+        if (update_old == 2 && s == 0) {
+            HpKArgs as = a;
+            as.shift = 1;
+            void* ps[] = {&d, &h->phys, &as};
+            void* psa[] = {&d, &h->phys, &as, &ka};
+            void* psi[] = {&d, &h->phys, &as, &ki};
+            if (chain_kernel(c, hpk::desc_cg_A(h->cfg, d), ps, h)) return -1;
+            if (h->nranks > 1 && chain_kernel(c, hpk::desc_wait(), psa)) return -1;
+            if (chain_kernel(c, hpk::desc_cg_B(h->cfg, d, h->opts.precond, h->opts.criterion), ps, h)) return -1;
+            if (h->nranks > 1 && chain_kernel(c, hpk::desc_wait(), psi)) return -1;
+        } else {
+            if (chain_kernel(c, hpk::desc_cg_init(h->cfg, d, h->opts.precond, h->opts.criterion), params, h)) return -1;
+            void* pwi[] = {&d, &h->phys, &a, &ki};
+            if (h->nranks > 1 && chain_kernel(c, hpk::desc_wait(), pwi)) return -1;
+        }
         cudaGraphNodeParams cp{};
         cp.type = cudaGraphNodeTypeConditional;
         cp.conditional.handle = cond;
@@ -523,25 +557,38 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
     return 0;
 }
 
-static int run_steps(hp_solver_s* h, double dt, int n_steps, int sweeps, int has_old, int update_old) {
+// is_step = 0: a bare sweep (hp_sweep; the caller manages T_old).  is_step = 1: whole time steps (hp_step / hp_run):
+// Told <- T at the step start when has_old or extrapolate is set; with extrapolate and a completed previous step the
+// first solve starts from T + (T - T_prev).
+static int run_steps(hp_solver_s* h, double dt, int n_steps, int sweeps, int has_old, int is_step) {
     if (!(dt > 0.0)) return fail("dt must be > 0");
     if (sweeps < 1) return fail("sweeps must be >= 1");
+    const bool ext = is_step && h->opts.extrapolate;
+    auto step_mode = [&]() { return !is_step ? 0 : (ext ? (h->have_prev ? 2 : 1) : (has_old ? 1 : 0)); };
     if (h->opts.loop_mode == 1 && (h->nranks == 1 || h->d.p2p) && !h->rhs_dbg && !h->prof_on) {
         if (h->nranks > 1 && h->ghost_dirty) { if (exchange_rows(h, h->d.T)) return -1; h->ghost_dirty = false; }
-        GraphEntry* g = nullptr;
-        if (get_graph(h, dt, sweeps, has_old, update_old, &g)) return -1;
         for (int s = 0; s < n_steps; ++s) {
+            GraphEntry* g = nullptr;
+            if (get_graph(h, dt, sweeps, has_old, step_mode(), &g)) return -1;
             CK(cudaGraphLaunch(g->exec, h->stream));
             h->launches_host += g->static_nodes;
             h->graph_body_nodes = g->body_nodes;
             h->sweeps_host += sweeps;
+            if (ext) h->have_prev = true;
         }
         return 0;
     }
     for (int s = 0; s < n_steps; ++s) {
-        if (update_old && hp_update_old(h)) return -1;
+        const int mode = step_mode();
+        if (mode == 2) {
+            HpKArgs a0 = make_args(h, dt, has_old);
+            void* p0[] = {&h->d, &h->phys, &a0};
+            if (launch(h, hpk::desc_delta(h->cfg, h->d), p0, KIND_OTHER)) return -1;
+        }
+        if (mode && hp_update_old(h)) return -1;
         for (int k = 0; k < sweeps; ++k)
-            if (sweep_stream(h, dt, has_old, (k % h->opts.refactor_every) == 0)) return -1;
+            if (sweep_stream(h, dt, has_old, (k % h->opts.refactor_every) == 0, mode == 2 && k == 0)) return -1;
+        if (ext) h->have_prev = true;
     }
     return 0;
 }
@@ -559,18 +606,22 @@ int hp_sweep(hp_handle h, double dt, int has_old, double* host_residual) {
 
 int hp_step(hp_handle h, double dt, int sweeps, int has_old) {
     if (!h) return fail("null handle");
-    return run_steps(h, dt, 1, sweeps, has_old, has_old ? 1 : 0);
+    return run_steps(h, dt, 1, sweeps, has_old, 1);
 }
 
 int hp_run(hp_handle h, double dt, int n_steps, int sweeps, int has_old) {
     if (!h) return fail("null handle");
     if (n_steps < 0) return fail("n_steps must be >= 0");
-    return run_steps(h, dt, n_steps, sweeps, has_old, has_old ? 1 : 0);
+    return run_steps(h, dt, n_steps, sweeps, has_old, 1);
 }
 
 int hp_run_host(hp_handle h, const double* h_T_in, double* h_T_out, double dt, int n_steps, int sweeps, int has_old) {
     if (!h || !h_T_in || !h_T_out) return fail("hp_run_host: null argument");
+    // the uploaded field continues the transient: the previous step start kept in Told stays the history of the
+    // extrapolated PCG start (it only seeds the solver; a stale history costs iterations, never accuracy)
+    const bool keep = h->have_prev;
     if (hp_set_T_host(h, h_T_in)) return -1;
+    h->have_prev = keep;
     if (hp_run(h, dt, n_steps, sweeps, has_old)) return -1;
     return hp_get_T_host(h, h_T_out);
 }

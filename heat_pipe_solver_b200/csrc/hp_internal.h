@@ -80,7 +80,8 @@ struct HpKArgs {
     int32_t criterion;
     int32_t use_cond;
     int32_t prefetch;          // bit0: k_cg_A, bit1: k_cg_B issue bulk L2 prefetches of the next row
-    int32_t _pad;
+    int32_t shift;             // 1: this (A, B) pair moves the start of the solve to x0 + z (z = extrapolated increment):
+                               //    alpha := 1, and k_cg_B finalises like the INIT kernel
     unsigned long long cond;   // cudaGraphConditionalHandle of the enclosing WHILE node (use_cond != 0)
     double* rhs_out;           // optional (debug): full rhs, ghost-inclusive layout
 };
@@ -110,6 +111,7 @@ bool pick_config(int nr, int nz, int num_sms, HpLaunchCfg* cfg, const char** err
 // variables with exactly these types/order (documented next to each kernel in hp_kernels.cu).
 HpKernelLaunch desc_snapshot_kout(const HpLaunchCfg&, const HpDev&);
 HpKernelLaunch desc_coef(const HpLaunchCfg&, const HpDev&);
+HpKernelLaunch desc_delta(const HpLaunchCfg&, const HpDev&);   // z = T - Told on every row (ghosts included)
 HpKernelLaunch desc_diag(const HpLaunchCfg&, const HpDev&);
 HpKernelLaunch desc_factor(const HpLaunchCfg&, const HpDev&);
 HpKernelLaunch desc_cg_init(const HpLaunchCfg&, const HpDev&, int precond, int criterion);

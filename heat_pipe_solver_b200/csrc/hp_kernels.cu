@@ -164,7 +164,9 @@ __device__ __forceinline__ void finalize_diag(const HpDev& d, const HpKArgs& a, 
 __device__ __forceinline__ void finalize_A(const HpDev& d, const HpKArgs& a, double pq) {
     HpState* s = d.st;
     s->pq = pq;
-    if (pq > 0.0 && isfinite(pq)) {
+    if (a.shift) {
+        s->alpha = 1.0;         // not a CG step: the pair only moves the start of the solve
+    } else if (pq > 0.0 && isfinite(pq)) {
         s->alpha = s->rz / pq;
     } else {
         s->alpha = 0.0;
@@ -266,7 +268,7 @@ __global__ void k_wait(HpDev d, hp_phys ph, HpKArgs a, int fin_kind) {
     }
     if (fin_kind == FIN_DIAG) finalize_diag(d, a, v[0], v[1]);
     else if (fin_kind == FIN_A) finalize_A(d, a, v[0]);
-    else finalize_B(d, a, fin_kind == FIN_INIT, v[0], v[1], v[2]);
+    else finalize_B(d, a, fin_kind == FIN_INIT || a.shift, v[0], v[1], v[2]);
     if (bad || (s->flags & 8)) {          // a peer never arrived: stop this sweep, make the failure sticky
         s->flags |= 8; s->done = 1;
         d.stats[(s->sweep_count - 1) % HP_STATS_CAP].flags |= 8;
@@ -287,7 +289,7 @@ __global__ void k_finalize(HpDev d, hp_phys ph, HpKArgs a, int kind) {
     }
     if (kind == FIN_DIAG) finalize_diag(d, a, v[0], v[1]);
     else if (kind == FIN_A) finalize_A(d, a, v[0]);
-    else finalize_B(d, a, kind == FIN_INIT, v[0], v[1], v[2]);
+    else finalize_B(d, a, kind == FIN_INIT || a.shift, v[0], v[1], v[2]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -633,7 +635,7 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT)
     const int i0 = tl * EPT;
     const long long team = (long long)blockIdx.x * G::LPC + team_in_cta, nteams = (long long)gridDim.x * G::LPC;
     const int ja = (int)(team * nz / nteams), jb = (int)((team + 1) * nz / nteams);
-    const double alpha = s0.alpha;
+    const double alpha = a.shift ? 1.0 : s0.alpha;
     const double* __restrict__ pcur = s0.parity ? d.p1 : d.p0;
     const bool need_diag = (a.criterion == 1);
 
@@ -771,7 +773,7 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT)
     double tot[3];
     if (cta_publish<3>(acc, 4u, d.partials, &d.st->ticket, tot, d.p2p != 0) && threadIdx.x == 0) {
         if (d.nranks > 1) stash_local<3>(d, tot, HP_COMM_B);
-        else finalize_B(d, a, INIT, tot[0], tot[1], tot[2]);
+        else finalize_B(d, a, INIT || a.shift, tot[0], tot[1], tot[2]);
     }
 }
 
@@ -826,6 +828,14 @@ __global__ void k_fill_rows(HpDev d, double* __restrict__ field) {
     const long long n = (long long)(d.nz + 2) * d.nr;
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x)
         field[c] = d.Tamb_line[(int)(c / d.nr)];
+}
+
+// z = T - Told on every row: the increment of the previous time step, used as the extrapolated start of the
+// first solve of the next step (x0 = T + (T - T_prev); the system itself is still assembled at T, like FiPy's)
+__global__ void __launch_bounds__(256) k_delta(HpDev d, hp_phys ph, HpKArgs a) {
+    const long long n = (long long)(d.nz + 2) * d.nr;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x)
+        d.z[c] = d.T[c] - d.Told[c];
 }
 
 // ---- instantiation table -----------------------------------------------------------------------
@@ -928,6 +938,9 @@ HpKernelLaunch desc_snapshot_kout(const HpLaunchCfg& c, const HpDev& d) {
 }
 HpKernelLaunch desc_coef(const HpLaunchCfg& c, const HpDev& d) {
     return {(const void*)k_coef, dim3(c.grid_cell), dim3(c.cta_cell), 0};
+}
+HpKernelLaunch desc_delta(const HpLaunchCfg& c, const HpDev& d) {
+    return {(const void*)k_delta, dim3(c.grid_cell), dim3(c.cta_cell), 0};
 }
 HpKernelLaunch desc_diag(const HpLaunchCfg& c, const HpDev& d) {
     return {(const void*)k_diag, dim3(c.grid_cell), dim3(c.cta_cell), 0};

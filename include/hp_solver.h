@@ -72,6 +72,9 @@ typedef struct hp_solve_opts {
     int32_t loop_mode;      /* 0 host-polled chunks of poll_chunk iterations; 1 CUDA graph, device-side WHILE */
     int32_t poll_chunk;
     int32_t refactor_every; /* re-factor the line preconditioner every k-th sweep (1 = every sweep) */
+    int32_t extrapolate;    /* 1: hp_step/hp_run start the first solve of a step from T + (T - T_prev) (the system is still
+                               assembled at T and `res` is still FiPy's pre-solve residual; only the PCG start changes) */
+    int32_t _pad;
 } hp_solve_opts;
 
 typedef struct hp_sweep_stat {

@@ -174,6 +174,35 @@ def test_transient_sweeps_with_old_value_from_hot_state(cfg):
     assert np.max(np.abs(T - o.T)) <= END_TOL_K
 
 
+def test_extrapolated_start_saves_iterations_same_answer(cfg):
+    """hp_step / hp_run start the first solve of a step from T + (T - T_prev).  The system is still assembled at T
+    (FiPy's semantics: same pre-solve residual), the answer is the same to solver tolerance, the PCG needs fewer
+    iterations."""
+    got = {}
+    for ext in (False, True):
+        s, o = make_pair(cfg, SHAPES['s96x100'], has_old=True, solver_kw=dict(extrapolate=ext))
+        with s:
+            s.run(0.1, 8, sweeps=3, has_old=True)
+            got[ext] = (s.value.reshape(o.T.shape), s.total_iters, np.array([st['residual_l2'] for st in s.stats(24)]))
+    for _ in range(8):
+        o.update_old()
+        for _ in range(3):
+            o.sweep(0.1, solver='banded')
+    for ext in (False, True):
+        assert np.max(np.abs(got[ext][0] - o.T)) <= 24 * PER_STEP_TOL_K
+    assert got[True][1] < got[False][1], (got[True][1], got[False][1])
+    big = got[False][2] > 1e-6            # residuals at solver-tolerance level differ in their last digits
+    assert np.allclose(got[True][2][big], got[False][2][big], rtol=1e-5)
+    # single sweep per step with hasOld=False (the reference's active loop) goes through the same path
+    s, o = make_pair(cfg, SHAPES['s64x32'])
+    with s:
+        s.run(0.1, 6)
+        T = s.value.reshape(o.T.shape)
+    for _ in range(6):
+        o.sweep(0.1, solver='banded')
+    assert np.max(np.abs(T - o.T)) <= 6 * PER_STEP_TOL_K
+
+
 def test_simple_properties_run(cfg):
     """BASELINE configs[0]: constant rho, cp, k (main.py:41-46); linear problem."""
     from heat_pipe_solver_b200.main import run
