@@ -32,7 +32,7 @@ if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
 RADIAL_SPLIT = {1024: (128, 256, 640), 4096: (512, 1024, 2560), 512: (64, 128, 320), 256: (32, 64, 160), 128: (16, 32, 80)}
 DT, SWEEPS, HAS_OLD = 0.1, 5, True
 # algorithmic bytes per cell and launch (fp64; DESIGN.md "Kernels"): reads + writes of full-size fields
-BYTES_PER_CELL = {'cg_A': 56, 'cg_B': 72, 'cg_init': 32, 'diag': 48, 'factor': 24, 'coef': 24}
+BYTES_PER_CELL = {'cg_A': 56, 'cg_B': 72, 'cg_init': 32, 'diag': 48, 'factor': 24, 'coef': 24, 'mg': 0}
 
 
 def parse_workload(s):
@@ -167,7 +167,7 @@ def run_gpu(args, rank, world, local_rank):
     with torch.cuda.stream(stream):
         loop_mode = 'host' if (world > 1 and args.comm == 'nccl') else args.loop_mode
         solver = make_solver_for_rank(mesh, cfg, rank, world, comm=args.comm, tol=args.tol, loop_mode=loop_mode,
-                                      extrapolate=os.environ.get('HP_EXTRAP', '1') != '0')
+                                      extrapolate=os.environ.get('HP_EXTRAP', '1') != '0', precond=args.precond)
 
         def barrier():
             stream.synchronize()
@@ -261,7 +261,7 @@ def run_gpu(args, rank, world, local_rank):
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak' if world == 1 else 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': f'synthetic composite mesh {nz}x{nr} (axial x radial), T-dependent properties, literal mode, '
-                                   f'dt={DT}s, updateOld + {SWEEPS} sweeps/step, radial-line PCG tol {args.tol:g} K',
+                                   f'dt={DT}s, updateOld + {SWEEPS} sweeps/step, PCG ({args.precond}) tol {args.tol:g} K',
                        'parallelism': 'single GPU' if world == 1 else (f'axial slabs x{world}, ' + ('NVLink peer-memory halo rows + CG scalars fused into the PCG kernels, one CUDA graph per step' if args.comm == 'p2p' else 'NCCL send/recv halo + all-gathered CG scalars, host-driven loop')),
                        'l2': 'working set (11 fp64 fields) exceeds the 126 MB L2; no flush needed',
                        'pcg_iterations_per_step': iters / args.steps, 'loop_mode': loop_mode},
@@ -287,6 +287,7 @@ def main():
     ap.add_argument('--tol', type=float, default=1e-9)
     ap.add_argument('--loop-mode', default='graph', choices=['graph', 'host'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--precond', default='rline', choices=['rline', 'mgline', 'jacobi'])
     ap.add_argument('--comm', default='p2p', choices=['p2p', 'nccl'], help='slab exchange: NVLink peer stores fused into the kernels, or NCCL calls')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))

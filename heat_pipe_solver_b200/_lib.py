@@ -34,7 +34,8 @@ class HpMeshDesc(C.Structure):
 class HpSolveOpts(C.Structure):
     _fields_ = [('precond', C.c_int32), ('criterion', C.c_int32), ('tol', C.c_double), ('max_iter', C.c_int32),
                 ('loop_mode', C.c_int32), ('poll_chunk', C.c_int32), ('refactor_every', C.c_int32),
-                ('extrapolate', C.c_int32), ('_pad', C.c_int32)]
+                ('extrapolate', C.c_int32), ('mg_levels', C.c_int32), ('mg_coarse_sweeps', C.c_int32), ('_pad', C.c_int32),
+                ('mg_omega', C.c_double)]
 
 
 class HpSweepStat(C.Structure):
@@ -46,7 +47,7 @@ class HpKernelTimes(C.Structure):
     _fields_ = [('count', C.c_int64 * 8), ('total_ms', C.c_double * 8)]
 
 
-KERNEL_KINDS = ('other', 'coef', 'diag', 'factor', 'cg_init', 'cg_A', 'cg_B')
+KERNEL_KINDS = ('other', 'coef', 'diag', 'factor', 'cg_init', 'cg_A', 'cg_B', 'mg')
 
 # every symbol include/hp_solver.h declares: name -> (restype, argtypes)
 _H = C.c_void_p

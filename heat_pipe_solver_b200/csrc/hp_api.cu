@@ -93,6 +93,9 @@ struct hp_solver_s {
     // slabs
     int rank = 0, nranks = 1;
     ncclComm_t nccl = nullptr;
+    // 'mgline' hierarchy (level 0 aliases the fine fields)
+    HpLevel lev[HP_MAX_LEVELS];
+    int nlev = 0, nlev_alloc = 0;
     // peer-memory exchange (hp_peer_export / hp_peer_import)
     HpComm* comm = nullptr;          // my mailbox
     double* qz_block = nullptr;      // base of the (q, z) allocation (IPC handle is per allocation)
@@ -162,16 +165,45 @@ static int apply_l2_to_stream(hp_solver_s* h) {
     return 0;
 }
 
+// ---- 'mgline' hierarchy: level l+1 has ceil(nz_l / 2) rows; stops at 16 rows or mg_levels -------------------
+static int setup_mg(hp_solver_s* h) {
+    HpDev& d = h->d;
+    int want = 1;
+    for (int nzl = d.nz; want < h->opts.mg_levels && nzl >= 32; nzl = (nzl + 1) / 2) ++want;
+    if (h->nlev_alloc == 0) {
+        HpLevel& L0 = h->lev[0];
+        L0.nz = d.nz; L0.cR = d.cR; L0.cZ = d.cZ; L0.diag = d.diag; L0.dinv = d.dinv;
+        L0.rhs = d.r; L0.x = d.z; L0.tmp = d.q;
+        if (dev_alloc(h, (void**)&L0.x2, h->field_elems * sizeof(double))) return -1;
+        CK(cudaMemsetAsync(L0.x2, 0, h->field_elems * sizeof(double), h->stream));
+        h->nlev_alloc = 1;
+    }
+    for (int l = h->nlev_alloc; l < want; ++l) {
+        HpLevel& L = h->lev[l];
+        L.nz = (h->lev[l - 1].nz + 1) / 2;
+        const size_t elems = (size_t)(L.nz + 2) * d.nr + 64;
+        double** f[] = {&L.cR, &L.cZ, &L.diag, &L.dinv, &L.rhs, &L.x, &L.x2, &L.tmp};
+        for (double** p : f) {
+            if (dev_alloc(h, (void**)p, elems * sizeof(double))) return -1;
+            CK(cudaMemsetAsync(*p, 0, elems * sizeof(double), h->stream));
+        }
+        h->nlev_alloc = l + 1;
+    }
+    h->nlev = want;
+    return 0;
+}
+
 static HpKArgs make_args(const hp_solver_s* h, double dt, int has_old) {
     HpKArgs a{};
     a.dt = dt; a.tol = h->opts.tol; a.has_old = has_old; a.max_iter = h->opts.max_iter;
     a.criterion = h->opts.criterion; a.use_cond = 0; a.cond = 0; a.rhs_out = nullptr;
     static const int pf = [] { const char* e = getenv("HP_PREFETCH"); return e ? atoi(e) : 0; }();
-    a.prefetch = pf;   // measured slower on B200 (profiles/): off unless asked for
+    a.prefetch = pf;
+    a.mg = (h->opts.precond == 2) ? 1 : 0; a.init_phase = 0; a.omega = h->opts.mg_omega; a.shift = 0;   // measured slower on B200 (profiles/): off unless asked for
     return a;
 }
 
-enum { KIND_OTHER = 0, KIND_COEF, KIND_DIAG, KIND_FACTOR, KIND_INIT, KIND_A, KIND_B, KIND_COUNT };
+enum { KIND_OTHER = 0, KIND_COEF, KIND_DIAG, KIND_FACTOR, KIND_INIT, KIND_A, KIND_B, KIND_MG, KIND_COUNT };
 
 static int launch(hp_solver_s* h, const HpKernelLaunch& k, void** params, int kind = KIND_OTHER) {
     const bool prof = h->prof_on && h->prof_used < h->prof_ev.size() / 2;
@@ -320,7 +352,7 @@ int hp_set_stream(hp_handle h, void* stream) {
 
 int hp_set_opts(hp_handle h, const hp_solve_opts* o) {
     if (!h || !o) return fail("hp_set_opts: null argument");
-    if (o->precond < 0 || o->precond > 1) return fail("hp_set_opts: precond must be 0 (jacobi) or 1 (rline)");
+    if (o->precond < 0 || o->precond > 2) return fail("hp_set_opts: precond must be 0 (jacobi), 1 (rline) or 2 (mgline)");
     if (o->criterion < 0 || o->criterion > 2) return fail("hp_set_opts: criterion must be 0, 1 or 2");
     if (!(o->tol > 0.0)) return fail("hp_set_opts: tol must be > 0");
     if (o->max_iter < 1) return fail("hp_set_opts: max_iter must be >= 1");
@@ -328,6 +360,14 @@ int hp_set_opts(hp_handle h, const hp_solve_opts* o) {
     h->opts = *o;
     if (h->opts.poll_chunk < 1) h->opts.poll_chunk = 8;
     if (h->opts.refactor_every < 1) h->opts.refactor_every = 1;
+    if (h->opts.mg_levels < 2) h->opts.mg_levels = 6;
+    if (h->opts.mg_levels > HP_MAX_LEVELS) h->opts.mg_levels = HP_MAX_LEVELS;
+    if (h->opts.mg_coarse_sweeps < 0) h->opts.mg_coarse_sweeps = 2;
+    if (!(h->opts.mg_omega > 0.0 && h->opts.mg_omega <= 1.0)) h->opts.mg_omega = 0.8;
+    if (h->opts.precond == 2) {
+        if (setup_mg(h)) return -1;
+        if (h->nlev < 2) h->opts.precond = 1;          // mesh too short to coarsen: plain line preconditioner
+    }
     return 0;
 }
 
@@ -383,78 +423,7 @@ static int exchange_rows(hp_solver_s* h, double* field) {
     return 0;
 }
 
-// all ranks' per-kernel sums -> every rank, then one thread advances the scalar recurrences identically everywhere
-static int combine(hp_solver_s* h, HpKArgs& a, int kind) {
-    if (h->nranks == 1) return 0;
-    if (h->d.p2p) {                  // sums already travelled by peer stores of the producing kernel
-        void* p4[] = {&h->d, &h->phys, &a, &kind};
-        return launch(h, hpk::desc_wait(), p4, KIND_OTHER);
-    }
-    NK(g_nccl.AllGather(h->d.red_local, h->d.red_all, HP_NRED, ncclFloat64, h->nccl, h->stream));
-    void* p4[] = {&h->d, &h->phys, &a, &kind};
-    return launch(h, hpk::desc_finalize(), p4, KIND_OTHER);
-}
-
-// ---- one sweep with plain stream launches, host-polled PCG loop ------------------------------------------
-// Under axial slabs (nranks > 1): ghost rows of T before assembly, ghost rows of z before every direction
-// update, and the CG scalars combined over ranks after every reducing kernel (FIN_* kinds of k_finalize).
-static int sweep_stream(hp_solver_s* h, double dt, int has_old, bool refactor, bool shift = false) {
-    HpDev& d = h->d;
-    HpKArgs a = make_args(h, dt, has_old);
-    a.rhs_out = h->rhs_dbg;
-    void* params[] = {&d, &h->phys, &a};
-    if (apply_l2_to_stream(h)) return -1;
-    if (!d.p2p || h->ghost_dirty) { if (exchange_rows(h, d.T)) return -1; h->ghost_dirty = false; }
-    if (h->phys.gamma == 1) {
-        if (launch(h, hpk::desc_coef(h->cfg, d), params, KIND_COEF)) return -1;
-    }
-    {
-        int write_dinv = (h->opts.precond == 0) ? 1 : 0;
-        void* p4[] = {&d, &h->phys, &a, &write_dinv};
-        if (launch(h, hpk::desc_diag(h->cfg, d), p4, KIND_DIAG)) return -1;
-        if (combine(h, a, 0)) return -1;
-    }
-    if (h->opts.precond == 1 && refactor) {
-        if (launch(h, hpk::desc_factor(h->cfg, d), params, KIND_FACTOR)) return -1;
-    }
-    const HpKernelLaunch kA = hpk::desc_cg_A(h->cfg, d);
-    const HpKernelLaunch kB = hpk::desc_cg_B(h->cfg, d, h->opts.precond, h->opts.criterion);
-    if (shift) {
-        // z holds T - T_prev (k_delta): one (A, B) pair with alpha := 1 moves the start of the solve to the extrapolated
-        // field, r0 -> r0 - L z, and finalises like the INIT kernel
-        HpKArgs as = a;
-        as.shift = 1;
-        void* ps[] = {&d, &h->phys, &as};
-        if (!d.p2p && exchange_rows(h, d.z)) return -1;
-        if (launch(h, kA, ps, KIND_A)) return -1;
-        if (combine(h, as, 1)) return -1;
-        if (launch(h, kB, ps, KIND_B)) return -1;
-        if (combine(h, as, 3)) return -1;
-    } else {
-        if (launch(h, hpk::desc_cg_init(h->cfg, d, h->opts.precond, h->opts.criterion), params, KIND_INIT)) return -1;
-        if (combine(h, a, 3)) return -1;
-    }
-    int launched = 0;
-    while (true) {
-        CK(cudaMemcpyAsync(h->h_state, d.st, sizeof(HpState), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        if (h->h_state->done) break;
-        if (launched >= h->opts.max_iter + h->opts.poll_chunk) return fail("sweep_stream: PCG loop did not terminate");
-        for (int k = 0; k < h->opts.poll_chunk; ++k) {
-            if (!d.p2p && exchange_rows(h, d.z)) return -1;      // p2p: k_cg_B stored the rows into the ghosts itself
-            if (launch(h, kA, params, KIND_A)) return -1;
-            if (combine(h, a, 1)) return -1;
-            if (launch(h, kB, params, KIND_B)) return -1;
-            if (combine(h, a, 2)) return -1;
-            launched++;
-        }
-    }
-    h->stream_mode_iters += h->h_state->iter;
-    h->sweeps_host++;
-    return 0;
-}
-
-// ---- CUDA graph: [updateOld] + sweeps x ( [coef] diag [factor] init WHILE{A,B} ) ---------------------------
+// ---- emission of the sweep either as plain stream launches or as CUDA-graph kernel nodes --------------------------------
 struct NodeChain {
     cudaGraph_t g; cudaGraphNode_t last = nullptr; int count = 0;
 };
@@ -474,9 +443,175 @@ static int chain_kernel(NodeChain& c, const HpKernelLaunch& k, void** params, co
     return 0;
 }
 
+struct Emitter {
+    hp_solver_s* h;
+    NodeChain* chain;        // nullptr: launch on the handle's stream
+};
+static int emit(Emitter& e, const HpKernelLaunch& k, void** params, int kind = KIND_OTHER) {
+    if (e.chain) return chain_kernel(*e.chain, k, params, e.h);
+    return launch(e.h, k, params, kind);
+}
+
+// all ranks' per-kernel sums -> every rank, then one thread advances the scalar recurrences identically everywhere.
+// fin_kind: 0 diag, 1 A, 2 B, 3 init, 4 end of the mgline V-cycle (FIN_* of hp_kernels.cu)
+static int emit_combine(Emitter& e, HpKArgs& a, int fin_kind) {
+    hp_solver_s* h = e.h;
+    if (h->nranks == 1) return 0;
+    void* p4[] = {&h->d, &h->phys, &a, &fin_kind};
+    if (h->d.p2p) return emit(e, hpk::desc_wait(), p4);          // sums already travelled by peer stores
+    if (e.chain) return fail("NCCL slab exchange cannot be captured: use loop_mode 0 or the peer-memory exchange");
+    NK(g_nccl.AllGather(h->d.red_local, h->d.red_all, HP_NRED, ncclFloat64, h->nccl, h->stream));
+    return emit(e, hpk::desc_finalize(), p4);
+}
+
+// mgline: Galerkin operators and line pivots of the coarse levels (after the fine diagonal / pivots are current)
+static int emit_mg_setup(Emitter& e) {
+    hp_solver_s* h = e.h;
+    int nr = h->d.nr;
+    const int* skip = &h->d.st->mg_skip;          // set by the INIT decision when the sweep is already converged
+    HpLevelSet ls;
+    ls.n = h->nlev;
+    int rows = 0;
+    for (int l = 0; l < h->nlev; ++l) ls.lev[l] = h->lev[l];
+    for (int l = 1; l < h->nlev; ++l) {
+        void* pc[] = {&h->lev[l - 1], &h->lev[l], &nr, &skip};
+        if (emit(e, hpk::desc_mg_coarsen(h->cfg, h->lev[l].nz, nr), pc, KIND_MG)) return -1;
+        rows += h->lev[l].nz;
+    }
+    void* pf[] = {&ls, &nr, &skip};
+    return emit(e, hpk::desc_factor_levels(rows), pf, KIND_MG);
+}
+
+// mgline V(1,1) cycle on r (level-0 rhs) starting from zline = M^-1 r in d.z (left there by k_cg_B); leaves the
+// preconditioned residual in d.z and finalises (r.z, beta) in the last kernel.
+static int emit_vcycle(Emitter& e, const HpKArgs& a_in, int init_phase) {
+    hp_solver_s* h = e.h;
+    HpDev& d = h->d;
+    HpKArgs a = a_in;
+    a.init_phase = init_phase;
+    const int nl = h->nlev, c = nl - 1;
+    auto res = [&](int l, const double* xin, const double* ec, double* xout, double* resout, double* crhs, double scale) -> int {
+        HpMgResArgs m{xin, ec, xout, resout, crhs, scale, (l + 1 < nl) ? h->lev[l + 1].nz : 1};
+        void* p[] = {&d, &a, &h->lev[l], &m};
+        return emit(e, hpk::desc_mg_res(h->cfg, h->lev[l].nz), p, KIND_MG);
+    };
+    auto line = [&](int l, const double* rhs, const double* base, double* out, int fin) -> int {
+        HpMgLineArgs m{rhs, base, out, fin};
+        void* p[] = {&d, &a, &h->lev[l], &m};
+        return emit(e, hpk::desc_mg_line(h->cfg, h->lev[l].nz), p, KIND_MG);
+    };
+    HpLevel* L = h->lev;
+    // down: level 0 starts from omega * zline (pre-smoothing already done by k_cg_B's line solve)
+    if (res(0, d.z, nullptr, L[0].x2, nullptr, L[1].rhs, a.omega)) return -1;
+    for (int l = 1; l < c; ++l) {
+        if (line(l, L[l].rhs, nullptr, L[l].x, 0)) return -1;
+        if (res(l, L[l].x, nullptr, nullptr, nullptr, L[l + 1].rhs, 1.0)) return -1;
+    }
+    // coarsest level: 1 + mg_coarse_sweeps damped line-Jacobi sweeps
+    if (line(c, L[c].rhs, nullptr, L[c].x, 0)) return -1;
+    for (int k = 0; k < h->opts.mg_coarse_sweeps; ++k) {
+        if (res(c, L[c].x, nullptr, nullptr, L[c].tmp, nullptr, 1.0)) return -1;
+        if (line(c, L[c].tmp, L[c].x, L[c].x, 0)) return -1;
+    }
+    // up: prolong + post-smooth
+    for (int l = c - 1; l >= 1; --l) {
+        if (res(l, L[l].x, L[l + 1].x, L[l].x2, L[l].tmp, nullptr, 1.0)) return -1;
+        if (line(l, L[l].tmp, L[l].x2, L[l].x, 0)) return -1;
+    }
+    if (res(0, L[0].x2, L[1].x, d.z, L[0].tmp, nullptr, 1.0)) return -1;
+    if (line(0, L[0].tmp, d.z, d.z, 1)) return -1;
+    HpKArgs af = a;
+    return emit_combine(e, af, 4);
+}
+
+// one PCG iteration: [ghost rows of z] A, B, [V-cycle]
+static int emit_iteration(Emitter& e, HpKArgs& a) {
+    hp_solver_s* h = e.h;
+    HpDev& d = h->d;
+    void* params[] = {&d, &h->phys, &a};
+    if (h->nranks > 1 && !d.p2p) {                       // p2p: the producer stored the rows into the ghosts itself
+        if (e.chain) return fail("NCCL slab exchange cannot be captured");
+        if (exchange_rows(h, d.z)) return -1;
+    }
+    if (emit(e, hpk::desc_cg_A(h->cfg, d), params, KIND_A)) return -1;
+    if (emit_combine(e, a, 1)) return -1;
+    if (emit(e, hpk::desc_cg_B(h->cfg, d, h->opts.precond != 0, h->opts.criterion), params, KIND_B)) return -1;
+    if (emit_combine(e, a, 2)) return -1;
+    if (a.mg && emit_vcycle(e, a, 0)) return -1;
+    return 0;
+}
+
+// everything of a sweep before the PCG loop: [coef] diag [factor] [mg setup] and the start of the solve (INIT kernel, or
+// the shift pair of the extrapolated start); `a` carries the WHILE handle in graph mode
+static int emit_sweep_head(Emitter& e, HpKArgs& a, bool refactor, bool shift) {
+    hp_solver_s* h = e.h;
+    HpDev& d = h->d;
+    void* params[] = {&d, &h->phys, &a};
+    if (h->phys.gamma == 1 && emit(e, hpk::desc_coef(h->cfg, d), params, KIND_COEF)) return -1;
+    int write_dinv = (h->opts.precond == 0) ? 1 : 0;
+    HpKArgs a0 = a;
+    a0.use_cond = 0;
+    void* p40[] = {&d, &h->phys, &a0, &write_dinv};
+    if (emit(e, hpk::desc_diag(h->cfg, d), p40, KIND_DIAG)) return -1;
+    if (emit_combine(e, a0, 0)) return -1;
+    if (h->opts.precond >= 1 && refactor) {
+        if (emit(e, hpk::desc_factor(h->cfg, d), params, KIND_FACTOR)) return -1;
+    }
+    if (shift) {
+        // z holds T - T_prev (k_delta): one (A, B) pair with alpha := 1 moves the start of the solve to the extrapolated
+        // field, r0 -> r0 - L z, and finalises like the INIT kernel
+        HpKArgs as = a;
+        as.shift = 1;
+        void* ps[] = {&d, &h->phys, &as};
+        if (h->nranks > 1 && !d.p2p) {
+            if (e.chain) return fail("NCCL slab exchange cannot be captured");
+            if (exchange_rows(h, d.z)) return -1;
+        }
+        if (emit(e, hpk::desc_cg_A(h->cfg, d), ps, KIND_A)) return -1;
+        if (emit_combine(e, as, 1)) return -1;
+        if (emit(e, hpk::desc_cg_B(h->cfg, d, h->opts.precond != 0, h->opts.criterion), ps, KIND_B)) return -1;
+        if (emit_combine(e, as, 3)) return -1;
+        if (a.mg && (emit_mg_setup(e) || emit_vcycle(e, as, 1))) return -1;
+    } else {
+        if (emit(e, hpk::desc_cg_init(h->cfg, d, h->opts.precond != 0, h->opts.criterion), params, KIND_INIT)) return -1;
+        if (emit_combine(e, a, 3)) return -1;
+        if (a.mg && (emit_mg_setup(e) || emit_vcycle(e, a, 1))) return -1;      // both skipped on the device if converged
+    }
+    return 0;
+}
+
+// ---- one sweep with plain stream launches, host-polled PCG loop ------------------------------------------
+// Under axial slabs (nranks > 1): ghost rows of T before assembly, ghost rows of z before every direction
+// update, and the CG scalars combined over ranks after every reducing kernel.
+static int sweep_stream(hp_solver_s* h, double dt, int has_old, bool refactor, bool shift = false) {
+    HpDev& d = h->d;
+    HpKArgs a = make_args(h, dt, has_old);
+    a.rhs_out = h->rhs_dbg;
+    Emitter e{h, nullptr};
+    if (apply_l2_to_stream(h)) return -1;
+    if (h->nranks > 1 && (!d.p2p || h->ghost_dirty)) { if (exchange_rows(h, d.T)) return -1; h->ghost_dirty = false; }
+    if (emit_sweep_head(e, a, refactor, shift)) return -1;
+    int launched = 0;
+    while (true) {
+        CK(cudaMemcpyAsync(h->h_state, d.st, sizeof(HpState), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->h_state->done) break;
+        if (launched >= h->opts.max_iter + h->opts.poll_chunk) return fail("sweep_stream: PCG loop did not terminate");
+        for (int k = 0; k < h->opts.poll_chunk; ++k) {
+            if (emit_iteration(e, a)) return -1;
+            launched++;
+        }
+    }
+    h->stream_mode_iters += h->h_state->iter;
+    h->sweeps_host++;
+    return 0;
+}
+
+// ---- CUDA graph: [delta] [Told <- T] + sweeps x ( head, WHILE{iteration} ) ---------------------------------------------
 static bool same_opts(const hp_solve_opts& a, const hp_solve_opts& b) {
     return a.precond == b.precond && a.criterion == b.criterion && a.tol == b.tol && a.max_iter == b.max_iter &&
-           a.loop_mode == b.loop_mode && a.refactor_every == b.refactor_every && a.extrapolate == b.extrapolate;
+           a.loop_mode == b.loop_mode && a.refactor_every == b.refactor_every && a.extrapolate == b.extrapolate &&
+           a.mg_levels == b.mg_levels && a.mg_coarse_sweeps == b.mg_coarse_sweeps && a.mg_omega == b.mg_omega;
 }
 
 static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int update_old, GraphEntry** out) {
@@ -486,10 +621,11 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
             return 0;
         }
     if (h->graphs.size() >= 16) { CK(cudaStreamSynchronize(h->stream)); destroy_graphs(h); }
-    GraphEntry e;
-    e.dt = dt; e.sweeps = sweeps; e.has_old = has_old; e.update_old = update_old; e.opts = h->opts;
-    CK(cudaGraphCreate(&e.graph, 0));
-    NodeChain c{e.graph};
+    GraphEntry ge;
+    ge.dt = dt; ge.sweeps = sweeps; ge.has_old = has_old; ge.update_old = update_old; ge.opts = h->opts;
+    CK(cudaGraphCreate(&ge.graph, 0));
+    NodeChain c{ge.graph};
+    Emitter e{h, &c};
     HpDev& d = h->d;
     // update_old: 0 nothing, 1 Told <- T, 2 z <- T - Told (extrapolated start of the first solve) then Told <- T
     if (update_old == 2) {
@@ -499,60 +635,32 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
     }
     if (update_old) {
         cudaGraphNode_t n;
-        CK(cudaGraphAddMemcpyNode1D(&n, e.graph, c.last ? &c.last : nullptr, c.last ? 1 : 0, d.Told, d.T,
+        CK(cudaGraphAddMemcpyNode1D(&n, ge.graph, c.last ? &c.last : nullptr, c.last ? 1 : 0, d.Told, d.T,
                                     (size_t)(d.nz + 2) * d.nr * sizeof(double), cudaMemcpyDeviceToDevice));
         c.last = n;
     }
     for (int s = 0; s < sweeps; ++s) {
         HpKArgs a = make_args(h, dt, has_old);
-        void* params[] = {&d, &h->phys, &a};
-        if (h->phys.gamma == 1 && chain_kernel(c, hpk::desc_coef(h->cfg, d), params)) return -1;
-        int write_dinv = (h->opts.precond == 0) ? 1 : 0;
-        void* p4[] = {&d, &h->phys, &a, &write_dinv};
-        if (chain_kernel(c, hpk::desc_diag(h->cfg, d), p4)) return -1;
-        int kd = 0, ka = 1, kb = 2, ki = 3;          // FIN_* kinds of k_wait
-        void* pwd[] = {&d, &h->phys, &a, &kd};
-        if (h->nranks > 1 && chain_kernel(c, hpk::desc_wait(), pwd)) return -1;
-        if (h->opts.precond == 1 && (s % h->opts.refactor_every) == 0)
-            if (chain_kernel(c, hpk::desc_factor(h->cfg, d), params)) return -1;
         cudaGraphConditionalHandle cond;
-        CK(cudaGraphConditionalHandleCreate(&cond, e.graph, 0, cudaGraphCondAssignDefault));
+        CK(cudaGraphConditionalHandleCreate(&cond, ge.graph, 0, cudaGraphCondAssignDefault));
         a.use_cond = 1; a.cond = (unsigned long long)cond;
-        if (update_old == 2 && s == 0) {
-            HpKArgs as = a;
-            as.shift = 1;
-            void* ps[] = {&d, &h->phys, &as};
-            void* psa[] = {&d, &h->phys, &as, &ka};
-            void* psi[] = {&d, &h->phys, &as, &ki};
-            if (chain_kernel(c, hpk::desc_cg_A(h->cfg, d), ps, h)) return -1;
-            if (h->nranks > 1 && chain_kernel(c, hpk::desc_wait(), psa)) return -1;
-            if (chain_kernel(c, hpk::desc_cg_B(h->cfg, d, h->opts.precond, h->opts.criterion), ps, h)) return -1;
-            if (h->nranks > 1 && chain_kernel(c, hpk::desc_wait(), psi)) return -1;
-        } else {
-            if (chain_kernel(c, hpk::desc_cg_init(h->cfg, d, h->opts.precond, h->opts.criterion), params, h)) return -1;
-            void* pwi[] = {&d, &h->phys, &a, &ki};
-            if (h->nranks > 1 && chain_kernel(c, hpk::desc_wait(), pwi)) return -1;
-        }
+        if (emit_sweep_head(e, a, (s % h->opts.refactor_every) == 0, update_old == 2 && s == 0)) return -1;
         cudaGraphNodeParams cp{};
         cp.type = cudaGraphNodeTypeConditional;
         cp.conditional.handle = cond;
         cp.conditional.type = cudaGraphCondTypeWhile;
         cp.conditional.size = 1;
         cudaGraphNode_t wn;
-        CK(cudaGraphAddNode(&wn, e.graph, c.last ? &c.last : nullptr, c.last ? 1 : 0, &cp));
+        CK(cudaGraphAddNode(&wn, ge.graph, c.last ? &c.last : nullptr, c.last ? 1 : 0, &cp));
         c.last = wn;
         NodeChain body{cp.conditional.phGraph_out[0]};
-        void* pwa[] = {&d, &h->phys, &a, &ka};
-        void* pwb[] = {&d, &h->phys, &a, &kb};
-        if (chain_kernel(body, hpk::desc_cg_A(h->cfg, d), params, h)) return -1;
-        if (h->nranks > 1 && chain_kernel(body, hpk::desc_wait(), pwa)) return -1;
-        if (chain_kernel(body, hpk::desc_cg_B(h->cfg, d, h->opts.precond, h->opts.criterion), params, h)) return -1;
-        if (h->nranks > 1 && chain_kernel(body, hpk::desc_wait(), pwb)) return -1;
-        e.body_nodes = body.count;
+        Emitter eb{h, &body};
+        if (emit_iteration(eb, a)) return -1;
+        ge.body_nodes = body.count;
     }
-    e.static_nodes = c.count;
-    CK(cudaGraphInstantiate(&e.exec, e.graph, 0));
-    h->graphs.push_back(e);
+    ge.static_nodes = c.count;
+    CK(cudaGraphInstantiate(&ge.exec, ge.graph, 0));
+    h->graphs.push_back(ge);
     *out = &h->graphs.back();
     return 0;
 }

@@ -9,7 +9,7 @@
 #define HP_NRED 4                // reduced values per kernel
 
 #define HP_MAX_RANKS 16
-enum { HP_COMM_DIAG = 0, HP_COMM_A = 1, HP_COMM_B = 2, HP_COMM_KINDS = 3 };
+enum { HP_COMM_DIAG = 0, HP_COMM_A = 1, HP_COMM_B = 2, HP_COMM_MG = 3, HP_COMM_KINDS = 4 };
 
 // Peer-memory mailbox of one rank (cudaMalloc'ed, IPC-mapped into every peer of the box over NVLink).
 // red[kind][src] / flag[kind][src] are WRITTEN BY rank `src` (remote stores from its reducing kernel) and read locally.
@@ -23,6 +23,8 @@ struct HpState {
     double alpha, beta, rz, pq, crit, rr, res2, b2;
     int32_t iter;        // PCG iterations of the current sweep
     int32_t done;        // 1 -> remaining (A,B) launches of this sweep are no-ops
+    int32_t mg_skip;     // 1 -> the V-cycle kernels of this iteration return immediately (k_cg_B found convergence)
+    int32_t _pad0;
     int32_t first;       // 1 -> next direction update uses beta = 0 (p := z)
     int32_t parity;      // which p buffer holds the current search direction
     int32_t flags;       // hp_sweep_stat.flags of the current sweep
@@ -71,6 +73,26 @@ struct HpDev {
     double* red_all;         // [nranks * HP_NRED]
 };
 
+// One level of the axially semi-coarsened hierarchy of the 'mgline' preconditioner (rows are aggregated in pairs,
+// radial lines stay whole; every level keeps the 5-point structure and the ghost-row layout of the fine fields).
+#define HP_MAX_LEVELS 12
+struct HpLevel {
+    int nz;                              // owned rows of this level
+    double *cR, *cZ, *diag, *dinv;       // operator (Galerkin, piecewise-constant aggregation) + line pivots
+    double *rhs, *x, *x2, *tmp;          // right-hand side, correction, prolonged correction, residual scratch
+};
+
+struct HpLevelSet { int n; HpLevel lev[HP_MAX_LEVELS]; };
+
+// arguments of k_mg_res / k_mg_line (hp_kernels.cu)
+struct HpMgResArgs {
+    const double* xin; const double* ec; double* xout; double* resout; double* crhs;
+    double scale; int nzc;
+};
+struct HpMgLineArgs {
+    const double* rhs; const double* base; double* out; int final_;
+};
+
 // Per-launch scalar arguments shared by all kernels: signature (HpDev, hp_phys, HpKArgs [, extra]).
 struct HpKArgs {
     double dt;
@@ -80,6 +102,10 @@ struct HpKArgs {
     int32_t criterion;
     int32_t use_cond;
     int32_t prefetch;          // bit0: k_cg_A, bit1: k_cg_B issue bulk L2 prefetches of the next row
+    int32_t mg;                // 1: 'mgline' preconditioner: k_cg_B only decides convergence, the V-cycle's last kernel
+                               //    produces z, r.z and advances the recurrences
+    int32_t init_phase;        // 1: this kernel sits in the INIT position of the sweep (no beta, iteration count kept)
+    double omega;              // damping of the line smoother in the V-cycle
     int32_t shift;             // 1: this (A, B) pair moves the start of the solve to x0 + z (z = extrapolated increment):
                                //    alpha := 1, and k_cg_B finalises like the INIT kernel
     unsigned long long cond;   // cudaGraphConditionalHandle of the enclosing WHILE node (use_cond != 0)
@@ -116,6 +142,11 @@ HpKernelLaunch desc_diag(const HpLaunchCfg&, const HpDev&);
 HpKernelLaunch desc_factor(const HpLaunchCfg&, const HpDev&);
 HpKernelLaunch desc_cg_init(const HpLaunchCfg&, const HpDev&, int precond, int criterion);
 HpKernelLaunch desc_cg_A(const HpLaunchCfg&, const HpDev&);
+// 'mgline' V-cycle pieces (argument lists next to the kernels in hp_kernels.cu)
+HpKernelLaunch desc_mg_coarsen(const HpLaunchCfg&, int nzc, int nr);
+HpKernelLaunch desc_mg_res(const HpLaunchCfg&, int nz_level);
+HpKernelLaunch desc_mg_line(const HpLaunchCfg&, int nz_level);
+HpKernelLaunch desc_factor_levels(int total_coarse_rows);   // args: (HpLevelSet, int nr, const int* skip)
 HpKernelLaunch desc_wait();       // args: (HpDev, hp_phys, HpKArgs, int kind): peer-memory variant of finalize
 HpKernelLaunch desc_finalize();   // args: (HpDev, hp_phys, HpKArgs, int kind) kind: 0 diag, 1 A, 2 B, 3 init
 HpKernelLaunch desc_cg_B(const HpLaunchCfg&, const HpDev&, int precond, int criterion);

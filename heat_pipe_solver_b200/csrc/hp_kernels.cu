@@ -147,13 +147,13 @@ __device__ __forceinline__ bool converged(const HpKArgs& a, double crit, double 
 // scalar recurrences of the sweep / PCG, executed by ONE thread per kernel: the last CTA of the producing
 // kernel (single GPU) or k_finalize after the all-gather of the per-rank sums (axial slabs).
 // ------------------------------------------------------------------------------------------------
-enum { FIN_DIAG = 0, FIN_A = 1, FIN_B = 2, FIN_INIT = 3 };
+enum { FIN_DIAG = 0, FIN_A = 1, FIN_B = 2, FIN_INIT = 3, FIN_MGFINAL = 4 };
 
 __device__ __forceinline__ void finalize_diag(const HpDev& d, const HpKArgs& a, double res2, double b2) {
     HpState* s = d.st;
     s->res2 = res2;
     s->b2 = b2;
-    s->iter = 0; s->done = 0; s->first = 1; s->flags &= 8;      // bit3 (a peer never arrived) is sticky
+    s->iter = 0; s->done = 0; s->mg_skip = 0; s->first = 1; s->flags &= 8;      // bit3 (a peer never arrived) is sticky
     hp_sweep_stat* stt = &d.stats[s->sweep_count % HP_STATS_CAP];
     stt->residual_l2 = sqrt(res2);
     stt->rhs_l2 = sqrt(b2);
@@ -176,27 +176,39 @@ __device__ __forceinline__ void finalize_A(const HpDev& d, const HpKArgs& a, dou
     s->first = 0;
 }
 
-__device__ __forceinline__ void finalize_B(const HpDev& d, const HpKArgs& a, bool init, double rz_new, double rr, double crit) {
+// stage 0: plain PCG (k_cg_B produced z = M^-1 r and r.z).  'mgline': stage 1 after k_cg_B (x, r updated, the
+// line-preconditioned residual measures convergence; the V-cycle only runs if the solve goes on), stage 2 after the
+// last kernel of the V-cycle (z and r.z are final: beta / rz recurrences).
+__device__ __forceinline__ void finalize_B(const HpDev& d, const HpKArgs& a, bool init, double rz_new, double rr, double crit,
+                                           int stage = 0) {
     HpState* s = d.st;
     int flags = s->flags;
     int done = 0;
-    if (init) {
-        s->rz = rz_new;
-        s->parity = 0;
-        s->first = 1;
-    } else {
-        s->beta = (s->rz != 0.0) ? rz_new / s->rz : 0.0;
-        s->rz = rz_new;
-        s->iter += 1;
-        s->total_iters += 1;
+    hp_sweep_stat* stt = &d.stats[(s->sweep_count - 1) % HP_STATS_CAP];
+    if (stage != 1) {
+        if (init) {
+            s->rz = rz_new;
+            s->parity = 0;
+            s->first = 1;
+        } else {
+            s->beta = (s->rz != 0.0) ? rz_new / s->rz : 0.0;
+            s->rz = rz_new;
+        }
     }
-    s->rr = rr; s->crit = crit;
-    const bool nan_bad = !(isfinite(rz_new) && isfinite(crit));
+    if (stage != 2) {
+        if (!init) { s->iter += 1; s->total_iters += 1; }
+        s->rr = rr; s->crit = crit;
+    }
+    if (stage == 2) {
+        if (!isfinite(rz_new)) { flags |= 4; s->done = 1; s->flags = flags; stt->flags = flags; set_cond(a, 0); }
+        return;
+    }
+    const bool nan_bad = !(isfinite(crit) && (stage == 1 || isfinite(rz_new)));
     if (converged(a, crit, rr, s->b2)) { done = 1; flags |= 1; }
     else if (nan_bad || (flags & 4)) { done = 1; flags |= 4; }
     else if (s->iter >= a.max_iter) { done = 1; flags |= 2; }
     s->done = done; s->flags = flags;
-    hp_sweep_stat* stt = &d.stats[(s->sweep_count - 1) % HP_STATS_CAP];
+    s->mg_skip = done;
     stt->crit = (a.criterion == 2) ? sqrt(rr) : crit;
     stt->iters = s->iter;
     stt->flags = flags;
@@ -243,9 +255,10 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // the same kernel sequence), then lane 0 combines the sums in rank order and advances the scalar recurrences.
 // A bounded wait (2 s): on timeout the sweep is aborted with flags bit3 instead of hanging the GPU.
 __global__ void k_wait(HpDev d, hp_phys ph, HpKArgs a, int fin_kind) {
-    const int kind = (fin_kind == FIN_DIAG) ? HP_COMM_DIAG : (fin_kind == FIN_A ? HP_COMM_A : HP_COMM_B);
+    const int kind = (fin_kind == FIN_DIAG) ? HP_COMM_DIAG : (fin_kind == FIN_A ? HP_COMM_A : (fin_kind == FIN_MGFINAL ? HP_COMM_MG : HP_COMM_B));
     HpState* s = d.st;
     if ((fin_kind == FIN_A || fin_kind == FIN_B) && s->done) return;
+    if (fin_kind == FIN_MGFINAL && s->mg_skip) return;
     const int lane = threadIdx.x;
     const HpComm* mine = d.comm_peer[d.rank];
     const unsigned long long want = d.seq[kind];
@@ -263,12 +276,13 @@ __global__ void k_wait(HpDev d, hp_phys ph, HpKArgs a, int fin_kind) {
     for (int r = 0; r < d.nranks; ++r) {
         const volatile double* p = mine->red[kind][r];
         if (fin_kind == FIN_DIAG) { v[0] += p[0]; v[1] += p[1]; }
-        else if (fin_kind == FIN_A) { v[0] += p[0]; }
+        else if (fin_kind == FIN_A || fin_kind == FIN_MGFINAL) { v[0] += p[0]; }
         else { v[0] += p[0]; v[1] += p[1]; v[2] = fmax(v[2], p[2]); }
     }
     if (fin_kind == FIN_DIAG) finalize_diag(d, a, v[0], v[1]);
     else if (fin_kind == FIN_A) finalize_A(d, a, v[0]);
-    else finalize_B(d, a, fin_kind == FIN_INIT || a.shift, v[0], v[1], v[2]);
+    else if (fin_kind == FIN_MGFINAL) finalize_B(d, a, a.init_phase != 0, v[0], 0.0, 0.0, 2);
+    else finalize_B(d, a, fin_kind == FIN_INIT || a.shift, v[0], v[1], v[2], a.mg ? 1 : 0);
     if (bad || (s->flags & 8)) {          // a peer never arrived: stop this sweep, make the failure sticky
         s->flags |= 8; s->done = 1;
         d.stats[(s->sweep_count - 1) % HP_STATS_CAP].flags |= 8;
@@ -279,17 +293,19 @@ __global__ void k_wait(HpDev d, hp_phys ph, HpKArgs a, int fin_kind) {
 __global__ void k_finalize(HpDev d, hp_phys ph, HpKArgs a, int kind) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if ((kind == FIN_A || kind == FIN_B) && d.st->done) return;
+    if (kind == FIN_MGFINAL && d.st->mg_skip) return;
     double v[HP_NRED];
     for (int k = 0; k < HP_NRED; ++k) v[k] = 0.0;
     for (int r = 0; r < d.nranks; ++r) {           // fixed rank order: every rank computes identical scalars
         const double* p = d.red_all + r * HP_NRED;
         if (kind == FIN_DIAG) { v[0] += p[0]; v[1] += p[1]; }
-        else if (kind == FIN_A) { v[0] += p[0]; }
+        else if (kind == FIN_A || kind == FIN_MGFINAL) { v[0] += p[0]; }
         else { v[0] += p[0]; v[1] += p[1]; v[2] = fmax(v[2], p[2]); }
     }
     if (kind == FIN_DIAG) finalize_diag(d, a, v[0], v[1]);
     else if (kind == FIN_A) finalize_A(d, a, v[0]);
-    else finalize_B(d, a, kind == FIN_INIT || a.shift, v[0], v[1], v[2]);
+    else if (kind == FIN_MGFINAL) finalize_B(d, a, a.init_phase != 0, v[0], 0.0, 0.0, 2);
+    else finalize_B(d, a, kind == FIN_INIT || a.shift, v[0], v[1], v[2], a.mg ? 1 : 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -428,15 +444,9 @@ __global__ void __launch_bounds__(256) k_diag(HpDev d, hp_phys ph, HpKArgs a, in
 // A nonlinear first-order recurrence, so rows are the parallel axis; loads of the next block are issued
 // before the dependent chain of the current one.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_factor_rline(HpDev d, hp_phys ph, HpKArgs a) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= d.nz) return;
-    const long long base = (long long)(j + 1) * d.nr;
-    const double* __restrict__ dg = d.diag + base;
-    const double* __restrict__ cr = d.cR + base;
-    double* __restrict__ out = d.dinv + base;
+__device__ __forceinline__ void factor_row(const double* __restrict__ dg, const double* __restrict__ cr,
+                                           double* __restrict__ out, int nr) {
     double prev = 0.0;    // cR_{i-1}^2 * dinv_{i-1}
-    const int nr = d.nr;
     constexpr int B = 8;
     double db[B], cb[B];
     int i = 0;
@@ -476,6 +486,13 @@ __global__ void __launch_bounds__(32) k_factor_rline(HpDev d, hp_phys ph, HpKArg
     }
 }
 
+__global__ void __launch_bounds__(32) k_factor_rline(HpDev d, hp_phys ph, HpKArgs a) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d.nz) return;
+    const long long base = (long long)(j + 1) * d.nr;
+    factor_row(d.diag + base, d.cR + base, d.dinv + base, d.nr);
+}
+
 // ------------------------------------------------------------------------------------------------
 // marching "row team" kernels.  A team of TPL threads owns whole rows (EPT consecutive cells per thread,
 // TPL*EPT >= nr) and walks a contiguous block of rows.
@@ -498,6 +515,80 @@ __device__ __forceinline__ void team_barrier(int team_in_cta) {
     } else {
         __syncwarp();
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// z = M^-1 r on one row held by a team (EPT cells per thread): two affine first-order scans over the precomputed
+// pivots,  y_i = r_i + (cR_{i-1} dinv_{i-1}) y_{i-1} ,  z_i = dinv_i y_i + (cR_i dinv_i) z_{i+1}.
+// Thread-local composition, warp shuffle scan, <= 32 warp totals through shared memory (one team barrier per
+// direction).  m0_edge = cR_{i0-1} dinv_{i0-1} for lane 0 of every warp but the first (fetched with the row loads).
+// ------------------------------------------------------------------------------------------------
+template <int TPL, int EPT>
+__device__ __forceinline__ void line_solve(const double (&rv)[EPT], const double (&dv)[EPT], const double (&cr)[EPT],
+                                           double m0_edge, int lane, int wt, int team_in_cta, double* s_fA, double* s_fB,
+                                           double* s_bA, double* s_bB, double (&zv)[EPT]) {
+    constexpr int NW = TPL / 32;
+    double nb[EPT];     // cR_i * dinv_i : backward multiplier of cell i, forward multiplier of cell i+1
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) nb[e] = cr[e] * dv[e];
+    double m0 = __shfl_up_sync(0xffffffffu, nb[EPT - 1], 1);
+    if (lane == 0) m0 = m0_edge;
+    double Pe[EPT], ye[EPT];
+    {
+        double P = 1.0, y = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const double m = (e == 0) ? m0 : nb[e - 1];
+            y = fma(m, y, rv[e]);
+            P *= m;
+            Pe[e] = P; ye[e] = y;
+        }
+    }
+    double A = Pe[EPT - 1], B = ye[EPT - 1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double Ap = __shfl_up_sync(0xffffffffu, A, o);
+        const double Bp = __shfl_up_sync(0xffffffffu, B, o);
+        if (lane >= o) { B = fma(A, Bp, B); A *= Ap; }
+    }
+    double Ax = __shfl_up_sync(0xffffffffu, A, 1), Bx = __shfl_up_sync(0xffffffffu, B, 1);
+    if (lane == 0) { Ax = 1.0; Bx = 0.0; }
+    double carry = 0.0;
+    if constexpr (NW > 1) {
+        if (lane == 31) { s_fA[wt] = A; s_fB[wt] = B; }
+        team_barrier<TPL>(team_in_cta);
+        for (int w = 0; w < wt; ++w) carry = fma(s_fA[w], carry, s_fB[w]);
+    }
+    const double ybefore = fma(Ax, carry, Bx);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) ye[e] = fma(Pe[e], ybefore, ye[e]);
+    {
+        double Q = 1.0, zz = 0.0;
+#pragma unroll
+        for (int e = EPT - 1; e >= 0; --e) {
+            zz = fma(nb[e], zz, dv[e] * ye[e]);
+            Q *= nb[e];
+            Pe[e] = Q; zv[e] = zz;
+        }
+    }
+    A = Pe[0]; B = zv[0];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double Ap = __shfl_down_sync(0xffffffffu, A, o);
+        const double Bp = __shfl_down_sync(0xffffffffu, B, o);
+        if (lane + o < 32) { B = fma(A, Bp, B); A *= Ap; }
+    }
+    Ax = __shfl_down_sync(0xffffffffu, A, 1); Bx = __shfl_down_sync(0xffffffffu, B, 1);
+    if (lane == 31) { Ax = 1.0; Bx = 0.0; }
+    carry = 0.0;
+    if constexpr (NW > 1) {
+        if (lane == 0) { s_bA[wt] = A; s_bB[wt] = B; }
+        team_barrier<TPL>(team_in_cta);
+        for (int w = NW - 1; w > wt; --w) carry = fma(s_bA[w], carry, s_bB[w]);
+    }
+    const double zafter = fma(Ax, carry, Bx);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) zv[e] = fma(Pe[e], zafter, zv[e]);
 }
 
 // ---- k_cg_A -------------------------------------------------------------------------------------
@@ -687,72 +778,11 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT)
 #pragma unroll
             for (int e = 0; e < EPT; ++e) zv[e] = rv[e] * dv[e];
         } else {
-            // ---------------- forward scan ----------------
-            double nb[EPT];     // cR_i * dinv_i : backward multiplier of cell i, forward multiplier of cell i+1
-#pragma unroll
-            for (int e = 0; e < EPT; ++e) nb[e] = cr[e] * dv[e];
-            double m0 = __shfl_up_sync(0xffffffffu, nb[EPT - 1], 1);
-            if (lane == 0) m0 = m0_edge;
-            double Pe[EPT], ye[EPT];
-            {
-                double P = 1.0, y = 0.0;
-#pragma unroll
-                for (int e = 0; e < EPT; ++e) {
-                    const double m = (e == 0) ? m0 : nb[e - 1];
-                    y = fma(m, y, rv[e]);
-                    P *= m;
-                    Pe[e] = P; ye[e] = y;
-                }
-            }
-            double A = Pe[EPT - 1], B = ye[EPT - 1];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double Ap = __shfl_up_sync(0xffffffffu, A, o);
-                const double Bp = __shfl_up_sync(0xffffffffu, B, o);
-                if (lane >= o) { B = fma(A, Bp, B); A *= Ap; }
-            }
-            double Ax = __shfl_up_sync(0xffffffffu, A, 1), Bx = __shfl_up_sync(0xffffffffu, B, 1);
-            if (lane == 0) { Ax = 1.0; Bx = 0.0; }
-            double carry = 0.0;
-            if constexpr (G::NW > 1) {
-                if (lane == 31) { s_fA[team_in_cta][wt] = A; s_fB[team_in_cta][wt] = B; }
-                team_barrier<TPL>(team_in_cta);
-                for (int w = 0; w < wt; ++w) carry = fma(s_fA[team_in_cta][w], carry, s_fB[team_in_cta][w]);
-            }
-            const double ybefore = fma(Ax, carry, Bx);
-#pragma unroll
-            for (int e = 0; e < EPT; ++e) ye[e] = fma(Pe[e], ybefore, ye[e]);
-            // ---------------- backward scan ----------------
-            {
-                double Q = 1.0, zz = 0.0;
-#pragma unroll
-                for (int e = EPT - 1; e >= 0; --e) {
-                    zz = fma(nb[e], zz, dv[e] * ye[e]);
-                    Q *= nb[e];
-                    Pe[e] = Q; zv[e] = zz;
-                }
-            }
-            A = Pe[0]; B = zv[0];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double Ap = __shfl_down_sync(0xffffffffu, A, o);
-                const double Bp = __shfl_down_sync(0xffffffffu, B, o);
-                if (lane + o < 32) { B = fma(A, Bp, B); A *= Ap; }
-            }
-            Ax = __shfl_down_sync(0xffffffffu, A, 1); Bx = __shfl_down_sync(0xffffffffu, B, 1);
-            if (lane == 31) { Ax = 1.0; Bx = 0.0; }
-            carry = 0.0;
-            if constexpr (G::NW > 1) {
-                if (lane == 0) { s_bA[team_in_cta][wt] = A; s_bB[team_in_cta][wt] = B; }
-                team_barrier<TPL>(team_in_cta);
-                for (int w = G::NW - 1; w > wt; --w) carry = fma(s_bA[team_in_cta][w], carry, s_bB[team_in_cta][w]);
-            }
-            const double zafter = fma(Ax, carry, Bx);
-#pragma unroll
-            for (int e = 0; e < EPT; ++e) zv[e] = fma(Pe[e], zafter, zv[e]);
+            line_solve<TPL, EPT>(rv, dv, cr, m0_edge, lane, wt, team_in_cta, s_fA[team_in_cta], s_fB[team_in_cta],
+                                 s_bA[team_in_cta], s_bB[team_in_cta], zv);
         }
         store_row<EPT, VEC>(d.z + rb, i0, nr, zv);
-        if (d.p2p) {            // halo of the preconditioned residual, fused into its producer
+        if (d.p2p && !a.mg) {   // halo of the preconditioned residual, fused into its producer
             if (g == 1 && d.z_lo) store_row<EPT, VEC>(d.z_lo, i0, nr, zv);
             if (g == nz && d.z_hi) store_row<EPT, VEC>(d.z_hi, i0, nr, zv);
         }
@@ -773,7 +803,7 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT)
     double tot[3];
     if (cta_publish<3>(acc, 4u, d.partials, &d.st->ticket, tot, d.p2p != 0) && threadIdx.x == 0) {
         if (d.nranks > 1) stash_local<3>(d, tot, HP_COMM_B);
-        else finalize_B(d, a, INIT || a.shift, tot[0], tot[1], tot[2]);
+        else finalize_B(d, a, INIT || a.shift, tot[0], tot[1], tot[2], a.mg ? 1 : 0);
     }
 }
 
@@ -836,6 +866,222 @@ __global__ void __launch_bounds__(256) k_delta(HpDev d, hp_phys ph, HpKArgs a) {
     const long long n = (long long)(d.nz + 2) * d.nr;
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x)
         d.z[c] = d.T[c] - d.Told[c];
+}
+
+
+// ================================================================================================
+// 'mgline' preconditioner: V(1,1) cycle, axial semi-coarsening (row pairs), damped radial-line Jacobi smoother.
+// The radial stiffness is removed exactly by the line solves on every level; coarsening the axial index removes the
+// axial stiffness that makes plain line-PCG need O(sqrt(D)) iterations (D = axial diffusion number of a cell).
+// Galerkin operators with piecewise-constant aggregation stay 5-point, so every level reuses the same row kernels.
+// Rank-local under slabs (ghost couplings are ignored inside the cycle): no communication in the preconditioner.
+// ================================================================================================
+
+// coarse level from a fine one:  cR_c = cR[2J] + cR[2J+1],  cZ_c = coupling of the pair's top row to the next pair,
+// diag_c = diag[2J] + diag[2J+1] - 2 cZ[2J]  (P^T A P with P = row-pair injection).      thread per coarse cell
+__global__ void __launch_bounds__(256) k_mg_coarsen(HpLevel f, HpLevel c, int nr, const int* skip) {
+    if (*skip) return;
+    const long long n = (long long)c.nz * nr;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int J = (int)(t / nr), i = (int)(t - (long long)J * nr);
+        const long long g0 = (long long)(2 * J + 1) * nr + i, g1 = g0 + nr;
+        const bool two = (2 * J + 1) < f.nz;
+        const long long gc = (long long)(J + 1) * nr + i;
+        const double inner = two ? f.cZ[g0] : 0.0;
+        c.cR[gc] = f.cR[g0] + (two ? f.cR[g1] : 0.0);
+        c.cZ[gc] = (J == c.nz - 1) ? 0.0 : (two ? f.cZ[g1] : f.cZ[g0]);        // rank-local: nothing beyond the last pair
+        c.diag[gc] = f.diag[g0] + (two ? f.diag[g1] - 2.0 * inner : 0.0);
+    }
+}
+
+// ---- k_mg_res : residual of one level, optionally with the coarse correction prolonged on load and / or the
+// residual restricted to the next level on store.  Same marching, column-tiled, barrier-free structure as k_cg_A.
+//   x(g)   = scale * xin(g) [+ ec(pair of g)]                          (PROLONG)
+//   res(g) = rhs(g) - (diag x - cR x_e - cR_w x_w - cZ x_n - cZ_s x_s) (couplings to ghost rows ignored)
+//   xout(g) = x(g) if xout;  resout(g) = res(g) if resout;  crhs(J) = res(2J) + res(2J+1) if crhs (RESTRICT)
+template <int TPL, int EPT, bool VEC>
+__global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_A(EPT))
+k_mg_res(HpDev d, HpKArgs a, HpLevel L, HpMgResArgs m) {
+    using G = TeamGeom<TPL>;
+    if (d.st->mg_skip) return;
+    const int nr = d.nr, nz = L.nz;
+    const int team_in_cta = threadIdx.x / TPL, tl = threadIdx.x % TPL, lane = threadIdx.x & 31;
+    const long long team = (long long)blockIdx.x * G::LPC + team_in_cta, nteams = (long long)gridDim.x * G::LPC;
+    const int ncol = d.ncolA;
+    const long long nchunks = nteams / ncol;
+    const long long chunk = team / ncol;
+    const int i0 = ((int)(team % ncol) * TPL + tl) * EPT;
+    // chunks are made of whole row pairs so that a restricted row is produced by one team
+    const long long npairs = (nz + 1) / 2;
+    int ja = 0, jb = 0;
+    if (chunk < nchunks) {
+        ja = (int)(2 * (chunk * npairs / nchunks));
+        jb = (int)(2 * ((chunk + 1) * npairs / nchunks));
+        if (jb > nz) jb = nz;
+    }
+    const bool has_l = (lane == 0) && (i0 != 0) && (i0 < nr);
+    const bool has_r = (lane == 31) && (i0 + EPT < nr);
+    const bool prolong = m.ec != nullptr;
+    const double scale = m.scale;
+    auto crow = [&](int g) {                       // coarse ghost-inclusive row of fine row g (clamped at the ends)
+        int J = (g - 1) >> 1;
+        J = J < 0 ? 0 : (J > m.nzc - 1 ? m.nzc - 1 : J);
+        return (long long)(J + 1) * nr;
+    };
+    auto xrow = [&](int g, double (&out)[EPT]) {
+        load_row<EPT, VEC>(m.xin + (long long)g * nr, i0, nr, out);
+        if (prolong) {
+            double e[EPT];
+            load_row<EPT, VEC>(m.ec + crow(g), i0, nr, e);
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) out[k] = fma(scale, out[k], e[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) out[k] *= scale;
+        }
+    };
+    auto xat = [&](int g, int i) -> double {
+        double v = scale * m.xin[(long long)g * nr + i];
+        if (prolong) v += m.ec[crow(g) + i];
+        return v;
+    };
+    if (jb > ja) {
+        double xm[EPT], xc[EPT], xn[EPT], czm[EPT], rprev[EPT];
+        double xc_l = 0.0, xc_r = 0.0;
+        xrow(ja, xm);
+        xrow(ja + 1, xc);
+        if (has_l) xc_l = xat(ja + 1, i0 - 1);
+        if (has_r) xc_r = xat(ja + 1, i0 + EPT);
+        load_row<EPT, VEC>(L.cZ + (long long)ja * nr, i0, nr, czm);
+        if (ja == 0) {
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) czm[k] = 0.0;        // rank-local: no coupling to the lower ghost row
+        }
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) rprev[k] = 0.0;
+        for (int g = ja + 1; g <= jb; ++g) {
+            const long long rb = (long long)g * nr;
+            double cr[EPT], cz[EPT], dg[EPT], rh[EPT];
+            xrow(g + 1, xn);
+            load_row<EPT, VEC>(L.cR + rb, i0, nr, cr);
+            load_row<EPT, VEC>(L.cZ + rb, i0, nr, cz);
+            load_row<EPT, VEC>(L.diag + rb, i0, nr, dg);
+            load_row<EPT, VEC>(L.rhs + rb, i0, nr, rh);
+            double xn_l = 0.0, xn_r = 0.0, crl_e = 0.0;
+            if (has_l) { xn_l = xat(g + 1, i0 - 1); crl_e = L.cR[rb + i0 - 1]; }
+            if (has_r) xn_r = xat(g + 1, i0 + EPT);
+            if (g == nz) {
+#pragma unroll
+                for (int k = 0; k < EPT; ++k) cz[k] = 0.0;     // rank-local: no coupling to the upper ghost row
+            }
+            double xl = __shfl_up_sync(0xffffffffu, xc[EPT - 1], 1);
+            double crl = __shfl_up_sync(0xffffffffu, cr[EPT - 1], 1);
+            double xr = __shfl_down_sync(0xffffffffu, xc[0], 1);
+            if (lane == 0) { xl = xc_l; crl = crl_e; }
+            if (lane == 31) xr = xc_r;
+            double res[EPT];
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                const double left = (k == 0) ? xl : xc[k - 1];
+                const double cleft = (k == 0) ? crl : cr[k - 1];
+                const double right = (k == EPT - 1) ? xr : xc[(k + 1) % EPT];
+                double t = dg[k] * xc[k];
+                t = fma(-cr[k], right, t);
+                t = fma(-cleft, left, t);
+                t = fma(-cz[k], xn[k], t);
+                t = fma(-czm[k], xm[k], t);
+                res[k] = rh[k] - t;
+            }
+            if (m.xout) store_row<EPT, VEC>(m.xout + rb, i0, nr, xc);
+            if (m.resout) store_row<EPT, VEC>(m.resout + rb, i0, nr, res);
+            if (m.crhs) {
+                const bool second = ((g - 1) & 1) != 0;
+                if (second || g == nz) {
+                    double sum[EPT];
+#pragma unroll
+                    for (int k = 0; k < EPT; ++k) sum[k] = second ? rprev[k] + res[k] : res[k];
+                    store_row<EPT, VEC>(m.crhs + (long long)(((g - 1) >> 1) + 1) * nr, i0, nr, sum);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < EPT; ++k) rprev[k] = res[k];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) { xm[k] = xc[k]; xc[k] = xn[k]; czm[k] = cz[k]; }
+            xc_l = xn_l; xc_r = xn_r;
+        }
+    }
+}
+
+// ---- k_mg_line : out(g) = [base(g) +] omega * M_L^-1 rhs(g)       (row teams, same line solve as k_cg_B)
+// FINAL (level 0, end of the V-cycle): out is the preconditioned residual z of the PCG; accumulates r.z, pushes the
+// boundary rows under peer-memory slabs, and the last CTA advances beta / rz (finalize_B stage 2).
+template <int TPL, int EPT, bool VEC>
+__global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT))
+k_mg_line(HpDev d, HpKArgs a, HpLevel L, HpMgLineArgs m) {
+    using G = TeamGeom<TPL>;
+    if (d.st->mg_skip) return;
+    __shared__ double s_fA[G::LPC][G::NW], s_fB[G::LPC][G::NW], s_bA[G::LPC][G::NW], s_bB[G::LPC][G::NW];
+    const int nr = d.nr, nz = L.nz;
+    const int team_in_cta = threadIdx.x / TPL, tl = threadIdx.x % TPL, lane = threadIdx.x & 31;
+    const int wt = tl >> 5;
+    const int i0 = tl * EPT;
+    const long long team = (long long)blockIdx.x * G::LPC + team_in_cta, nteams = (long long)gridDim.x * G::LPC;
+    const int ja = (int)(team * nz / nteams), jb = (int)((team + 1) * nz / nteams);
+    const double omega = a.omega;
+    double acc[1] = {0.0};
+    for (int g = ja + 1; g <= jb; ++g) {
+        const long long rb = (long long)g * nr;
+        double rv[EPT], dv[EPT], cr[EPT], zv[EPT];
+        [[maybe_unused]] double bs[EPT], r0[EPT];
+        load_row<EPT, VEC>(m.rhs + rb, i0, nr, rv);
+        load_row<EPT, VEC>(L.dinv + rb, i0, nr, dv);
+        load_row<EPT, VEC>(L.cR + rb, i0, nr, cr);
+        if (m.base) load_row<EPT, VEC>(m.base + rb, i0, nr, bs);
+        if (m.final_) load_row<EPT, VEC>(d.r + rb, i0, nr, r0);
+        double m0_edge = 0.0;
+        if (lane == 0 && tl != 0 && i0 < nr) m0_edge = L.cR[rb + i0 - 1] * L.dinv[rb + i0 - 1];
+        line_solve<TPL, EPT>(rv, dv, cr, m0_edge, lane, wt, team_in_cta, s_fA[team_in_cta], s_fB[team_in_cta],
+                             s_bA[team_in_cta], s_bB[team_in_cta], zv);
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) zv[k] = m.base ? fma(omega, zv[k], bs[k]) : omega * zv[k];
+        store_row<EPT, VEC>(m.out + rb, i0, nr, zv);
+        if (m.final_) {
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) acc[0] = fma(r0[k], zv[k], acc[0]);
+            if (d.p2p) {
+                if (g == 1 && d.z_lo) store_row<EPT, VEC>(d.z_lo, i0, nr, zv);
+                if (g == nz && d.z_hi) store_row<EPT, VEC>(d.z_hi, i0, nr, zv);
+            }
+        }
+    }
+    if (m.final_) {
+        double tot[1];
+        if (cta_publish<1>(acc, 0u, d.partials, &d.st->ticket, tot, d.p2p != 0) && threadIdx.x == 0) {
+            if (d.nranks > 1) stash_local<1>(d, tot, HP_COMM_MG);
+            else finalize_B(d, a, a.init_phase != 0, tot[0], 0.0, 0.0, 2);
+        }
+    }
+}
+
+template <int TPL, int EPT, bool VEC>
+const void* fn_mg_res() { return (const void*)k_mg_res<TPL, EPT, VEC>; }
+template <int TPL, int EPT, bool VEC>
+const void* fn_mg_line() { return (const void*)k_mg_line<TPL, EPT, VEC>; }
+
+// pivots of ALL coarse levels in one launch (thread per row of any level: the recurrence is a serial chain of nr
+// steps whatever the row count, so one launch costs the same latency as one level alone)
+__global__ void __launch_bounds__(32) k_factor_levels(HpLevelSet ls, int nr, const int* skip) {
+    if (*skip) return;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int l = 1; l < ls.n; ++l) {
+        if (j < ls.lev[l].nz) {
+            const long long base = (long long)(j + 1) * nr;
+            factor_row(ls.lev[l].diag + base, ls.lev[l].cR + base, ls.lev[l].dinv + base, nr);
+            return;
+        }
+        j -= ls.lev[l].nz;
+    }
 }
 
 // ---- instantiation table -----------------------------------------------------------------------
@@ -947,6 +1193,32 @@ HpKernelLaunch desc_diag(const HpLaunchCfg& c, const HpDev& d) {
 }
 HpKernelLaunch desc_factor(const HpLaunchCfg& c, const HpDev& d) {
     return {(const void*)k_factor_rline, dim3(c.grid_factor), dim3(c.cta_factor), 0};
+}
+HpKernelLaunch desc_mg_coarsen(const HpLaunchCfg& c, int nzc, int nr) {
+    long long g = ((long long)nzc * nr + 255) / 256;
+    long long cap = (long long)c.num_sms * 8;
+    return {(const void*)k_mg_coarsen, dim3((unsigned)(g < cap ? (g < 1 ? 1 : g) : cap)), dim3(256), 0};
+}
+HpKernelLaunch desc_mg_res(const HpLaunchCfg& c, int nz_level) {
+    const void* f = nullptr;
+#define HP_X(T, E, V) f = fn_mg_res<T, E, V>()
+    HP_DISPATCH_A(c, HP_X);
+#undef HP_X
+    HpLaunchCfg cl = c;
+    cl.nz = (nz_level + 1) / 2;                      // chunks are whole row pairs
+    return {f, dim3(team_grid(f, cl, c.ctaA, c.teams_per_ctaA, c.ncolA)), dim3(c.ctaA), 0};
+}
+HpKernelLaunch desc_mg_line(const HpLaunchCfg& c, int nz_level) {
+    const void* f = nullptr;
+#define HP_X(T, E, V) f = fn_mg_line<T, E, V>()
+    HP_DISPATCH(c, HP_X);
+#undef HP_X
+    HpLaunchCfg cl = c;
+    cl.nz = nz_level;
+    return {f, dim3(team_grid(f, cl, c.cta_threads, c.teams_per_cta, 1)), dim3(c.cta_threads), 0};
+}
+HpKernelLaunch desc_factor_levels(int total_coarse_rows) {
+    return {(const void*)k_factor_levels, dim3((total_coarse_rows + 31) / 32), dim3(32), 0};
 }
 HpKernelLaunch desc_finalize() { return {(const void*)k_finalize, dim3(1), dim3(32), 0}; }
 HpKernelLaunch desc_wait() { return {(const void*)k_wait, dim3(1), dim3(32), 0}; }

@@ -15,7 +15,7 @@ import numpy as np
 from . import _lib
 from .regions import Regions
 
-PRECOND = {'jacobi': 0, 'rline': 1}
+PRECOND = {'jacobi': 0, 'rline': 1, 'mgline': 2}
 CRITERION = {'precond_inf': 0, 'rowscaled_inf': 1, 'l2_rel_rhs': 2}
 LOOP_MODE = {'host': 0, 'graph': 1}
 PROPERTIES = {'temperature_dependent': 0, 'simple': 1}
@@ -101,7 +101,8 @@ class ConductionSolver:
                  properties='temperature_dependent', gamma='snapshot', source='q_over_k',
                  face_k='masked_at_Tface', radiation=False, axial_break=None, rows=None,
                  precond='rline', criterion='precond_inf', tol=1e-9, max_iter=5000, loop_mode='graph',
-                 poll_chunk=8, refactor_every=1, extrapolate=True, device=None, simple=(7200.0, 440.5, 55.0),
+                 poll_chunk=8, refactor_every=1, extrapolate=True, mg_levels=6, mg_coarse_sweeps=2, mg_omega=0.8,
+                 device=None, simple=(7200.0, 440.5, 55.0),
                  layout=None, regions=None):
         import torch
         if not torch.cuda.is_available():
@@ -152,12 +153,14 @@ class ConductionSolver:
             _lib.check(self.lib.hp_create(C.byref(self._h), C.byref(md), C.byref(self.phys),
                                           C.c_void_p(self._stream.cuda_stream)), 'hp_create')
         self.set_options(precond=precond, criterion=criterion, tol=tol, max_iter=max_iter, loop_mode=loop_mode,
-                         poll_chunk=poll_chunk, refactor_every=refactor_every, extrapolate=extrapolate)
+                         poll_chunk=poll_chunk, refactor_every=refactor_every, extrapolate=extrapolate,
+                         mg_levels=mg_levels, mg_coarse_sweeps=mg_coarse_sweeps, mg_omega=mg_omega)
 
     # ------------------------------------------------------------------ options
     def set_options(self, **kw):
         cur = getattr(self, 'options', dict(precond='rline', criterion='precond_inf', tol=1e-9, max_iter=5000,
-                                            loop_mode='graph', poll_chunk=8, refactor_every=1, extrapolate=True))
+                                            loop_mode='graph', poll_chunk=8, refactor_every=1, extrapolate=True,
+                                            mg_levels=6, mg_coarse_sweeps=2, mg_omega=0.8))
         cur = dict(cur)
         for k, v in kw.items():
             if k not in cur:
@@ -170,6 +173,7 @@ class ConductionSolver:
         o.loop_mode = _choice(LOOP_MODE, cur['loop_mode'], 'loop_mode')
         o.poll_chunk, o.refactor_every = int(cur['poll_chunk']), int(cur['refactor_every'])
         o.extrapolate = 1 if cur['extrapolate'] else 0
+        o.mg_levels, o.mg_coarse_sweeps, o.mg_omega = int(cur['mg_levels']), int(cur['mg_coarse_sweeps']), float(cur['mg_omega'])
         _lib.check(self.lib.hp_set_opts(self._h, C.byref(o)), 'hp_set_opts')
         self.options = cur
 

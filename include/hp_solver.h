@@ -65,7 +65,8 @@ typedef struct hp_mesh_desc {
 } hp_mesh_desc;
 
 typedef struct hp_solve_opts {
-    int32_t precond;        /* 0 Jacobi, 1 radial-line tridiagonal */
+    int32_t precond;        /* 0 Jacobi, 1 radial-line tridiagonal, 2 'mgline': V(1,1) multigrid, axial semi-coarsening,
+                               damped radial-line smoother (the stopping rule stays the line-preconditioned residual) */
     int32_t criterion;      /* 0 max|M^-1 r| <= tol [K]; 1 max|r_i/a_ii| <= tol [K]; 2 ||r||_2 <= tol*||b||_2 */
     double tol;
     int32_t max_iter;
@@ -74,7 +75,10 @@ typedef struct hp_solve_opts {
     int32_t refactor_every; /* re-factor the line preconditioner every k-th sweep (1 = every sweep) */
     int32_t extrapolate;    /* 1: hp_step/hp_run start the first solve of a step from T + (T - T_prev) (the system is still
                                assembled at T and `res` is still FiPy's pre-solve residual; only the PCG start changes) */
+    int32_t mg_levels;      /* mgline: maximum number of levels (>= 2) */
+    int32_t mg_coarse_sweeps; /* mgline: extra smoothing sweeps on the coarsest level */
     int32_t _pad;
+    double mg_omega;        /* mgline: damping of the line smoother */
 } hp_solve_opts;
 
 typedef struct hp_sweep_stat {

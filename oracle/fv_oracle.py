@@ -419,7 +419,7 @@ def solve_system(S: System, x0=None, solver='auto', info=None, **kw):
         return x.reshape(nz, nr)
     if solver == 'splu':
         return spla.splu(S.to_csr()).solve(S.rhs.ravel()).reshape(nz, nr)
-    if solver in ('pcg_rline', 'pcg_jacobi'):
+    if solver in ('pcg_rline', 'pcg_jacobi', 'pcg_mgline'):
         return pcg(S, x0=x0, precond=solver[4:], info=info, **kw)
     raise ValueError(solver)
 
@@ -434,7 +434,76 @@ def rline_factor(S: System):
     return d, e
 
 
-def pcg(S: System, x0=None, precond='rline', tol=1e-9, criterion='precond_inf', max_iter=10000, info=None):
+
+# ---------------------------------------------------------------------------
+# 'mgline' preconditioner twin: V(1,1), axial semi-coarsening by row pairs (Galerkin, piecewise constant), damped
+# radial-line Jacobi smoother -- the same cycle as csrc/hp_kernels.cu (k_mg_coarsen / k_mg_res / k_mg_line)
+# ---------------------------------------------------------------------------
+class _MgLevel:
+    def __init__(self, cR, cZ, diag):
+        self.S = System(cR, cZ, diag, np.zeros_like(diag))
+        self.fd, self.fe = rline_factor(self.S)
+
+    def line(self, v):
+        y, _ = sla.lapack.dpttrs(self.fd, self.fe, v.ravel().copy())
+        return y.reshape(v.shape)
+
+    def coarsen(self):
+        cR, cZ, dg = self.S.cR, self.S.cZ, self.S.diag
+        nz = dg.shape[0]
+        nzc = (nz + 1) // 2
+        a = slice(0, nz, 2)
+        cRc, cZc, dgc = cR[a].copy(), np.zeros((nzc, cR.shape[1])), dg[a].copy()
+        nb = nz // 2                                    # complete pairs
+        cRc[:nb] += cR[1::2]
+        dgc[:nb] += dg[1::2] - 2.0 * cZ[0:2 * nb:2]
+        top = np.where(np.arange(nzc) < nb, 2 * np.arange(nzc) + 1, 2 * np.arange(nzc))   # top fine row of every pair
+        cZc[:] = cZ[top]
+        cZc[-1, :] = 0.0
+        return _MgLevel(cRc, cZc, dgc)
+
+
+def mg_hierarchy(S: System, max_levels=6):
+    cZ = S.cZ.copy()
+    cZ[-1, :] = 0.0
+    levels = [_MgLevel(S.cR, cZ, S.diag)]
+    nzl = S.diag.shape[0]
+    while len(levels) < max_levels and nzl >= 32:
+        levels.append(levels[-1].coarsen())
+        nzl = (nzl + 1) // 2
+    return levels
+
+
+def _restrict(r):
+    nz = r.shape[0]
+    out = r[0::2].copy()
+    out[:nz // 2] += r[1::2]
+    return out
+
+
+def _prolong(e, nz):
+    return np.repeat(e, 2, axis=0)[:nz]
+
+
+def mg_vcycle(levels, r, zline, omega=0.8, coarse_sweeps=2):
+    """z = V(r); `zline` = M_line^-1 r of the fine level (what k_cg_B leaves in z)."""
+    c = len(levels) - 1
+    xs, rs = [omega * zline], [r]
+    rs.append(_restrict(rs[0] - levels[0].S.matvec(xs[0])))
+    for l in range(1, c):
+        xs.append(omega * levels[l].line(rs[l]))
+        rs.append(_restrict(rs[l] - levels[l].S.matvec(xs[l])))
+    xc = omega * levels[c].line(rs[c])
+    for _ in range(coarse_sweeps):
+        xc = xc + omega * levels[c].line(rs[c] - levels[c].S.matvec(xc))
+    e = xc
+    for l in range(c - 1, -1, -1):
+        xt = xs[l] + _prolong(e, xs[l].shape[0])
+        e = xt + omega * levels[l].line(rs[l] - levels[l].S.matvec(xt))
+    return e
+
+
+def pcg(S: System, x0=None, precond='rline', tol=1e-9, criterion='precond_inf', max_iter=10000, info=None, mg=None):
     """Preconditioned CG restating the GPU algorithm (same preconditioners, same stopping rules, same order
     of operations: x/r update, z = M^-1 r, test, direction update).
 
@@ -457,6 +526,8 @@ def pcg(S: System, x0=None, precond='rline', tol=1e-9, criterion='precond_inf', 
 
         def apply_M(v):
             return v * dinv
+    elif precond == 'mgline':
+        return _pcg_mgline(S, x, r, tol, criterion, max_iter, info, **(mg or {}))
     else:
         raise ValueError(precond)
     bnorm = float(np.linalg.norm(b.ravel()))
@@ -492,6 +563,41 @@ def pcg(S: System, x0=None, precond='rline', tol=1e-9, criterion='precond_inf', 
     if info is not None:
         info['iterations'] = it
         info['crit'] = crit
+    return x
+
+
+def _pcg_mgline(S, x, r, tol, criterion, max_iter, info, max_levels=6, omega=0.8, coarse_sweeps=2):
+    """PCG with the V-cycle as preconditioner; the stopping measure stays max|M_line^-1 r| (same rule as 'rline')."""
+    if criterion != 'precond_inf':
+        raise ValueError("mgline twin implements the precond_inf criterion")
+    levels = mg_hierarchy(S, max_levels)
+    if len(levels) < 2:
+        raise ValueError("mesh too short to coarsen")
+    it = 0
+    zl = levels[0].line(r)
+    crit = float(np.max(np.abs(zl)))
+    if crit > tol:
+        z = mg_vcycle(levels, r, zl, omega, coarse_sweeps)
+        p = z.copy()
+        rz = float(np.vdot(r, z))
+        while it < max_iter:
+            q = S.matvec(p)
+            alpha = rz / float(np.vdot(p, q))
+            x += alpha * p
+            r -= alpha * q
+            it += 1
+            zl = levels[0].line(r)
+            crit = float(np.max(np.abs(zl)))
+            if crit <= tol:
+                break
+            z = mg_vcycle(levels, r, zl, omega, coarse_sweeps)
+            rz_new = float(np.vdot(r, z))
+            p = z + (rz_new / rz) * p
+            rz = rz_new
+    if info is not None:
+        info['iterations'] = it
+        info['crit'] = crit
+        info['levels'] = len(levels)
     return x
 
 

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main(rank, world, port, shape, n_steps, sweeps, out_path, comm='nccl', loop_mode='host'):
+def main(rank, world, port, shape, n_steps, sweeps, out_path, comm='nccl', loop_mode='host', precond='rline'):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -20,7 +20,7 @@ def main(rank, world, port, shape, n_steps, sweeps, out_path, comm='nccl', loop_
     from oracle import fv_oracle as fo
     cfg = params.load_config()
     mesh, _ = generate_composite_mesh(fo.synthetic_mesh_params(*shape), cfg['dimensions'])
-    solver = make_solver_for_rank(mesh, cfg, rank, world, comm=comm, loop_mode=loop_mode, poll_chunk=4)
+    solver = make_solver_for_rank(mesh, cfg, rank, world, comm=comm, loop_mode=loop_mode, poll_chunk=4, precond=precond)
     j0, j1 = solver.layout.j0, solver.layout.j1
     z = mesh.z_c[:, None] / mesh.z_v[-1]
     T0 = 290.0 + 250.0 * np.exp(-((z - 0.45) / 0.3) ** 2) * np.ones((1, mesh.nr))     # hot spot across the slab cut
@@ -39,4 +39,4 @@ def main(rank, world, port, shape, n_steps, sweeps, out_path, comm='nccl', loop_
 
 if __name__ == '__main__':
     main(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), tuple(int(v) for v in sys.argv[4].split(',')),
-         int(sys.argv[5]), int(sys.argv[6]), sys.argv[7], *(sys.argv[8:10]))
+         int(sys.argv[5]), int(sys.argv[6]), sys.argv[7], *(sys.argv[8:11]))

@@ -134,6 +134,45 @@ def test_solver_options_agree(cfg, opts):
         assert err <= 3 * PER_STEP_TOL_K
 
 
+@pytest.mark.parametrize('tag', ['native', 's64x32', 's96x100', 's80x130', 's128x256', 's48x1024', 's16x4096'])
+def test_mgline_sweep_matches_oracle(cfg, tag):
+    """'mgline' (V-cycle, axial semi-coarsening, radial-line smoother): same answer as the direct solve, and the same
+    PCG iteration count as the oracle's twin of the cycle (+-1).  Covers odd row counts on coarse levels (500 -> 250 ->
+    125 -> 63 -> 32 -> 16) and meshes too short to coarsen (falls back to the line preconditioner)."""
+    s, o = make_pair(cfg, SHAPES[tag], T0=hot_field, solver_kw=dict(precond='mgline'))
+    with s:
+        res = s.sweep(0.1)
+        T = s.value.reshape(o.T.shape)
+        st = s.stats(1)[0]
+    o2 = fo.Oracle(o.grid, o.case, T0=o.T.copy())
+    res_ref = o.sweep(0.1, solver='banded' if o.grid.nr <= 160 else 'splu')
+    assert st['converged'] and not st['breakdown'], st
+    assert abs(res - res_ref) <= 1e-9 * res_ref
+    assert np.max(np.abs(T - o.T)) <= PER_STEP_TOL_K, (tag, st)
+    if o.grid.nz >= 32:
+        o2.sweep(0.1, solver='pcg_mgline', tol=1e-9)
+        assert abs(st['iters'] - o2.last_solver_info['iterations']) <= 1, (st, o2.last_solver_info)
+
+
+@pytest.mark.parametrize('loop_mode', ['graph', 'host'])
+def test_mgline_transient_with_sweeps(cfg, loop_mode):
+    s, o = make_pair(cfg, None, T0=lambda g: hot_field(g, amp=120.0), has_old=True,
+                     solver_kw=dict(precond='mgline', loop_mode=loop_mode))
+    with s:
+        s.run(0.5, 10, sweeps=5, has_old=True)
+        T = s.value.reshape(o.T.shape)
+        it_mg = s.total_iters
+    for _ in range(10):
+        o.update_old()
+        for _ in range(5):
+            o.sweep(0.5, solver='banded')
+    assert np.max(np.abs(T - o.T)) <= END_TOL_K
+    s2, _ = make_pair(cfg, None, T0=lambda g: hot_field(g, amp=120.0), has_old=True, solver_kw=dict(precond='rline'))
+    with s2:
+        s2.run(0.5, 10, sweeps=5, has_old=True)
+        assert it_mg < s2.total_iters
+
+
 def test_iteration_counts_match_oracle_pcg(cfg):
     """Same algorithm, same stopping rule -> same number of PCG iterations as the oracle's PCG (+-1)."""
     s, o = make_pair(cfg, SHAPES['s128x256'], T0=hot_field)

@@ -20,9 +20,10 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize('comm,loop_mode', [('nccl', 'host'), ('p2p', 'host'), ('p2p', 'graph')])
+@pytest.mark.parametrize('comm,loop_mode,precond', [('nccl', 'host', 'rline'), ('p2p', 'host', 'rline'), ('p2p', 'graph', 'rline'),
+                                                    ('p2p', 'graph', 'mgline'), ('nccl', 'host', 'mgline')])
 @pytest.mark.parametrize('world,shape', [(2, (64, 4, 8, 20)), (2, (50, 32, 64, 160)), (4, (96, 12, 24, 64))])
-def test_slabs_match_single_domain_oracle(cfg, tmp_path, world, shape, comm, loop_mode):
+def test_slabs_match_single_domain_oracle(cfg, tmp_path, world, shape, comm, loop_mode, precond):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -31,7 +32,7 @@ def test_slabs_match_single_domain_oracle(cfg, tmp_path, world, shape, comm, loo
     port = _free_port()
     n_steps, sweeps = 2, 3
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, 'tests', 'slab_worker.py'), str(r), str(world), str(port),
-                               ','.join(map(str, shape)), str(n_steps), str(sweeps), out, comm, loop_mode]) for r in range(world)]
+                               ','.join(map(str, shape)), str(n_steps), str(sweeps), out, comm, loop_mode, precond]) for r in range(world)]
     for p in procs:
         assert p.wait(timeout=300) == 0
     T = np.load(out)
