@@ -32,7 +32,8 @@ if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
 RADIAL_SPLIT = {1024: (128, 256, 640), 4096: (512, 1024, 2560), 512: (64, 128, 320), 256: (32, 64, 160), 128: (16, 32, 80)}
 DT, SWEEPS, HAS_OLD = 0.1, 5, True
 # algorithmic bytes per cell and launch (fp64; DESIGN.md "Kernels"): reads + writes of full-size fields
-BYTES_PER_CELL = {'cg_A': 56, 'cg_B': 72, 'cg_init': 32, 'diag': 48, 'factor': 24, 'coef': 24, 'mg': 0}
+BYTES_PER_CELL = {'cg_A': 56, 'cg_B': 72, 'cg_init': 32, 'diag': 48, 'factor': 24, 'coef': 24,
+                  'mg_res': 56, 'mg_line': 48}      # fine-level V-cycle kernels (down 52 / up 60 B per cell; final line solve 48)
 
 
 def parse_workload(s):
@@ -105,13 +106,14 @@ def measured_peak():
 # ------------------------------------------------------------------------------------------------------------
 # oracle timing (cpu_baseline leg and --impl reference)
 # ------------------------------------------------------------------------------------------------------------
-def oracle_steps(nz, nr, n_steps, warmup=0):
-    """Time n_steps implicit-Euler steps (updateOld + 5 sweeps, line-PCG at the GPU's tolerance) of the oracle."""
+def oracle_steps(nz, nr, n_steps, warmup=0, precond='mgline'):
+    """Time n_steps implicit-Euler steps (updateOld + 5 sweeps, the same PCG + preconditioner + tolerance as the GPU arm)
+    of the oracle."""
     from oracle import fv_oracle as fo
     cfg = fo.load_config()
     grid = fo.build_grid(mesh_params_for(nz, nr), cfg['dimensions'])
     o = fo.Oracle(grid, fo.case_from_config(), has_old=HAS_OLD)
-    solver = 'banded' if nr <= 64 else 'pcg_rline'
+    solver = 'banded' if nr <= 64 else ('pcg_mgline' if precond == 'mgline' else 'pcg_rline')
 
     def one():
         o.update_old()
@@ -131,9 +133,9 @@ def run_reference(args, rank, world):
         return
     nz, nr = parse_workload(args.workload or ('4096x1024' if world == 1 else '16384x4096'))
     snz, snr = 1024, 256      # bounded sample: same mesh recipe and physics, 1/16 (or 1/256) of the cells per step
-    value, secs = oracle_steps(snz, snr, args.steps, args.warmup)
+    value, secs = oracle_steps(snz, snr, args.steps, args.warmup, args.precond)
     sample = (f"{args.steps} steps (after {args.warmup} warm-up) of the oracle on a synthetic composite mesh {snz}x{snr} "
-              f"(same recipe as {nz}x{nr}, T-dependent, updateOld + {SWEEPS} sweeps, line-PCG tol 1e-9 K); FiPy itself is not installable")
+              f"(same recipe as {nz}x{nr}, T-dependent, updateOld + {SWEEPS} sweeps, PCG/{args.precond} tol 1e-9 K); FiPy itself is not installable")
     line = {
         'impl': 'reference', 'metric': 'cell-timesteps/s (incl. sweeps)', 'value': value, 'unit': 'cell-timesteps/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * secs / max(args.steps, 1),
@@ -167,7 +169,8 @@ def run_gpu(args, rank, world, local_rank):
     with torch.cuda.stream(stream):
         loop_mode = 'host' if (world > 1 and args.comm == 'nccl') else args.loop_mode
         solver = make_solver_for_rank(mesh, cfg, rank, world, comm=args.comm, tol=args.tol, loop_mode=loop_mode,
-                                      extrapolate=os.environ.get('HP_EXTRAP', '1') != '0', precond=args.precond)
+                                      extrapolate=os.environ.get('HP_EXTRAP', '1') != '0', precond=args.precond,
+                                      mg_levels=args.mg_levels, mg_coarse_sweeps=args.mg_sweeps, mg_omega=args.mg_omega)
 
         def barrier():
             stream.synchronize()
@@ -228,7 +231,7 @@ def run_gpu(args, rank, world, local_rank):
             kt = solver.profile_end()
             peak, peak_src = measured_peak()
             tot_ms = sum(v[1] for v in kt.values())
-            dom = max(kt, key=lambda k: kt[k][1])
+            dom = max((k for k in kt if k in BYTES_PER_CELL), key=lambda k: kt[k][1])
             cnt, tms = kt[dom]
             bytes_per_launch = BYTES_PER_CELL.get(dom, 0) * n_cells
             achieved = bytes_per_launch / (tms / cnt * 1e-3) / 1e9 if cnt else 0.0
@@ -247,13 +250,35 @@ def run_gpu(args, rank, world, local_rank):
                                         'GBps': (BYTES_PER_CELL.get(k, 0) * n_cells / (m / c * 1e-3) / 1e9 if c else None)}
                                     for k, (c, m) in kt.items() if c}}
         solver.close()
+        # strong-scaling reference: the same 16384x4096 workload on ONE GPU (rank 0, after the slab handles are gone)
+        strong = None
+        if world > 1:
+            barrier()
+            if rank == 0 and not args.no_single_gpu_ref:
+                one = make_solver_for_rank(mesh, cfg, 0, 1, tol=args.tol, loop_mode=args.loop_mode, precond=args.precond,
+                                           mg_levels=args.mg_levels, mg_coarse_sweeps=args.mg_sweeps, mg_omega=args.mg_omega)
+                one.run(DT, 3, sweeps=SWEEPS, has_old=HAS_OLD)
+                stream.synchronize()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                it1 = one.total_iters
+                s0.record(stream)
+                one.run(DT, 3, sweeps=SWEEPS, has_old=HAS_OLD)
+                s1.record(stream)
+                stream.synchronize()
+                ms1 = s0.elapsed_time(s1) / 3
+                strong = {'single_gpu_ms_per_step': ms1, 'single_gpu_value': n_cells / (ms1 * 1e-3),
+                          'single_gpu_pcg_iterations_per_step': (one.total_iters - it1) / 3,
+                          'speedup_vs_single_gpu': ms1 / (ms / args.steps),
+                          'note': 'same 16384x4096 workload on one B200, 3 timed steps after 3 warm-up steps, measured in this run'}
+                one.close()
+            barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         snz, snr = 2048, 512
-        v, secs = oracle_steps(snz, snr, 2)
+        v, secs = oracle_steps(snz, snr, 2, 0, args.precond)
         cpu = {'value': v, 'unit': 'cell-timesteps/s', 'cores': 1, 'kind': 'port',
-               'sample': f'2 steps of the numpy/scipy oracle (FiPy restatement, line-PCG tol 1e-9 K) on a {snz}x{snr} synthetic '
+               'sample': f'2 steps of the numpy/scipy oracle (FiPy restatement, PCG/{args.precond} tol 1e-9 K) on a {snz}x{snr} synthetic '
                          f'composite mesh, same physics and sweeps ({secs:.1f} s); host has {os.cpu_count()} cores, the port uses 1'}
     if rank == 0:
         line = {
@@ -267,7 +292,7 @@ def run_gpu(args, rank, world, local_rank):
                        'pcg_iterations_per_step': iters / args.steps, 'loop_mode': loop_mode},
             'e2e': {'value': e2e_value, 'unit': 'cell-timesteps/s', 'h2d_bytes_per_step': 8 * n_cells,
                     'd2h_bytes_per_step': 8 * n_cells, 'ms_per_step': e2e_ms / args.steps},
-            'gpu_launches': int(launches), 'clocks': clk,
+            'gpu_launches': int(launches), 'clocks': clk, 'strong_scaling': strong if world > 1 else None,
             'roofline': roof, 'cpu_baseline': cpu,
             'last_sweep_stats': stats[-SWEEPS:],
         }
@@ -287,7 +312,13 @@ def main():
     ap.add_argument('--tol', type=float, default=1e-9)
     ap.add_argument('--loop-mode', default='graph', choices=['graph', 'host'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--precond', default='rline', choices=['rline', 'mgline', 'jacobi'])
+    ap.add_argument('--no-single-gpu-ref', action='store_true', help='N>1: skip the one-GPU run of the same workload')
+    ap.add_argument('--precond', default='mgline', choices=['rline', 'mgline', 'jacobi'],
+                    help='PCG preconditioner: mgline (V-cycle over radial-line smoothing, default), rline (the radial-line '
+                         'tridiagonal preconditioner alone), jacobi')
+    ap.add_argument('--mg-levels', type=int, default=6)
+    ap.add_argument('--mg-sweeps', type=int, default=2)
+    ap.add_argument('--mg-omega', type=float, default=0.7)
     ap.add_argument('--comm', default='p2p', choices=['p2p', 'nccl'], help='slab exchange: NVLink peer stores fused into the kernels, or NCCL calls')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))

@@ -44,10 +44,10 @@ class HpSweepStat(C.Structure):
 
 
 class HpKernelTimes(C.Structure):
-    _fields_ = [('count', C.c_int64 * 8), ('total_ms', C.c_double * 8)]
+    _fields_ = [('count', C.c_int64 * 16), ('total_ms', C.c_double * 16)]
 
 
-KERNEL_KINDS = ('other', 'coef', 'diag', 'factor', 'cg_init', 'cg_A', 'cg_B', 'mg')
+KERNEL_KINDS = ('other', 'coef', 'diag', 'factor', 'cg_init', 'cg_A', 'cg_B', 'mg_res', 'mg_line', 'mg_coarse', 'mg_setup')
 
 # every symbol include/hp_solver.h declares: name -> (restype, argtypes)
 _H = C.c_void_p

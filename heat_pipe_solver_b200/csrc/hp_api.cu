@@ -203,7 +203,8 @@ static HpKArgs make_args(const hp_solver_s* h, double dt, int has_old) {
     return a;
 }
 
-enum { KIND_OTHER = 0, KIND_COEF, KIND_DIAG, KIND_FACTOR, KIND_INIT, KIND_A, KIND_B, KIND_MG, KIND_COUNT };
+enum { KIND_OTHER = 0, KIND_COEF, KIND_DIAG, KIND_FACTOR, KIND_INIT, KIND_A, KIND_B, KIND_MG_RES0, KIND_MG_LINE0, KIND_MG_COARSE,
+       KIND_MG_SETUP, KIND_COUNT };
 
 static int launch(hp_solver_s* h, const HpKernelLaunch& k, void** params, int kind = KIND_OTHER) {
     const bool prof = h->prof_on && h->prof_used < h->prof_ev.size() / 2;
@@ -303,6 +304,7 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
 
     h->opts.precond = 1; h->opts.criterion = 0; h->opts.tol = 1e-9; h->opts.max_iter = 5000;
     h->opts.loop_mode = 1; h->opts.poll_chunk = 8; h->opts.refactor_every = 1; h->opts.extrapolate = 1;
+    h->opts.mg_levels = 6; h->opts.mg_coarse_sweeps = 2; h->opts.mg_omega = 0.7;
 
     // initial field + snapshots (main.py:34,133,145,152)
     CK(hpk::launch_fill_rows(d, d.T, h->stream));
@@ -363,7 +365,7 @@ int hp_set_opts(hp_handle h, const hp_solve_opts* o) {
     if (h->opts.mg_levels < 2) h->opts.mg_levels = 6;
     if (h->opts.mg_levels > HP_MAX_LEVELS) h->opts.mg_levels = HP_MAX_LEVELS;
     if (h->opts.mg_coarse_sweeps < 0) h->opts.mg_coarse_sweeps = 2;
-    if (!(h->opts.mg_omega > 0.0 && h->opts.mg_omega <= 1.0)) h->opts.mg_omega = 0.8;
+    if (!(h->opts.mg_omega > 0.0 && h->opts.mg_omega <= 1.0)) h->opts.mg_omega = 0.7;
     if (h->opts.precond == 2) {
         if (setup_mg(h)) return -1;
         if (h->nlev < 2) h->opts.precond = 1;          // mesh too short to coarsen: plain line preconditioner
@@ -475,11 +477,11 @@ static int emit_mg_setup(Emitter& e) {
     for (int l = 0; l < h->nlev; ++l) ls.lev[l] = h->lev[l];
     for (int l = 1; l < h->nlev; ++l) {
         void* pc[] = {&h->lev[l - 1], &h->lev[l], &nr, &skip};
-        if (emit(e, hpk::desc_mg_coarsen(h->cfg, h->lev[l].nz, nr), pc, KIND_MG)) return -1;
+        if (emit(e, hpk::desc_mg_coarsen(h->cfg, h->lev[l].nz, nr), pc, KIND_MG_SETUP)) return -1;
         rows += h->lev[l].nz;
     }
     void* pf[] = {&ls, &nr, &skip};
-    return emit(e, hpk::desc_factor_levels(rows), pf, KIND_MG);
+    return emit(e, hpk::desc_factor_levels(rows), pf, KIND_MG_SETUP);
 }
 
 // mgline V(1,1) cycle on r (level-0 rhs) starting from zline = M^-1 r in d.z (left there by k_cg_B); leaves the
@@ -493,12 +495,12 @@ static int emit_vcycle(Emitter& e, const HpKArgs& a_in, int init_phase) {
     auto res = [&](int l, const double* xin, const double* ec, double* xout, double* resout, double* crhs, double scale) -> int {
         HpMgResArgs m{xin, ec, xout, resout, crhs, scale, (l + 1 < nl) ? h->lev[l + 1].nz : 1};
         void* p[] = {&d, &a, &h->lev[l], &m};
-        return emit(e, hpk::desc_mg_res(h->cfg, h->lev[l].nz), p, KIND_MG);
+        return emit(e, hpk::desc_mg_res(h->cfg, h->lev[l].nz), p, l == 0 ? KIND_MG_RES0 : KIND_MG_COARSE);
     };
     auto line = [&](int l, const double* rhs, const double* base, double* out, int fin) -> int {
         HpMgLineArgs m{rhs, base, out, fin};
         void* p[] = {&d, &a, &h->lev[l], &m};
-        return emit(e, hpk::desc_mg_line(h->cfg, h->lev[l].nz), p, KIND_MG);
+        return emit(e, hpk::desc_mg_line(h->cfg, h->lev[l].nz), p, l == 0 ? KIND_MG_LINE0 : KIND_MG_COARSE);
     };
     HpLevel* L = h->lev;
     // down: level 0 starts from omega * zline (pre-smoothing already done by k_cg_B's line solve)

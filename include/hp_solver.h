@@ -141,10 +141,11 @@ int hp_eval_cell_fields(hp_handle h, double* d_rho, double* d_cp, double* d_kavg
 
 /* per-kernel device times by CUDA events (bench.py roofline).  Between begin and end every sweep runs in
  * stream-launch mode with an event pair around each kernel launch (at most max_launches are recorded).
- * kinds: 0 other, 1 coef, 2 diag, 3 factor, 4 cg_init, 5 cg_A, 6 cg_B */
+ * kinds: 0 other, 1 coef, 2 diag, 3 factor, 4 cg_init, 5 cg_A, 6 cg_B, 7 mg_res (fine level), 8 mg_line (fine level),
+ * 9 mg kernels of the coarse levels, 10 mg setup (coarsening + coarse pivots) */
 typedef struct hp_kernel_times {
-    int64_t count[8];
-    double total_ms[8];
+    int64_t count[16];
+    double total_ms[16];
 } hp_kernel_times;
 int hp_profile_begin(hp_handle h, int max_launches);
 int hp_profile_end(hp_handle h, hp_kernel_times* out);
