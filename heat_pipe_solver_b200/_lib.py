@@ -80,7 +80,7 @@ SIGNATURES = {
     'hp_profile_end': (C.c_int, [_H, C.POINTER(HpKernelTimes)]),
     'hp_comm_unique_id': (C.c_int, [C.c_void_p]),
     'hp_comm_init': (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
-    'hp_peer_export': (C.c_int, [_H, C.c_void_p]),
+    'hp_peer_export': (C.c_int, [_H, C.POINTER(C.c_int32), C.c_void_p]),
     'hp_peer_import': (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_int32)]),
 }
 

@@ -96,6 +96,16 @@ struct hp_solver_s {
     // 'mgline' hierarchy (level 0 aliases the fine fields)
     HpLevel lev[HP_MAX_LEVELS];
     int nlev = 0, nlev_alloc = 0;
+    // replicated global coarse levels of mgline under peer-memory slabs (shape fixed at hp_peer_export time)
+    std::vector<int> nz_of_rank;
+    int g_switch = 0;                // local level whose rows are gathered into global level 0 (0 = rank-local cycle)
+    int g_rows_mine = 0, g_row0 = 0; // my rows / first row inside global level 0
+    int nglev = 0;
+    HpLevel glev[HP_MAX_LEVELS];
+    long long g_off[HP_MAX_LEVELS][8];   // element offsets of (cR, cZ, diag, dinv, rhs, x, x2, tmp) inside gblock
+    double* gblock = nullptr;
+    size_t gblock_elems = 0;
+    bool g_active = false;
     // peer-memory exchange (hp_peer_export / hp_peer_import)
     HpComm* comm = nullptr;          // my mailbox
     double* qz_block = nullptr;      // base of the (q, z) allocation (IPC handle is per allocation)
@@ -166,10 +176,30 @@ static int apply_l2_to_stream(hp_solver_s* h) {
 }
 
 // ---- 'mgline' hierarchy: level l+1 has ceil(nz_l / 2) rows; stops at 16 rows or mg_levels -------------------
+static int local_level_count(int nz, int max_levels) {
+    int n = 1;
+    for (int nzl = nz; n < max_levels && nzl >= 32; nzl = (nzl + 1) / 2) ++n;
+    return n;
+}
+static int rows_at_level(int nz, int l) {
+    for (int k = 0; k < l; ++k) nz = (nz + 1) / 2;
+    return nz;
+}
+
 static int setup_mg(hp_solver_s* h) {
     HpDev& d = h->d;
-    int want = 1;
-    for (int nzl = d.nz; want < h->opts.mg_levels && nzl >= 32; nzl = (nzl + 1) / 2) ++want;
+    int want = local_level_count(d.nz, h->opts.mg_levels);
+    // under peer-memory slabs every rank stops at the same level, and the rows of that level are gathered into the
+    // replicated global hierarchy whose shape was fixed at export time
+    h->g_active = false;
+    if (h->nranks > 1 && d.p2p && h->gblock && !h->nz_of_rank.empty()) {
+        int s_min = HP_MAX_LEVELS;
+        for (int r = 0; r < h->nranks; ++r) {
+            int c = local_level_count(h->nz_of_rank[r], h->opts.mg_levels) - 1;
+            if (c < s_min) s_min = c;
+        }
+        if (s_min >= 1 && s_min == h->g_switch) { want = s_min + 1; h->g_active = true; }
+    }
     if (h->nlev_alloc == 0) {
         HpLevel& L0 = h->lev[0];
         L0.nz = d.nz; L0.cR = d.cR; L0.cZ = d.cZ; L0.diag = d.diag; L0.dinv = d.dinv;
@@ -249,7 +279,7 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
 
     HpDev& d = h->d;
     d.nr = nr; d.nz = nz; d.ncolA = h->cfg.ncolA; d.p2p = 0; d.seq = nullptr; d.z_lo = d.z_hi = d.T_lo = d.T_hi = nullptr;
-    for (int r = 0; r < HP_MAX_RANKS; ++r) d.comm_peer[r] = nullptr;
+    for (int r = 0; r < HP_MAX_RANKS; ++r) { d.comm_peer[r] = nullptr; d.gblock_peer[r] = nullptr; }
     d.nranks = 1; d.rank = 0; d.red_local = nullptr; d.red_all = nullptr;
     std::vector<double> r_v(m->r_v, m->r_v + nr + 1), r_c(nr), dr(nr), ar(nr, 0.0), dcr(nr, 1.0);
     for (int i = 0; i < nr; ++i) { r_c[i] = 0.5 * (r_v[i] + r_v[i + 1]); dr[i] = r_v[i + 1] - r_v[i]; }
@@ -466,20 +496,44 @@ static int emit_combine(Emitter& e, HpKArgs& a, int fin_kind) {
     return emit(e, hpk::desc_finalize(), p4);
 }
 
-// mgline: Galerkin operators and line pivots of the coarse levels (after the fine diagonal / pivots are current)
+// mgline: Galerkin operators and line pivots of the coarse levels (after the fine diagonal / pivots are current).
+// Under peer-memory slabs the rows of the last local level are gathered into the replicated global level 0 of every
+// rank (with the true interface couplings), which is then coarsened further on every rank redundantly.
 static int emit_mg_setup(Emitter& e) {
     hp_solver_s* h = e.h;
-    int nr = h->d.nr;
-    const int* skip = &h->d.st->mg_skip;          // set by the INIT decision when the sweep is already converged
+    HpDev& d = h->d;
+    int nr = d.nr;
+    const int* skip = &d.st->mg_skip;          // set by the INIT decision when the sweep is already converged
     HpLevelSet ls;
-    ls.n = h->nlev;
+    ls.n = 1;
+    ls.lev[0] = h->lev[0];
     int rows = 0;
-    for (int l = 0; l < h->nlev; ++l) ls.lev[l] = h->lev[l];
+    const int s = h->nlev - 1;
     for (int l = 1; l < h->nlev; ++l) {
         void* pc[] = {&h->lev[l - 1], &h->lev[l], &nr, &skip};
         if (emit(e, hpk::desc_mg_coarsen(h->cfg, h->lev[l].nz, nr), pc, KIND_MG_SETUP)) return -1;
-        rows += h->lev[l].nz;
+        if (!(h->g_active && l == s)) { ls.lev[ls.n++] = h->lev[l]; rows += h->lev[l].nz; }
     }
+    if (h->g_active) {
+        HpGatherArgs g{};
+        g.src[0] = h->lev[s].cR; g.src[1] = h->lev[s].cZ; g.src[2] = h->lev[s].diag;
+        g.dst_off[0] = h->g_off[0][0]; g.dst_off[1] = h->g_off[0][1]; g.dst_off[2] = h->g_off[0][2];
+        g.top_override = d.cZ + (size_t)d.nz * nr;      // fine coupling of my last row to the next slab (0 at the top end)
+        g.override_idx = 1;
+        g.nsrc = 3; g.nrows = h->g_rows_mine; g.row0_dst = h->g_row0; g.kind = HP_COMM_GOP;
+        void* pg[] = {&d, &g, &skip};
+        if (emit(e, hpk::desc_gather_rows(h->cfg, 3LL * g.nrows * nr), pg, KIND_MG_SETUP)) return -1;
+        int kind = HP_COMM_GOP;
+        void* pw[] = {&d, &kind, &skip};
+        if (emit(e, hpk::desc_wait_flag(), pw, KIND_MG_SETUP)) return -1;
+        ls.lev[ls.n++] = h->glev[0]; rows += h->glev[0].nz;
+        for (int gl = 1; gl < h->nglev; ++gl) {
+            void* pc[] = {&h->glev[gl - 1], &h->glev[gl], &nr, &skip};
+            if (emit(e, hpk::desc_mg_coarsen(h->cfg, h->glev[gl].nz, nr), pc, KIND_MG_SETUP)) return -1;
+            ls.lev[ls.n++] = h->glev[gl]; rows += h->glev[gl].nz;
+        }
+    }
+    if (rows == 0) return 0;
     void* pf[] = {&ls, &nr, &skip};
     return emit(e, hpk::desc_factor_levels(rows), pf, KIND_MG_SETUP);
 }
@@ -491,37 +545,70 @@ static int emit_vcycle(Emitter& e, const HpKArgs& a_in, int init_phase) {
     HpDev& d = h->d;
     HpKArgs a = a_in;
     a.init_phase = init_phase;
-    const int nl = h->nlev, c = nl - 1;
-    auto res = [&](int l, const double* xin, const double* ec, double* xout, double* resout, double* crhs, double scale) -> int {
-        HpMgResArgs m{xin, ec, xout, resout, crhs, scale, (l + 1 < nl) ? h->lev[l + 1].nz : 1};
-        void* p[] = {&d, &a, &h->lev[l], &m};
-        return emit(e, hpk::desc_mg_res(h->cfg, h->lev[l].nz), p, l == 0 ? KIND_MG_RES0 : KIND_MG_COARSE);
+    const int nr = d.nr;
+    auto res = [&](HpLevel& Lv, bool fine, const double* xin, const double* ec, int nzc, double* xout, double* resout,
+                   double* crhs, double scale) -> int {
+        HpMgResArgs m{xin, ec, xout, resout, crhs, scale, nzc};
+        void* p[] = {&d, &a, &Lv, &m};
+        return emit(e, hpk::desc_mg_res(h->cfg, Lv.nz), p, fine ? KIND_MG_RES0 : KIND_MG_COARSE);
     };
-    auto line = [&](int l, const double* rhs, const double* base, double* out, int fin) -> int {
+    auto line = [&](HpLevel& Lv, bool fine, const double* rhs, const double* base, double* out, int fin) -> int {
         HpMgLineArgs m{rhs, base, out, fin};
-        void* p[] = {&d, &a, &h->lev[l], &m};
-        return emit(e, hpk::desc_mg_line(h->cfg, h->lev[l].nz), p, l == 0 ? KIND_MG_LINE0 : KIND_MG_COARSE);
+        void* p[] = {&d, &a, &Lv, &m};
+        return emit(e, hpk::desc_mg_line(h->cfg, Lv.nz), p, fine ? KIND_MG_LINE0 : KIND_MG_COARSE);
+    };
+    // complete V-cycle on levels lo..n-1 of Ls (rhs of level lo given, correction left in Ls[lo].x)
+    auto subcycle = [&](HpLevel* Ls, int lo, int n) -> int {
+        const int c = n - 1;
+        for (int l = lo; l < c; ++l) {
+            if (line(Ls[l], false, Ls[l].rhs, nullptr, Ls[l].x, 0)) return -1;
+            if (res(Ls[l], false, Ls[l].x, nullptr, Ls[l + 1].nz, nullptr, nullptr, Ls[l + 1].rhs, 1.0)) return -1;
+        }
+        if (line(Ls[c], false, Ls[c].rhs, nullptr, Ls[c].x, 0)) return -1;
+        for (int k = 0; k < h->opts.mg_coarse_sweeps; ++k) {
+            if (res(Ls[c], false, Ls[c].x, nullptr, 1, nullptr, Ls[c].tmp, nullptr, 1.0)) return -1;
+            if (line(Ls[c], false, Ls[c].tmp, Ls[c].x, Ls[c].x, 0)) return -1;
+        }
+        for (int l = c - 1; l >= lo; --l) {
+            if (res(Ls[l], false, Ls[l].x, Ls[l + 1].x, Ls[l + 1].nz, Ls[l].x2, Ls[l].tmp, nullptr, 1.0)) return -1;
+            if (line(Ls[l], false, Ls[l].tmp, Ls[l].x2, Ls[l].x, 0)) return -1;
+        }
+        return 0;
     };
     HpLevel* L = h->lev;
-    // down: level 0 starts from omega * zline (pre-smoothing already done by k_cg_B's line solve)
-    if (res(0, d.z, nullptr, L[0].x2, nullptr, L[1].rhs, a.omega)) return -1;
-    for (int l = 1; l < c; ++l) {
-        if (line(l, L[l].rhs, nullptr, L[l].x, 0)) return -1;
-        if (res(l, L[l].x, nullptr, nullptr, nullptr, L[l + 1].rhs, 1.0)) return -1;
+    const int nl = h->nlev;
+    // level 0 starts from omega * zline (its pre-smoothing is k_cg_B's line solve)
+    if (res(L[0], true, d.z, nullptr, L[1].nz, L[0].x2, nullptr, L[1].rhs, a.omega)) return -1;
+    const double* ec0 = L[1].x;          // coarse correction seen by level 0
+    if (!h->g_active) {
+        if (subcycle(L, 1, nl)) return -1;
+    } else {
+        const int s = nl - 1;              // rows of local level s are one slice of the replicated global level 0
+        for (int l = 1; l < s; ++l) {
+            if (line(L[l], false, L[l].rhs, nullptr, L[l].x, 0)) return -1;
+            if (res(L[l], false, L[l].x, nullptr, L[l + 1].nz, nullptr, nullptr, L[l + 1].rhs, 1.0)) return -1;
+        }
+        const int* skip = &d.st->mg_skip;
+        HpGatherArgs g{};
+        g.src[0] = L[s].rhs; g.dst_off[0] = h->g_off[0][4];
+        g.top_override = nullptr; g.override_idx = -1;
+        g.nsrc = 1; g.nrows = h->g_rows_mine; g.row0_dst = h->g_row0; g.kind = HP_COMM_GRHS;
+        void* pg[] = {&d, &g, &skip};
+        if (emit(e, hpk::desc_gather_rows(h->cfg, (long long)g.nrows * nr), pg, KIND_MG_COARSE)) return -1;
+        int kind = HP_COMM_GRHS;
+        void* pw[] = {&d, &kind, &skip};
+        if (emit(e, hpk::desc_wait_flag(), pw, KIND_MG_COARSE)) return -1;
+        if (subcycle(h->glev, 0, h->nglev)) return -1;
+        const double* mine = h->glev[0].x + (size_t)h->g_row0 * nr;      // my slice (ghost-inclusive indexing kept)
+        for (int l = s - 1; l >= 1; --l) {
+            const double* ec = (l == s - 1) ? mine : L[l + 1].x;
+            if (res(L[l], false, L[l].x, ec, L[l + 1].nz, L[l].x2, L[l].tmp, nullptr, 1.0)) return -1;
+            if (line(L[l], false, L[l].tmp, L[l].x2, L[l].x, 0)) return -1;
+        }
+        if (s == 1) ec0 = mine;
     }
-    // coarsest level: 1 + mg_coarse_sweeps damped line-Jacobi sweeps
-    if (line(c, L[c].rhs, nullptr, L[c].x, 0)) return -1;
-    for (int k = 0; k < h->opts.mg_coarse_sweeps; ++k) {
-        if (res(c, L[c].x, nullptr, nullptr, L[c].tmp, nullptr, 1.0)) return -1;
-        if (line(c, L[c].tmp, L[c].x, L[c].x, 0)) return -1;
-    }
-    // up: prolong + post-smooth
-    for (int l = c - 1; l >= 1; --l) {
-        if (res(l, L[l].x, L[l + 1].x, L[l].x2, L[l].tmp, nullptr, 1.0)) return -1;
-        if (line(l, L[l].tmp, L[l].x2, L[l].x, 0)) return -1;
-    }
-    if (res(0, L[0].x2, L[1].x, d.z, L[0].tmp, nullptr, 1.0)) return -1;
-    if (line(0, L[0].tmp, d.z, d.z, 1)) return -1;
+    if (res(L[0], true, L[0].x2, ec0, L[1].nz, d.z, L[0].tmp, nullptr, 1.0)) return -1;
+    if (line(L[0], true, L[0].tmp, d.z, d.z, 1)) return -1;
     HpKArgs af = a;
     return emit_combine(e, af, 4);
 }
@@ -819,20 +906,57 @@ int hp_eval_cell_fields(hp_handle h, double* d_rho, double* d_cp, double* d_kavg
 }
 
 // ---- peer memory over NVLink: every rank maps every other rank's mailbox, and its neighbours' z / T arrays -------
-int hp_peer_export(hp_handle h, void* out192) {
-    if (!h || !out192) return fail("hp_peer_export: null argument");
+int hp_peer_export(hp_handle h, const int32_t* nz_of_rank, void* out256) {
+    if (!h || !out256 || !nz_of_rank) return fail("hp_peer_export: null argument");
+    if (h->nranks < 2) return fail("hp_peer_export: call hp_comm_init first");
+    HpDev& d = h->d;
     if (!h->comm) {
         if (dev_alloc(h, (void**)&h->comm, sizeof(HpComm))) return -1;
         CK(cudaMemset(h->comm, 0, sizeof(HpComm)));
-        if (dev_alloc(h, (void**)&h->d.seq, sizeof(unsigned long long) * HP_COMM_KINDS)) return -1;
-        CK(cudaMemset(h->d.seq, 0, sizeof(unsigned long long) * HP_COMM_KINDS));
+        if (dev_alloc(h, (void**)&d.seq, sizeof(unsigned long long) * HP_COMM_KINDS)) return -1;
+        CK(cudaMemset(d.seq, 0, sizeof(unsigned long long) * HP_COMM_KINDS));
     }
-    cudaIpcMemHandle_t hd[3];
+    // shape of the replicated global coarse hierarchy (identical on every rank: it only depends on nz_of_rank, nr, opts)
+    h->nz_of_rank.assign(nz_of_rank, nz_of_rank + h->nranks);
+    int s_min = HP_MAX_LEVELS;
+    for (int r = 0; r < h->nranks; ++r) {
+        int c = local_level_count(nz_of_rank[r], h->opts.mg_levels) - 1;
+        if (c < s_min) s_min = c;
+    }
+    h->g_switch = s_min;
+    int M = 0;
+    for (int r = 0; r < h->nranks; ++r) {
+        if (r == h->rank) h->g_row0 = M;
+        M += rows_at_level(nz_of_rank[r], s_min);
+    }
+    h->g_rows_mine = rows_at_level(nz_of_rank[h->rank], s_min);
+    h->nglev = 0;
+    size_t elems = 0;
+    for (int rows = M; h->nglev < HP_MAX_LEVELS; rows = (rows + 1) / 2) {
+        h->glev[h->nglev].nz = rows;
+        for (int k = 0; k < 8; ++k) { h->g_off[h->nglev][k] = (long long)elems; elems += (size_t)(rows + 2) * d.nr + 64; }
+        h->nglev++;
+        if (rows < 32) break;
+    }
+    if (!h->gblock) {
+        h->gblock_elems = elems;
+        if (dev_alloc(h, (void**)&h->gblock, elems * sizeof(double))) return -1;
+        CK(cudaMemset(h->gblock, 0, elems * sizeof(double)));
+    } else if (elems != h->gblock_elems) {
+        return fail("hp_peer_export: called twice with different shapes");
+    }
+    for (int g = 0; g < h->nglev; ++g) {
+        double** f[] = {&h->glev[g].cR, &h->glev[g].cZ, &h->glev[g].diag, &h->glev[g].dinv,
+                        &h->glev[g].rhs, &h->glev[g].x, &h->glev[g].x2, &h->glev[g].tmp};
+        for (int k = 0; k < 8; ++k) *f[k] = h->gblock + h->g_off[g][k];
+    }
+    cudaIpcMemHandle_t hd[4];
     CK(cudaIpcGetMemHandle(&hd[0], h->comm));
     CK(cudaIpcGetMemHandle(&hd[1], h->qz_block));
-    CK(cudaIpcGetMemHandle(&hd[2], h->d.T));
+    CK(cudaIpcGetMemHandle(&hd[2], d.T));
+    CK(cudaIpcGetMemHandle(&hd[3], h->gblock));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    memcpy(out192, hd, sizeof(hd));
+    memcpy(out256, hd, sizeof(hd));
     return 0;
 }
 
@@ -846,18 +970,21 @@ int hp_peer_import(hp_handle h, const void* all_handles, const int32_t* nz_of_ra
     HpDev& d = h->d;
     const size_t nr = d.nr;
     for (int r = 0; r < h->nranks; ++r) {
-        if (r == h->rank) { d.comm_peer[r] = h->comm; continue; }
+        if (r == h->rank) { d.comm_peer[r] = h->comm; d.gblock_peer[r] = h->gblock; continue; }
         void* p = nullptr;
-        CK(cudaIpcOpenMemHandle(&p, hd[3 * r + 0], cudaIpcMemLazyEnablePeerAccess));
+        CK(cudaIpcOpenMemHandle(&p, hd[4 * r + 0], cudaIpcMemLazyEnablePeerAccess));
         h->ipc_opened.push_back(p);
         d.comm_peer[r] = (HpComm*)p;
+        CK(cudaIpcOpenMemHandle(&p, hd[4 * r + 3], cudaIpcMemLazyEnablePeerAccess));
+        h->ipc_opened.push_back(p);
+        d.gblock_peer[r] = (double*)p;
     }
     d.z_lo = d.z_hi = d.T_lo = d.T_hi = nullptr;
     auto open_nb = [&](int r, double** qz, double** T) -> int {
         void* p = nullptr;
-        CK(cudaIpcOpenMemHandle(&p, hd[3 * r + 1], cudaIpcMemLazyEnablePeerAccess));
+        CK(cudaIpcOpenMemHandle(&p, hd[4 * r + 1], cudaIpcMemLazyEnablePeerAccess));
         h->ipc_opened.push_back(p); *qz = (double*)p;
-        CK(cudaIpcOpenMemHandle(&p, hd[3 * r + 2], cudaIpcMemLazyEnablePeerAccess));
+        CK(cudaIpcOpenMemHandle(&p, hd[4 * r + 2], cudaIpcMemLazyEnablePeerAccess));
         h->ipc_opened.push_back(p); *T = (double*)p;
         return 0;
     };
@@ -880,6 +1007,7 @@ int hp_peer_import(hp_handle h, const void* all_handles, const int32_t* nz_of_ra
     d.p2p = 1;
     h->ghost_dirty = true;
     destroy_graphs(h);
+    if (h->opts.precond == 2 && setup_mg(h)) return -1;      // switch the cycle to the replicated global coarse levels
     return 0;
 }
 

@@ -9,7 +9,7 @@
 #define HP_NRED 4                // reduced values per kernel
 
 #define HP_MAX_RANKS 16
-enum { HP_COMM_DIAG = 0, HP_COMM_A = 1, HP_COMM_B = 2, HP_COMM_MG = 3, HP_COMM_KINDS = 4 };
+enum { HP_COMM_DIAG = 0, HP_COMM_A = 1, HP_COMM_B = 2, HP_COMM_MG = 3, HP_COMM_GOP = 4, HP_COMM_GRHS = 5, HP_COMM_KINDS = 6 };
 
 // Peer-memory mailbox of one rank (cudaMalloc'ed, IPC-mapped into every peer of the box over NVLink).
 // red[kind][src] / flag[kind][src] are WRITTEN BY rank `src` (remote stores from its reducing kernel) and read locally.
@@ -67,6 +67,7 @@ struct HpDev {
     int p2p;
     HpComm* comm_peer[HP_MAX_RANKS];   // every rank's mailbox (own one included) as seen from this GPU
     unsigned long long* seq;           // [HP_COMM_KINDS] how many times this rank has produced each kind
+    double* gblock_peer[HP_MAX_RANKS]; // every rank's block of replicated global coarse levels (mgline under slabs)
     double *z_lo, *z_hi;               // neighbour's z ghost row that mirrors my first / last owned row (or null)
     double *T_lo, *T_hi;               // same for the field T
     double* red_local;       // [HP_NRED]
@@ -82,7 +83,17 @@ struct HpLevel {
     double *rhs, *x, *x2, *tmp;          // right-hand side, correction, prolonged correction, residual scratch
 };
 
-struct HpLevelSet { int n; HpLevel lev[HP_MAX_LEVELS]; };
+struct HpLevelSet { int n; HpLevel lev[2 * HP_MAX_LEVELS]; };   // entry 0 is skipped by k_factor_levels
+
+// k_gather_rows: this rank's rows of up to 3 level arrays -> the same rows of EVERY rank's replicated global level
+struct HpGatherArgs {
+    const double* src[3];        // ghost-inclusive local arrays (row 1 = first owned row)
+    long long dst_off[3];        // element offset of the destination array inside a rank's gblock
+    const double* top_override;  // if set: replaces the LAST owned row of src[override_idx] (interface coupling)
+    int override_idx;
+    int nsrc, nrows, row0_dst;   // rows to copy, first destination row (owned index) in the global level
+    int kind;                    // HP_COMM_* flag signalled to every rank when all rows are stored
+};
 
 // arguments of k_mg_res / k_mg_line (hp_kernels.cu)
 struct HpMgResArgs {
@@ -147,6 +158,8 @@ HpKernelLaunch desc_mg_coarsen(const HpLaunchCfg&, int nzc, int nr);
 HpKernelLaunch desc_mg_res(const HpLaunchCfg&, int nz_level);
 HpKernelLaunch desc_mg_line(const HpLaunchCfg&, int nz_level);
 HpKernelLaunch desc_factor_levels(int total_coarse_rows);   // args: (HpLevelSet, int nr, const int* skip)
+HpKernelLaunch desc_gather_rows(const HpLaunchCfg&, long long elems);  // args: (HpDev, HpGatherArgs, const int* skip)
+HpKernelLaunch desc_wait_flag();                                        // args: (HpDev, int kind, const int* skip)
 HpKernelLaunch desc_wait();       // args: (HpDev, hp_phys, HpKArgs, int kind): peer-memory variant of finalize
 HpKernelLaunch desc_finalize();   // args: (HpDev, hp_phys, HpKArgs, int kind) kind: 0 diag, 1 A, 2 B, 3 init
 HpKernelLaunch desc_cg_B(const HpLaunchCfg&, const HpDev&, int precond, int criterion);

@@ -869,6 +869,66 @@ __global__ void __launch_bounds__(256) k_delta(HpDev d, hp_phys ph, HpKArgs a) {
 }
 
 
+
+// ---- replicated global coarse levels under slabs ---------------------------------------------------------------------
+// signal `kind` to every rank (sequence flag, release at system scope); called by ONE thread after the data stores of the
+// whole grid are ordered before it (system fence + ticket in every CTA)
+__device__ __forceinline__ void signal_all(const HpDev& d, int kind) {
+    const unsigned long long sq = d.seq[kind] + 1ull;
+    d.seq[kind] = sq;
+    __threadfence_system();
+    for (int r = 0; r < d.nranks; ++r) {
+        unsigned long long* f = &d.comm_peer[r]->flag[kind][d.rank];
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(sq) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gather_rows(HpDev d, HpGatherArgs g, const int* skip) {
+    if (*skip) return;
+    const long long per = (long long)g.nrows * d.nr, n = per * g.nsrc;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(t / per);
+        const long long e = t - (long long)k * per;
+        const int row = (int)(e / d.nr), i = (int)(e - (long long)row * d.nr);
+        double v = g.src[k][(long long)(row + 1) * d.nr + i];
+        if (g.top_override && k == g.override_idx && row == g.nrows - 1) v = g.top_override[i];
+        const long long off = g.dst_off[k] + (long long)(g.row0_dst + row + 1) * d.nr + i;
+        for (int r = 0; r < d.nranks; ++r) d.gblock_peer[r][off] = v;
+    }
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        s_last = (atomicAdd(&d.st->ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        d.st->ticket = 0u;
+        signal_all(d, g.kind);
+    }
+}
+
+// wait (bounded) until every rank has signalled `kind` as often as this rank has
+__global__ void k_wait_flag(HpDev d, int kind, const int* skip) {
+    if (*skip) return;
+    const int lane = threadIdx.x;
+    const HpComm* mine = d.comm_peer[d.rank];
+    const unsigned long long want = d.seq[kind];
+    bool ok = true;
+    if (lane < d.nranks && !(d.st->flags & 8)) {
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(&mine->flag[kind][lane]) < want) {
+            if (global_ns() - t0 > 2000000000ull) { ok = false; break; }
+            __nanosleep(64);
+        }
+    }
+    const unsigned bad = __ballot_sync(0xffffffffu, !ok);
+    if (lane == 0 && bad) {
+        d.st->flags |= 8;
+        d.stats[(d.st->sweep_count - 1) % HP_STATS_CAP].flags |= 8;
+    }
+}
+
 // ================================================================================================
 // 'mgline' preconditioner: V(1,1) cycle, axial semi-coarsening (row pairs), damped radial-line Jacobi smoother.
 // The radial stiffness is removed exactly by the line solves on every level; coarsening the axial index removes the
@@ -1220,6 +1280,12 @@ HpKernelLaunch desc_mg_line(const HpLaunchCfg& c, int nz_level) {
 HpKernelLaunch desc_factor_levels(int total_coarse_rows) {
     return {(const void*)k_factor_levels, dim3((total_coarse_rows + 31) / 32), dim3(32), 0};
 }
+HpKernelLaunch desc_gather_rows(const HpLaunchCfg& c, long long elems) {
+    long long g = (elems + 255) / 256;
+    long long cap = (long long)c.num_sms * 4;
+    return {(const void*)k_gather_rows, dim3((unsigned)(g < 1 ? 1 : (g < cap ? g : cap))), dim3(256), 0};
+}
+HpKernelLaunch desc_wait_flag() { return {(const void*)k_wait_flag, dim3(1), dim3(32), 0}; }
 HpKernelLaunch desc_finalize() { return {(const void*)k_finalize, dim3(1), dim3(32), 0}; }
 HpKernelLaunch desc_wait() { return {(const void*)k_wait, dim3(1), dim3(32), 0}; }
 HpKernelLaunch desc_cg_A(const HpLaunchCfg& c, const HpDev& d) {

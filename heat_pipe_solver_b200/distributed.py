@@ -71,12 +71,12 @@ def make_solver_for_rank(mesh, cfg, rank, world, comm='p2p', **solver_kw):
     dist.broadcast(ident, src=0)
     solver.init_comm(rank, world, bytes(ident.cpu().numpy().tobytes()))
     if comm == 'p2p':
-        mine = torch.frombuffer(bytearray(solver.peer_export()), dtype=torch.uint8).cuda()
+        nzs = [b - a for a, b in (slab_rows(mesh.nz, r, world) for r in range(world))]
+        mine = torch.frombuffer(bytearray(solver.peer_export(nzs)), dtype=torch.uint8).cuda()
         gathered = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine)
         handles = b''.join(bytes(g.cpu().numpy().tobytes()) for g in gathered)
-        nzs = [slab_rows(mesh.nz, r, world) for r in range(world)]
-        solver.init_peer(handles, [b - a for a, b in nzs])
+        solver.init_peer(handles, nzs)
         dist.barrier()
     elif comm != 'nccl':
         raise ValueError("comm must be 'p2p' or 'nccl'")

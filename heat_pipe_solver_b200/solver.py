@@ -266,17 +266,18 @@ class ConductionSolver:
         _lib.check(self.lib.hp_comm_init(self._h, int(rank), int(world), buf), 'hp_comm_init')
         self.rank, self.world = rank, world
 
-    def peer_export(self) -> bytes:
-        """192 bytes of CUDA-IPC handles (mailbox, (q,z) block, T) for `init_peer` on the other ranks."""
-        buf = (C.c_uint8 * 192)()
-        _lib.check(self.lib.hp_peer_export(self._h, buf), 'hp_peer_export')
+    def peer_export(self, nz_of_rank) -> bytes:
+        """256 bytes of CUDA-IPC handles (mailbox, (q,z) block, T, global coarse levels) for `init_peer` on the other ranks."""
+        buf = (C.c_uint8 * 256)()
+        nzs = (C.c_int32 * len(nz_of_rank))(*[int(v) for v in nz_of_rank])
+        _lib.check(self.lib.hp_peer_export(self._h, nzs, buf), 'hp_peer_export')
         return bytes(buf)
 
     def init_peer(self, all_handles: bytes, nz_of_rank):
         """Switch the slab exchange from NCCL calls to peer-memory stores fused into the kernels."""
         n = len(nz_of_rank)
-        if len(all_handles) != 192 * n:
-            raise ValueError("need 192 bytes of handles per rank")
+        if len(all_handles) != 256 * n:
+            raise ValueError("need 256 bytes of handles per rank")
         buf = (C.c_uint8 * len(all_handles)).from_buffer_copy(all_handles)
         nzs = (C.c_int32 * n)(*[int(v) for v in nz_of_rank])
         _lib.check(self.lib.hp_peer_import(self._h, buf, nzs), 'hp_peer_import')

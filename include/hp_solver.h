@@ -156,12 +156,13 @@ int hp_profile_end(hp_handle h, hp_kernel_times* out);
 int hp_comm_unique_id(void* id128);
 int hp_comm_init(hp_handle h, int rank, int nranks, const void* id128);
 /* peer-memory (NVLink) exchange fused into the PCG kernels, replacing the NCCL calls inside a sweep: every rank
- * exports 3 CUDA-IPC handles (192 bytes: mailbox, (q,z) block, T), the host gathers them (nranks*192 bytes, rank
+ * exports 4 CUDA-IPC handles (256 bytes: mailbox, (q,z) block, T, replicated global coarse levels of mgline), the host
+ * gathers them (nranks*256 bytes, rank
  * order) and every rank imports them together with the owned-row count of every rank.  After it k_cg_B stores its
  * boundary rows of z and T straight into the neighbours' ghost rows and the last CTA of every reducing kernel stores
  * its sums + a sequence flag into every rank's mailbox; a one-warp kernel waits for the flags (bounded) and combines
  * the sums in rank order.  The whole time step is then one CUDA graph per rank (loop_mode 1). */
-int hp_peer_export(hp_handle h, void* out192);
+int hp_peer_export(hp_handle h, const int32_t* nz_of_rank, void* out256);
 int hp_peer_import(hp_handle h, const void* all_handles, const int32_t* nz_of_rank);
 
 #ifdef __cplusplus

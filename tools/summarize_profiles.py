@@ -34,7 +34,7 @@ for r in data:
     c[1] += v
 tot = sum(v[1] for v in agg.values())
 with open(os.path.join(P, f'{tag}_launches_summary.txt'), 'w') as f:
-    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --loop-mode host`\n")
+    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --loop-mode host` (default preconditioner)\n")
     f.write("# (cold-cache, serialised launches: compare SHARES, not absolutes)\n")
     f.write(f"{'kernel':58s} {'launches':>8s} {'total ms':>10s} {'avg us':>9s} {'share':>7s}\n")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -66,14 +66,16 @@ with open(os.path.join(P, f'{tag}_ncu_cg_metrics.csv'), 'w', newline='') as f:
     w.writerow([units[i] for i in idx])
     for r in body:
         w.writerow([r[i] for i in idx])
-        name = 'cg_A' if 'k_cg_A' in r[h.index('Kernel Name')] else 'cg_B'
+        kname = r[h.index('Kernel Name')]
+        name = next((v for k, v in (('k_cg_A', 'cg_A'), ('k_cg_B', 'cg_B'), ('k_mg_res', 'mg_res'), ('k_mg_line', 'mg_line')) if k in kname), 'other')
 
         def tobytes(col):
             v, u = float(r[h.index(col)].replace(',', '')), units[h.index(col)]
             return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
         traffic.setdefault(name, []).append(tobytes('dram__bytes_read.sum') + tobytes('dram__bytes_write.sum'))
-json.dump({k: sum(v) / len(v) for k, v in traffic.items()}, open(os.path.join(P, 'ncu_traffic.json'), 'w'), indent=1)
-for name in ('bench.json', 'bench_ref.json'):
+# the capture also holds coarse-level launches of the V-cycle kernels: the fine level is the one with the most traffic
+json.dump({k: max(v) for k, v in traffic.items()}, open(os.path.join(P, 'ncu_traffic.json'), 'w'), indent=1)
+for name in ('bench.json', 'bench_ref.json', 'bench_rline.json'):
     src = os.path.join(G, name)
     if os.path.exists(src):
         shutil.copy(src, os.path.join(P, f'{tag}_{name}'))
