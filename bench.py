@@ -25,9 +25,16 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; stdout must carry exactly one JSON line
-if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-    os.environ['NCCL_DEBUG'] = 'WARN'
+# stdout must carry exactly ONE JSON line, but libraries chat on it (NCCL prints its version banner there at
+# NCCL_DEBUG=VERSION/WARN): keep a private copy of the real stdout for the result and point fd 1 at stderr meanwhile
+_REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+os.dup2(2, 1)
+
+
+def emit_line(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + '\n')
+    _REAL_STDOUT.flush()
+
 
 RADIAL_SPLIT = {1024: (128, 256, 640), 4096: (512, 1024, 2560), 512: (64, 128, 320), 256: (32, 64, 160), 128: (16, 32, 80)}
 DT, SWEEPS, HAS_OLD = 0.1, 5, True
@@ -146,7 +153,7 @@ def run_reference(args, rank, world):
         'e2e': {'value': value, 'unit': 'cell-timesteps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -170,7 +177,8 @@ def run_gpu(args, rank, world, local_rank):
         loop_mode = 'host' if (world > 1 and args.comm == 'nccl') else args.loop_mode
         solver = make_solver_for_rank(mesh, cfg, rank, world, comm=args.comm, tol=args.tol, loop_mode=loop_mode,
                                       extrapolate=os.environ.get('HP_EXTRAP', '1') != '0', precond=args.precond,
-                                      mg_levels=args.mg_levels, mg_coarse_sweeps=args.mg_sweeps, mg_omega=args.mg_omega)
+                                      mg_levels=args.mg_levels, mg_coarse_sweeps=args.mg_sweeps, mg_omega=args.mg_omega,
+                                      refactor_every=args.refactor_every)
 
         def barrier():
             stream.synchronize()
@@ -256,6 +264,7 @@ def run_gpu(args, rank, world, local_rank):
             barrier()
             if rank == 0 and not args.no_single_gpu_ref:
                 one = make_solver_for_rank(mesh, cfg, 0, 1, tol=args.tol, loop_mode=args.loop_mode, precond=args.precond,
+                                           refactor_every=args.refactor_every,
                                            mg_levels=args.mg_levels, mg_coarse_sweeps=args.mg_sweeps, mg_omega=args.mg_omega)
                 one.run(DT, 3, sweeps=SWEEPS, has_old=HAS_OLD)
                 stream.synchronize()
@@ -289,14 +298,15 @@ def run_gpu(args, rank, world, local_rank):
                                    f'dt={DT}s, updateOld + {SWEEPS} sweeps/step, PCG ({args.precond}) tol {args.tol:g} K',
                        'parallelism': 'single GPU' if world == 1 else (f'axial slabs x{world}, ' + ('NVLink peer-memory halo rows + CG scalars fused into the PCG kernels, one CUDA graph per step' if args.comm == 'p2p' else 'NCCL send/recv halo + all-gathered CG scalars, host-driven loop')),
                        'l2': 'working set (11 fp64 fields) exceeds the 126 MB L2; no flush needed',
-                       'pcg_iterations_per_step': iters / args.steps, 'loop_mode': loop_mode},
+                       'pcg_iterations_per_step': iters / args.steps, 'loop_mode': loop_mode,
+                       'refactor_every_sweeps': args.refactor_every},
             'e2e': {'value': e2e_value, 'unit': 'cell-timesteps/s', 'h2d_bytes_per_step': 8 * n_cells,
                     'd2h_bytes_per_step': 8 * n_cells, 'ms_per_step': e2e_ms / args.steps},
             'gpu_launches': int(launches), 'clocks': clk, 'strong_scaling': strong if world > 1 else None,
             'roofline': roof, 'cpu_baseline': cpu,
             'last_sweep_stats': stats[-SWEEPS:],
         }
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -316,6 +326,9 @@ def main():
     ap.add_argument('--precond', default='mgline', choices=['rline', 'mgline', 'jacobi'],
                     help='PCG preconditioner: mgline (V-cycle over radial-line smoothing, default), rline (the radial-line '
                          'tridiagonal preconditioner alone), jacobi')
+    ap.add_argument('--refactor-every', type=int, default=SWEEPS,
+                    help='re-factor the line pivots / coarse operators every k-th sweep of a step (default: once per step; '
+                         'they only precondition, the answer is unchanged)')
     ap.add_argument('--mg-levels', type=int, default=6)
     ap.add_argument('--mg-sweeps', type=int, default=2)
     ap.add_argument('--mg-omega', type=float, default=0.7)

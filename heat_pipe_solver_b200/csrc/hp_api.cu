@@ -499,11 +499,13 @@ static int emit_combine(Emitter& e, HpKArgs& a, int fin_kind) {
 // mgline: Galerkin operators and line pivots of the coarse levels (after the fine diagonal / pivots are current).
 // Under peer-memory slabs the rows of the last local level are gathered into the replicated global level 0 of every
 // rank (with the true interface couplings), which is then coarsened further on every rank redundantly.
-static int emit_mg_setup(Emitter& e) {
+static int emit_mg_setup(Emitter& e, bool always) {
     hp_solver_s* h = e.h;
     HpDev& d = h->d;
     int nr = d.nr;
-    const int* skip = &d.st->mg_skip;          // set by the INIT decision when the sweep is already converged
+    // skipped on the device when the INIT decision found the sweep converged -- unless later sweeps reuse this set-up
+    // (refactor_every > 1): then it must exist, so it runs unconditionally (_pad0 is a constant zero)
+    const int* skip = always ? &d.st->_pad0 : &d.st->mg_skip;
     HpLevelSet ls;
     ls.n = 1;
     ls.lev[0] = h->lev[0];
@@ -660,11 +662,13 @@ static int emit_sweep_head(Emitter& e, HpKArgs& a, bool refactor, bool shift) {
         if (emit_combine(e, as, 1)) return -1;
         if (emit(e, hpk::desc_cg_B(h->cfg, d, h->opts.precond != 0, h->opts.criterion), ps, KIND_B)) return -1;
         if (emit_combine(e, as, 3)) return -1;
-        if (a.mg && (emit_mg_setup(e) || emit_vcycle(e, as, 1))) return -1;
+        if (a.mg && refactor && emit_mg_setup(e, h->opts.refactor_every > 1)) return -1;
+        if (a.mg && emit_vcycle(e, as, 1)) return -1;
     } else {
         if (emit(e, hpk::desc_cg_init(h->cfg, d, h->opts.precond != 0, h->opts.criterion), params, KIND_INIT)) return -1;
         if (emit_combine(e, a, 3)) return -1;
-        if (a.mg && (emit_mg_setup(e) || emit_vcycle(e, a, 1))) return -1;      // both skipped on the device if converged
+        if (a.mg && refactor && emit_mg_setup(e, h->opts.refactor_every > 1)) return -1;
+        if (a.mg && emit_vcycle(e, a, 1)) return -1;      // skipped on the device if the sweep is already converged
     }
     return 0;
 }
