@@ -170,15 +170,41 @@ def run_gpu(args, rank, world, local_rank):
     from heat_pipe_solver_b200 import generate_composite_mesh, params
     from heat_pipe_solver_b200.distributed import make_solver_for_rank
     cfg = params.load_config()
-    nz, nr = parse_workload(args.workload or ('4096x1024' if world == 1 else '16384x4096'))
-    mesh, _ = generate_composite_mesh(mesh_params_for(nz, nr), cfg['dimensions'])
+    ensemble = (args.workload or '').startswith('ensemble')
     stream = torch.cuda.Stream()
+    if ensemble:
+        # BASELINE configs[4]: M independent Faghri-geometry pipes (native 500x9 mesh), members sharded over the ranks,
+        # no data-path collective; member m: q ~ U(0.5,1.5)*26770, h ~ U(2,20), T_amb ~ U(280,300), rng(1234)
+        import numpy as np
+        from heat_pipe_solver_b200.ensemble import EnsembleSolver, shard_members
+        M = int(args.workload.split(':')[1]) if ':' in args.workload else 1024
+        rng = np.random.default_rng(1234)
+        q = cfg['parameters']['Q_input_flux'] * rng.uniform(0.5, 1.5, M)
+        hh = rng.uniform(2.0, 20.0, M)
+        Ta = rng.uniform(280.0, 300.0, M)
+        lo, hi = shard_members(M, rank, world)
+        nz, nr = int(cfg['mesh']['nx_wall']), int(cfg['mesh']['nr_vc'] + cfg['mesh']['nr_wick'] + cfg['mesh']['nr_wall'])
+        loop_mode = args.loop_mode
+        with torch.cuda.stream(stream):
+            ens = EnsembleSolver(dict(cfg['mesh']), cfg['dimensions'], cfg['parameters'], cfg['constants'], q=q[lo:hi], h=hh[lo:hi],
+                                 T_amb=Ta[lo:hi], tol=args.tol, loop_mode=loop_mode, precond=args.precond,
+                                 refactor_every=args.refactor_every, mg_levels=args.mg_levels,
+                                 mg_coarse_sweeps=args.mg_sweeps, mg_omega=args.mg_omega)
+        solver = ens.solver
+
+        class _M:                      # what the rest of the function needs from a mesh
+            numberOfCells = M * nz * nr
+        mesh = _M()
+    else:
+        nz, nr = parse_workload(args.workload or ('4096x1024' if world == 1 else '16384x4096'))
+        mesh, _ = generate_composite_mesh(mesh_params_for(nz, nr), cfg['dimensions'])
     with torch.cuda.stream(stream):
-        loop_mode = 'host' if (world > 1 and args.comm == 'nccl') else args.loop_mode
-        solver = make_solver_for_rank(mesh, cfg, rank, world, comm=args.comm, tol=args.tol, loop_mode=loop_mode,
-                                      extrapolate=os.environ.get('HP_EXTRAP', '1') != '0', precond=args.precond,
-                                      mg_levels=args.mg_levels, mg_coarse_sweeps=args.mg_sweeps, mg_omega=args.mg_omega,
-                                      refactor_every=args.refactor_every)
+        loop_mode = 'host' if (world > 1 and args.comm == 'nccl' and not ensemble) else args.loop_mode
+        if not ensemble:
+            solver = make_solver_for_rank(mesh, cfg, rank, world, comm=args.comm, tol=args.tol, loop_mode=loop_mode,
+                                          extrapolate=os.environ.get('HP_EXTRAP', '1') != '0', precond=args.precond,
+                                          mg_levels=args.mg_levels, mg_coarse_sweeps=args.mg_sweeps, mg_omega=args.mg_omega,
+                                          refactor_every=args.refactor_every)
 
         def barrier():
             stream.synchronize()
@@ -233,7 +259,7 @@ def run_gpu(args, rank, world, local_rank):
 
         # ---- per-kernel CUDA-event times (stream-launch mode, same workload continuing) ----------------------
         roof = None
-        if world == 1:
+        if world == 1 and not ensemble:
             solver.profile_begin(16384)
             solver.run(DT, max(1, min(3, args.steps)), sweeps=SWEEPS, has_old=HAS_OLD)
             kt = solver.profile_end()
@@ -260,7 +286,7 @@ def run_gpu(args, rank, world, local_rank):
         solver.close()
         # strong-scaling reference: the same 16384x4096 workload on ONE GPU (rank 0, after the slab handles are gone)
         strong = None
-        if world > 1:
+        if world > 1 and not ensemble:
             barrier()
             if rank == 0 and not args.no_single_gpu_ref:
                 one = make_solver_for_rank(mesh, cfg, 0, 1, tol=args.tol, loop_mode=args.loop_mode, precond=args.precond,
@@ -283,7 +309,7 @@ def run_gpu(args, rank, world, local_rank):
             barrier()
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not ensemble:
         snz, snr = 2048, 512
         v, secs = oracle_steps(snz, snr, 2, 0, args.precond)
         cpu = {'value': v, 'unit': 'cell-timesteps/s', 'cores': 1, 'kind': 'port',
@@ -293,10 +319,10 @@ def run_gpu(args, rank, world, local_rank):
         line = {
             'metric': 'cell-timesteps/s (incl. sweeps)', 'value': value, 'unit': 'cell-timesteps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak' if world == 1 else 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': f'synthetic composite mesh {nz}x{nr} (axial x radial), T-dependent properties, literal mode, '
-                                   f'dt={DT}s, updateOld + {SWEEPS} sweeps/step, PCG ({args.precond}) tol {args.tol:g} K',
-                       'parallelism': 'single GPU' if world == 1 else (f'axial slabs x{world}, ' + ('NVLink peer-memory halo rows + CG scalars fused into the PCG kernels, one CUDA graph per step' if args.comm == 'p2p' else 'NCCL send/recv halo + all-gathered CG scalars, host-driven loop')),
+            'scaling': 'weak' if (world == 1 or ensemble) else 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': (f'ensemble of {args.workload.split(":")[1] if ":" in args.workload else 1024} independent Faghri pipes (500x9 each, stacked), ' if ensemble else f'synthetic composite mesh {nz}x{nr} (axial x radial), ') +
+                                   f'T-dependent properties, literal mode, dt={DT}s, updateOld + {SWEEPS} sweeps/step, PCG ({args.precond}) tol {args.tol:g} K',
+                       'parallelism': 'single GPU' if world == 1 else (f'members sharded over {world} ranks, no collective' if ensemble else f'axial slabs x{world}, ' + ('NVLink peer-memory halo rows + CG scalars fused into the PCG kernels, one CUDA graph per step' if args.comm == 'p2p' else 'NCCL send/recv halo + all-gathered CG scalars, host-driven loop')),
                        'l2': 'working set (11 fp64 fields) exceeds the 126 MB L2; no flush needed',
                        'pcg_iterations_per_step': iters / args.steps, 'loop_mode': loop_mode,
                        'refactor_every_sweeps': args.refactor_every},
@@ -318,7 +344,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default=None, help='NZxNR, e.g. 4096x1024 (default) or 16384x4096')
+    ap.add_argument('--workload', default=None, help='NZxNR, e.g. 4096x1024 (default at N=1) or 16384x4096 (default at N>1), or ensemble[:M]')
     ap.add_argument('--tol', type=float, default=1e-9)
     ap.add_argument('--loop-mode', default='graph', choices=['graph', 'host'])
     ap.add_argument('--no-cpu-baseline', action='store_true')

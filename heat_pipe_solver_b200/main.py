@@ -42,7 +42,7 @@ def measurement_schedule(t_end, dt, measure_times):
 def run(config_file=None, *, t_end=101.0, dt=0.1, sweeps=1, has_old=False, h=5.0,
         properties='temperature_dependent', gamma='snapshot', source='q_over_k', face_k='masked_at_Tface',
         radiation=False, measure_every=5, measure_times=None, mesh_params=None, T0=None,
-        precond='rline', criterion='precond_inf', tol=1e-9, max_iter=5000, loop_mode='graph',
+        precond='auto', criterion='precond_inf', tol=1e-9, max_iter=5000, loop_mode='graph',
         capture_properties=True, verbose=False, device=None):
     """Transient conduction run.  Defaults = the reference's active code path (main.py:119-120,200-202:
     t_end=101 s, dt=0.1 s, one sweep per step with hasOld=False, h=5 W/m2K, temperature-dependent laws).

@@ -100,7 +100,7 @@ class ConductionSolver:
     def __init__(self, mesh, dimensions, parameters, constants, *, h=5.0, q=None, T_amb=None, emissivity=None,
                  properties='temperature_dependent', gamma='snapshot', source='q_over_k',
                  face_k='masked_at_Tface', radiation=False, axial_break=None, rows=None,
-                 precond='rline', criterion='precond_inf', tol=1e-9, max_iter=5000, loop_mode='graph',
+                 precond='auto', criterion='precond_inf', tol=1e-9, max_iter=5000, loop_mode='graph',
                  poll_chunk=8, refactor_every=1, extrapolate=True, mg_levels=6, mg_coarse_sweeps=2, mg_omega=0.7,
                  device=None, simple=(7200.0, 440.5, 55.0),
                  layout=None, regions=None):
@@ -152,6 +152,10 @@ class ConductionSolver:
             self._stream = torch.cuda.current_stream(self.device)
             _lib.check(self.lib.hp_create(C.byref(self._h), C.byref(md), C.byref(self.phys),
                                           C.c_void_p(self._stream.cuda_stream)), 'hp_create')
+        if precond == 'auto':
+            # multigrid pays off once the mesh is refined axially (mesh-independent iteration counts); on small meshes
+            # the solve is launch-latency bound and the plain radial-line preconditioner has fewer launches per iteration
+            precond = 'mgline' if (self.nz >= 256 and self.nz * self.nr >= 262144) else 'rline'
         self.set_options(precond=precond, criterion=criterion, tol=tol, max_iter=max_iter, loop_mode=loop_mode,
                          poll_chunk=poll_chunk, refactor_every=refactor_every, extrapolate=extrapolate,
                          mg_levels=mg_levels, mg_coarse_sweeps=mg_coarse_sweeps, mg_omega=mg_omega)
