@@ -110,6 +110,8 @@ struct hp_solver_s {
     HpComm* comm = nullptr;          // my mailbox
     double* qz_block = nullptr;      // base of the (q, z) allocation (IPC handle is per allocation)
     std::vector<void*> ipc_opened;
+    unsigned long long* gbar = nullptr;   // grid-barrier words of k_mg_subcycle
+    bool mg_fused = true;
     bool have_prev = false;          // Told holds the field of the previous step start (extrapolated PCG start)
     bool ghost_dirty = true;         // ghost rows of T must be refreshed by an explicit exchange before the next sweep
     // L2 access-policy window over the contiguous (q, z) block
@@ -206,6 +208,12 @@ static int setup_mg(hp_solver_s* h) {
         L0.rhs = d.r; L0.x = d.z; L0.tmp = d.q;
         if (dev_alloc(h, (void**)&L0.x2, h->field_elems * sizeof(double))) return -1;
         CK(cudaMemsetAsync(L0.x2, 0, h->field_elems * sizeof(double), h->stream));
+        if (dev_alloc(h, (void**)&h->gbar, 2 * sizeof(unsigned long long))) return -1;
+        CK(cudaMemsetAsync(h->gbar, 0, 2 * sizeof(unsigned long long), h->stream));
+        const char* ef = getenv("HP_MG_FUSED");
+        // measured on B200: inside the step graph the fused cycle (132 us) is no faster than its 21 separate launches
+        // (~6 us each), both are bound by the chain of dependent row latencies -> off unless asked for
+        h->mg_fused = (ef && ef[0] == '1') && hpk::mg_subcycle_supported(h->cfg);
         h->nlev_alloc = 1;
     }
     for (int l = h->nlev_alloc; l < want; ++l) {
@@ -239,7 +247,8 @@ enum { KIND_OTHER = 0, KIND_COEF, KIND_DIAG, KIND_FACTOR, KIND_INIT, KIND_A, KIN
 static int launch(hp_solver_s* h, const HpKernelLaunch& k, void** params, int kind = KIND_OTHER) {
     const bool prof = h->prof_on && h->prof_used < h->prof_ev.size() / 2;
     if (prof) CK(cudaEventRecord(h->prof_ev[2 * h->prof_used], h->stream));
-    CK(cudaLaunchKernel(k.func, k.grid, k.block, params, k.smem, h->stream));
+    if (k.cooperative) CK(cudaLaunchCooperativeKernel(k.func, k.grid, k.block, params, k.smem, h->stream));
+    else CK(cudaLaunchKernel(k.func, k.grid, k.block, params, k.smem, h->stream));
     if (prof) {
         CK(cudaEventRecord(h->prof_ev[2 * h->prof_used + 1], h->stream));
         h->prof_kind.push_back(kind);
@@ -465,6 +474,12 @@ static int chain_kernel(NodeChain& c, const HpKernelLaunch& k, void** params, co
     np.kernelParams = params; np.extra = nullptr;
     cudaGraphNode_t n;
     CK(cudaGraphAddKernelNode(&n, c.g, c.last ? &c.last : nullptr, c.last ? 1 : 0, &np));
+    if (k.cooperative) {
+        cudaKernelNodeAttrValue v;
+        memset(&v, 0, sizeof(v));
+        v.cooperative = 1;
+        CK(cudaGraphKernelNodeSetAttribute(n, cudaKernelNodeAttributeCooperative, &v));
+    }
     if (h && h->l2_on) {
         cudaKernelNodeAttrValue v;
         memset(&v, 0, sizeof(v));
@@ -577,18 +592,31 @@ static int emit_vcycle(Emitter& e, const HpKArgs& a_in, int init_phase) {
         }
         return 0;
     };
+    // same cycle in ONE cooperative launch (grid barriers instead of kernel boundaries) when the row-team shapes allow
+    auto fused = [&](HpLevel* Ls, int lo, int n, int part, const double* ec_top) -> int {
+        HpLevelSet ls;
+        ls.n = n;
+        for (int l = 0; l < n; ++l) ls.lev[l] = Ls[l];
+        HpSubcycleArgs sc{lo, n, h->opts.mg_coarse_sweeps, part, ec_top, h->gbar};
+        void* p[] = {&d, &a, &ls, &sc};
+        return emit(e, hpk::desc_mg_subcycle(h->cfg), p, KIND_MG_COARSE);
+    };
     HpLevel* L = h->lev;
     const int nl = h->nlev;
     // level 0 starts from omega * zline (its pre-smoothing is k_cg_B's line solve)
     if (res(L[0], true, d.z, nullptr, L[1].nz, L[0].x2, nullptr, L[1].rhs, a.omega)) return -1;
     const double* ec0 = L[1].x;          // coarse correction seen by level 0
     if (!h->g_active) {
-        if (subcycle(L, 1, nl)) return -1;
+        if (h->mg_fused ? fused(L, 1, nl, 0, nullptr) : subcycle(L, 1, nl)) return -1;
     } else {
         const int s = nl - 1;              // rows of local level s are one slice of the replicated global level 0
-        for (int l = 1; l < s; ++l) {
-            if (line(L[l], false, L[l].rhs, nullptr, L[l].x, 0)) return -1;
-            if (res(L[l], false, L[l].x, nullptr, L[l + 1].nz, nullptr, nullptr, L[l + 1].rhs, 1.0)) return -1;
+        if (h->mg_fused && s > 1) {
+            if (fused(L, 1, nl, 1, nullptr)) return -1;
+        } else {
+            for (int l = 1; l < s; ++l) {
+                if (line(L[l], false, L[l].rhs, nullptr, L[l].x, 0)) return -1;
+                if (res(L[l], false, L[l].x, nullptr, L[l + 1].nz, nullptr, nullptr, L[l + 1].rhs, 1.0)) return -1;
+            }
         }
         const int* skip = &d.st->mg_skip;
         HpGatherArgs g{};
@@ -600,12 +628,16 @@ static int emit_vcycle(Emitter& e, const HpKArgs& a_in, int init_phase) {
         int kind = HP_COMM_GRHS;
         void* pw[] = {&d, &kind, &skip};
         if (emit(e, hpk::desc_wait_flag(), pw, KIND_MG_COARSE)) return -1;
-        if (subcycle(h->glev, 0, h->nglev)) return -1;
+        if (h->mg_fused ? fused(h->glev, 0, h->nglev, 0, nullptr) : subcycle(h->glev, 0, h->nglev)) return -1;
         const double* mine = h->glev[0].x + (size_t)h->g_row0 * nr;      // my slice (ghost-inclusive indexing kept)
-        for (int l = s - 1; l >= 1; --l) {
-            const double* ec = (l == s - 1) ? mine : L[l + 1].x;
-            if (res(L[l], false, L[l].x, ec, L[l + 1].nz, L[l].x2, L[l].tmp, nullptr, 1.0)) return -1;
-            if (line(L[l], false, L[l].tmp, L[l].x2, L[l].x, 0)) return -1;
+        if (h->mg_fused && s > 1) {
+            if (fused(L, 1, nl, 2, mine)) return -1;
+        } else {
+            for (int l = s - 1; l >= 1; --l) {
+                const double* ec = (l == s - 1) ? mine : L[l + 1].x;
+                if (res(L[l], false, L[l].x, ec, L[l + 1].nz, L[l].x2, L[l].tmp, nullptr, 1.0)) return -1;
+                if (line(L[l], false, L[l].tmp, L[l].x2, L[l].x, 0)) return -1;
+            }
         }
         if (s == 1) ec0 = mine;
     }
@@ -642,7 +674,8 @@ static int emit_sweep_head(Emitter& e, HpKArgs& a, bool refactor, bool shift) {
     int write_dinv = (h->opts.precond == 0) ? 1 : 0;
     HpKArgs a0 = a;
     a0.use_cond = 0;
-    void* p40[] = {&d, &h->phys, &a0, &write_dinv};
+    int tprl = hpk::diag_tpr_log2(d.nr);
+    void* p40[] = {&d, &h->phys, &a0, &write_dinv, &tprl};
     if (emit(e, hpk::desc_diag(h->cfg, d), p40, KIND_DIAG)) return -1;
     if (emit_combine(e, a0, 0)) return -1;
     if (h->opts.precond >= 1 && refactor) {
@@ -752,7 +785,17 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
         ge.body_nodes = body.count;
     }
     ge.static_nodes = c.count;
-    CK(cudaGraphInstantiate(&ge.exec, ge.graph, 0));
+    {
+        cudaError_t ie = cudaGraphInstantiate(&ge.exec, ge.graph, 0);
+        if (ie != cudaSuccess && h->mg_fused && h->opts.precond == 2) {
+            // cooperative kernel nodes not accepted in this graph shape: rebuild with one launch per V-cycle stage
+            cudaGetLastError();
+            cudaGraphDestroy(ge.graph);
+            h->mg_fused = false;
+            return get_graph(h, dt, sweeps, has_old, update_old, out);
+        }
+        CK(ie);
+    }
     h->graphs.push_back(ge);
     *out = &h->graphs.back();
     return 0;
@@ -872,8 +915,8 @@ int hp_assemble_debug(hp_handle h, double dt, int has_old, double* d_cR, double*
     int rc = 0;
     if (h->phys.gamma == 1) rc = launch(h, hpk::desc_coef(h->cfg, d), params);
     if (!rc) {
-        int write_dinv = 0;
-        void* p4[] = {&d, &h->phys, &a, &write_dinv};
+        int write_dinv = 0, tprl = hpk::diag_tpr_log2(d.nr);
+        void* p4[] = {&d, &h->phys, &a, &write_dinv, &tprl};
         rc = launch(h, hpk::desc_diag(h->cfg, d), p4);
     }
     const long long n = (long long)d.nz * d.nr;

@@ -104,6 +104,15 @@ struct HpMgLineArgs {
     const double* rhs; const double* base; double* out; int final_;
 };
 
+// k_mg_subcycle: the complete V-cycle on levels lo..n-1 of a level set in ONE cooperative launch (grid barriers between
+// the stages instead of kernel boundaries: the coarse levels are launch-latency bound)
+struct HpSubcycleArgs {
+    int lo, n, sweeps;
+    int part;                   // 0 whole cycle; 1 down leg only (levels lo..n-2: smooth, restrict); 2 up leg only
+    const double* ec_top;       // part 2: correction prolonged into level n-2 (a slice of the replicated global level 0)
+    unsigned long long* gbar;   // [0] arrival counter (monotonic), [1] its value at the start of the next launch
+};
+
 // Per-launch scalar arguments shared by all kernels: signature (HpDev, hp_phys, HpKArgs [, extra]).
 struct HpKArgs {
     double dt;
@@ -139,6 +148,7 @@ struct HpKernelLaunch {
     const void* func;
     dim3 grid, block;
     size_t smem;
+    bool cooperative = false;   // all CTAs must be co-resident (grid barriers inside)
 };
 
 namespace hpk {
@@ -149,7 +159,8 @@ bool pick_config(int nr, int nz, int num_sms, HpLaunchCfg* cfg, const char** err
 HpKernelLaunch desc_snapshot_kout(const HpLaunchCfg&, const HpDev&);
 HpKernelLaunch desc_coef(const HpLaunchCfg&, const HpDev&);
 HpKernelLaunch desc_delta(const HpLaunchCfg&, const HpDev&);   // z = T - Told on every row (ghosts included)
-HpKernelLaunch desc_diag(const HpLaunchCfg&, const HpDev&);
+HpKernelLaunch desc_diag(const HpLaunchCfg&, const HpDev&);     // args: (HpDev, hp_phys, HpKArgs, int write_dinv, int tpr_log2)
+int diag_tpr_log2(int nr);
 HpKernelLaunch desc_factor(const HpLaunchCfg&, const HpDev&);
 HpKernelLaunch desc_cg_init(const HpLaunchCfg&, const HpDev&, int precond, int criterion);
 HpKernelLaunch desc_cg_A(const HpLaunchCfg&, const HpDev&);
@@ -157,6 +168,8 @@ HpKernelLaunch desc_cg_A(const HpLaunchCfg&, const HpDev&);
 HpKernelLaunch desc_mg_coarsen(const HpLaunchCfg&, int nzc, int nr);
 HpKernelLaunch desc_mg_res(const HpLaunchCfg&, int nz_level);
 HpKernelLaunch desc_mg_line(const HpLaunchCfg&, int nz_level);
+HpKernelLaunch desc_mg_subcycle(const HpLaunchCfg&);            // args: (HpDev, HpKArgs, HpLevelSet, HpSubcycleArgs); cooperative
+bool mg_subcycle_supported(const HpLaunchCfg&);
 HpKernelLaunch desc_factor_levels(int total_coarse_rows);   // args: (HpLevelSet, int nr, const int* skip)
 HpKernelLaunch desc_gather_rows(const HpLaunchCfg&, long long elems);  // args: (HpDev, HpGatherArgs, const int* skip)
 HpKernelLaunch desc_wait_flag();                                        // args: (HpDev, int kind, const int* skip)

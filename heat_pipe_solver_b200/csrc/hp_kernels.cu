@@ -388,48 +388,56 @@ __global__ void __launch_bounds__(256) k_coef(HpDev d, hp_phys ph, HpKArgs a) {
 //   rhs  = cap*T_old (+ Robin*g + evaporator)                                     main.py:146-150
 //   r    = rhs - L T          (PCG start residual; FiPy's `res` = ||L T - rhs||_2) main.py:202
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_diag(HpDev d, hp_phys ph, HpKArgs a, int write_dinv_jacobi) {
-    const long long n = (long long)d.nz * d.nr;
+__global__ void __launch_bounds__(256) k_diag(HpDev d, hp_phys ph, HpKArgs a, int write_dinv_jacobi, int tpr_log2) {
+    // rows over CTAs (and over row groups inside a CTA when a row is shorter than the CTA), columns over threads:
+    // no integer division per cell, per-row quantities read once
+    const int nr = d.nr;
+    const int tpr = 1 << tpr_log2, rpb = blockDim.x >> tpr_log2;
+    const int col0 = threadIdx.x & (tpr - 1), rsub = threadIdx.x >> tpr_log2;
     double acc[2] = {0.0, 0.0};
-    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
-        const int j = (int)(c / d.nr), i = (int)(c - (long long)j * d.nr), g = j + 1;
-        const long long idx = c + d.nr;
-        const double Tc = d.T[idx];
-        const double Told = a.has_old ? d.Told[idx] : Tc;
-        double rho, cp;
-        hp::rho_cp_region(ph, d.cell_band[i], d.zc_flags[g], Tc, rho, cp);
-        const double vol = d.wc[i] * d.dr[i] * d.dz[g];
-        const double cap = cp * rho * vol / a.dt;
-        const double cE = d.cR[idx], cW = d.cR[idx - 1], cN = d.cZ[idx], cS = d.cZ[idx - d.nr];
-        double dg = cap;
-        dg += cE; dg += cW; dg += cN; dg += cS;
-        double rhs = cap * Told;
-        if (i == d.nr - 1) {
-            const unsigned zf = d.zc_flags[g];
-            const double kout = k_outface(d, ph, g, Tc);
-            const double k0 = (ph.gamma == 0) ? d.k0_out[g] : kout;
-            const double A_out = d.A_out_r * d.dz[g];
-            const double h = d.h_line[g], Ta = d.Tamb_line[g];
-            if (zf & HP_ZF_BC_COND) {
-                const double robin = kout * A_out / (h * d.d_out + k0);
-                dg += robin * h;
-                double gs = h * Ta;
-                if (ph.radiation) gs += ph.sigma * d.eps_line[g] * (Ta * Ta * Ta * Ta - Tc * Tc * Tc * Tc);
-                rhs += robin * gs;
+    for (long long j = (long long)blockIdx.x * rpb + rsub; j < d.nz; j += (long long)gridDim.x * rpb) {
+        const int g = (int)j + 1;
+        const long long rb = (long long)g * nr;
+        const unsigned zf = d.zc_flags[g];
+        const double dzg = d.dz[g];
+        for (int i = col0; i < nr; i += tpr) {
+            const long long idx = rb + i;
+            const double Tc = d.T[idx];
+            const double Told = a.has_old ? d.Told[idx] : Tc;
+            double rho, cp;
+            hp::rho_cp_region(ph, d.cell_band[i], zf, Tc, rho, cp);
+            const double vol = d.wc[i] * d.dr[i] * dzg;
+            const double cap = cp * rho * vol / a.dt;
+            const double cE = d.cR[idx], cW = d.cR[idx - 1], cN = d.cZ[idx], cS = d.cZ[idx - nr];
+            double dg = cap;
+            dg += cE; dg += cW; dg += cN; dg += cS;
+            double rhs = cap * Told;
+            if (i == nr - 1) {
+                const double kout = k_outface(d, ph, g, Tc);
+                const double k0 = (ph.gamma == 0) ? d.k0_out[g] : kout;
+                const double A_out = d.A_out_r * dzg;
+                const double h = d.h_line[g], Ta = d.Tamb_line[g];
+                if (zf & HP_ZF_BC_COND) {
+                    const double robin = kout * A_out / (h * d.d_out + k0);
+                    dg += robin * h;
+                    double gs = h * Ta;
+                    if (ph.radiation) gs += ph.sigma * d.eps_line[g] * (Ta * Ta * Ta * Ta - Tc * Tc * Tc * Tc);
+                    rhs += robin * gs;
+                }
+                if (zf & HP_ZF_BC_EVAP) {
+                    const double q = d.q_line[g];
+                    rhs += ((ph.source == 0) ? (q / kout) : q) * A_out;
+                }
             }
-            if (zf & HP_ZF_BC_EVAP) {
-                const double q = d.q_line[g];
-                rhs += ((ph.source == 0) ? (q / kout) : q) * A_out;
-            }
+            const double LT = dg * Tc - cE * d.T[idx + 1] - cW * d.T[idx - 1] - cN * d.T[idx + nr] - cS * d.T[idx - nr];
+            const double r0 = rhs - LT;
+            d.diag[idx] = dg;
+            d.r[idx] = r0;
+            if (write_dinv_jacobi) d.dinv[idx] = 1.0 / dg;
+            if (a.rhs_out) a.rhs_out[idx] = rhs;
+            acc[0] += r0 * r0;
+            acc[1] += rhs * rhs;
         }
-        const double LT = dg * Tc - cE * d.T[idx + 1] - cW * d.T[idx - 1] - cN * d.T[idx + d.nr] - cS * d.T[idx - d.nr];
-        const double r0 = rhs - LT;
-        d.diag[idx] = dg;
-        d.r[idx] = r0;
-        if (write_dinv_jacobi) d.dinv[idx] = 1.0 / dg;
-        if (a.rhs_out) a.rhs_out[idx] = rhs;
-        acc[0] += r0 * r0;
-        acc[1] += rhs * rhs;
     }
     double tot[2];
     if (cta_publish<2>(acc, 0u, d.partials, &d.st->ticket, tot, d.p2p != 0) && threadIdx.x == 0) {
@@ -960,13 +968,10 @@ __global__ void __launch_bounds__(256) k_mg_coarsen(HpLevel f, HpLevel c, int nr
 //   res(g) = rhs(g) - (diag x - cR x_e - cR_w x_w - cZ x_n - cZ_s x_s) (couplings to ghost rows ignored)
 //   xout(g) = x(g) if xout;  resout(g) = res(g) if resout;  crhs(J) = res(2J) + res(2J+1) if crhs (RESTRICT)
 template <int TPL, int EPT, bool VEC>
-__global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_A(EPT))
-k_mg_res(HpDev d, HpKArgs a, HpLevel L, HpMgResArgs m) {
-    using G = TeamGeom<TPL>;
-    if (d.st->mg_skip) return;
+__device__ __forceinline__ void mg_res_body(const HpDev& d, const HpLevel& L, const HpMgResArgs& m, long long team,
+                                            long long nteams) {
     const int nr = d.nr, nz = L.nz;
-    const int team_in_cta = threadIdx.x / TPL, tl = threadIdx.x % TPL, lane = threadIdx.x & 31;
-    const long long team = (long long)blockIdx.x * G::LPC + team_in_cta, nteams = (long long)gridDim.x * G::LPC;
+    const int tl = threadIdx.x % TPL, lane = threadIdx.x & 31;
     const int ncol = d.ncolA;
     const long long nchunks = nteams / ncol;
     const long long chunk = team / ncol;
@@ -1073,23 +1078,28 @@ k_mg_res(HpDev d, HpKArgs a, HpLevel L, HpMgResArgs m) {
     }
 }
 
+template <int TPL, int EPT, bool VEC>
+__global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_A(EPT))
+k_mg_res(HpDev d, HpKArgs a, HpLevel L, HpMgResArgs m) {
+    using G = TeamGeom<TPL>;
+    if (d.st->mg_skip) return;
+    mg_res_body<TPL, EPT, VEC>(d, L, m, (long long)blockIdx.x * G::LPC + threadIdx.x / TPL, (long long)gridDim.x * G::LPC);
+}
+
 // ---- k_mg_line : out(g) = [base(g) +] omega * M_L^-1 rhs(g)       (row teams, same line solve as k_cg_B)
 // FINAL (level 0, end of the V-cycle): out is the preconditioned residual z of the PCG; accumulates r.z, pushes the
 // boundary rows under peer-memory slabs, and the last CTA advances beta / rz (finalize_B stage 2).
 template <int TPL, int EPT, bool VEC>
-__global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT))
-k_mg_line(HpDev d, HpKArgs a, HpLevel L, HpMgLineArgs m) {
-    using G = TeamGeom<TPL>;
-    if (d.st->mg_skip) return;
-    __shared__ double s_fA[G::LPC][G::NW], s_fB[G::LPC][G::NW], s_bA[G::LPC][G::NW], s_bB[G::LPC][G::NW];
+__device__ __forceinline__ double mg_line_body(const HpDev& d, double omega, const HpLevel& L, const HpMgLineArgs& m,
+                                               long long team, long long nteams, double* s_fA, double* s_fB, double* s_bA,
+                                               double* s_bB) {
     const int nr = d.nr, nz = L.nz;
     const int team_in_cta = threadIdx.x / TPL, tl = threadIdx.x % TPL, lane = threadIdx.x & 31;
     const int wt = tl >> 5;
     const int i0 = tl * EPT;
-    const long long team = (long long)blockIdx.x * G::LPC + team_in_cta, nteams = (long long)gridDim.x * G::LPC;
-    const int ja = (int)(team * nz / nteams), jb = (int)((team + 1) * nz / nteams);
-    const double omega = a.omega;
-    double acc[1] = {0.0};
+    int ja = 0, jb = 0;
+    if (team < nteams) { ja = (int)(team * nz / nteams); jb = (int)((team + 1) * nz / nteams); }
+    double acc = 0.0;
     for (int g = ja + 1; g <= jb; ++g) {
         const long long rb = (long long)g * nr;
         double rv[EPT], dv[EPT], cr[EPT], zv[EPT];
@@ -1101,20 +1111,32 @@ k_mg_line(HpDev d, HpKArgs a, HpLevel L, HpMgLineArgs m) {
         if (m.final_) load_row<EPT, VEC>(d.r + rb, i0, nr, r0);
         double m0_edge = 0.0;
         if (lane == 0 && tl != 0 && i0 < nr) m0_edge = L.cR[rb + i0 - 1] * L.dinv[rb + i0 - 1];
-        line_solve<TPL, EPT>(rv, dv, cr, m0_edge, lane, wt, team_in_cta, s_fA[team_in_cta], s_fB[team_in_cta],
-                             s_bA[team_in_cta], s_bB[team_in_cta], zv);
+        line_solve<TPL, EPT>(rv, dv, cr, m0_edge, lane, wt, team_in_cta, s_fA, s_fB, s_bA, s_bB, zv);
 #pragma unroll
         for (int k = 0; k < EPT; ++k) zv[k] = m.base ? fma(omega, zv[k], bs[k]) : omega * zv[k];
         store_row<EPT, VEC>(m.out + rb, i0, nr, zv);
         if (m.final_) {
 #pragma unroll
-            for (int k = 0; k < EPT; ++k) acc[0] = fma(r0[k], zv[k], acc[0]);
+            for (int k = 0; k < EPT; ++k) acc = fma(r0[k], zv[k], acc);
             if (d.p2p) {
                 if (g == 1 && d.z_lo) store_row<EPT, VEC>(d.z_lo, i0, nr, zv);
                 if (g == nz && d.z_hi) store_row<EPT, VEC>(d.z_hi, i0, nr, zv);
             }
         }
     }
+    return acc;
+}
+
+template <int TPL, int EPT, bool VEC>
+__global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT))
+k_mg_line(HpDev d, HpKArgs a, HpLevel L, HpMgLineArgs m) {
+    using G = TeamGeom<TPL>;
+    if (d.st->mg_skip) return;
+    __shared__ double s_fA[G::LPC][G::NW], s_fB[G::LPC][G::NW], s_bA[G::LPC][G::NW], s_bB[G::LPC][G::NW];
+    const int tic = threadIdx.x / TPL;
+    double acc[1];
+    acc[0] = mg_line_body<TPL, EPT, VEC>(d, a.omega, L, m, (long long)blockIdx.x * G::LPC + tic, (long long)gridDim.x * G::LPC,
+                                         s_fA[tic], s_fB[tic], s_bA[tic], s_bB[tic]);
     if (m.final_) {
         double tot[1];
         if (cta_publish<1>(acc, 0u, d.partials, &d.st->ticket, tot, d.p2p != 0) && threadIdx.x == 0) {
@@ -1123,6 +1145,84 @@ k_mg_line(HpDev d, HpKArgs a, HpLevel L, HpMgLineArgs m) {
         }
     }
 }
+
+// ---- k_mg_subcycle : the V-cycle below the fine level in one cooperative launch -----------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// all CTAs of the (co-resident) grid; `target` = counter value once every CTA has arrived.  Bounded: a missing CTA sets
+// the sticky error bit instead of hanging the GPU.
+__device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target, HpState* st) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1ull);
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_gpu(ctr) < target) {
+            if (global_ns() - t0 > 2000000000ull) { st->flags |= 8; break; }
+        }
+    }
+    __syncthreads();
+    __threadfence();        // gpu-scope fence: invalidates this SM's L1 so rows written by other SMs are re-fetched
+}
+
+template <int TPL, int EPT, bool VEC>
+__global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_A(EPT))
+k_mg_subcycle(HpDev d, HpKArgs a, HpLevelSet ls, HpSubcycleArgs sc) {
+    using G = TeamGeom<TPL>;
+    if (d.st->mg_skip) return;
+    __shared__ double s_fA[G::LPC][G::NW], s_fB[G::LPC][G::NW], s_bA[G::LPC][G::NW], s_bB[G::LPC][G::NW];
+    const int tic = threadIdx.x / TPL;
+    const long long team = (long long)blockIdx.x * G::LPC + tic, total = (long long)gridDim.x * G::LPC;
+    const unsigned long long base = sc.gbar[1];
+    unsigned long long nb = 0;
+    const double omega = a.omega;
+    auto sync = [&]() { ++nb; grid_barrier(&sc.gbar[0], base + nb * gridDim.x, d.st); };
+    auto teams_for = [&](int nz) -> long long {           // >= 2 rows per team, whole column-tile groups
+        long long t = (nz + 1) / 2;
+        t = t < 1 ? 1 : t;
+        t *= d.ncolA;
+        return t < total ? t : (total / d.ncolA) * d.ncolA;
+    };
+    auto line = [&](int l, const double* rhs, const double* bs, double* out) {
+        HpMgLineArgs m{rhs, bs, out, 0};
+        long long nt = teams_for(ls.lev[l].nz) / d.ncolA;
+        (void)mg_line_body<TPL, EPT, VEC>(d, omega, ls.lev[l], m, team, nt, s_fA[tic], s_fB[tic], s_bA[tic], s_bB[tic]);
+        sync();
+    };
+    auto res = [&](int l, const double* xin, const double* ec, int nzc, double* xout, double* resout, double* crhs) {
+        HpMgResArgs m{xin, ec, xout, resout, crhs, 1.0, nzc};
+        mg_res_body<TPL, EPT, VEC>(d, ls.lev[l], m, team, teams_for(ls.lev[l].nz));
+        sync();
+    };
+    HpLevel* L = ls.lev;
+    const int c = sc.n - 1;
+    if (sc.part != 2) {
+        for (int l = sc.lo; l < c; ++l) {
+            line(l, L[l].rhs, nullptr, L[l].x);
+            res(l, L[l].x, nullptr, L[l + 1].nz, nullptr, nullptr, L[l + 1].rhs);
+        }
+    }
+    if (sc.part == 0) {
+        line(c, L[c].rhs, nullptr, L[c].x);
+        for (int k = 0; k < sc.sweeps; ++k) {
+            res(c, L[c].x, nullptr, 1, nullptr, L[c].tmp, nullptr);
+            line(c, L[c].tmp, L[c].x, L[c].x);
+        }
+    }
+    if (sc.part != 1) {
+        for (int l = c - 1; l >= sc.lo; --l) {
+            const double* ec = (sc.part == 2 && l == c - 1) ? sc.ec_top : L[l + 1].x;
+            res(l, L[l].x, ec, L[l + 1].nz, L[l].x2, L[l].tmp, nullptr);
+            line(l, L[l].tmp, L[l].x2, L[l].x);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) sc.gbar[1] = base + nb * gridDim.x;
+}
+template <int TPL, int EPT, bool VEC>
+const void* fn_mg_subcycle() { return (const void*)k_mg_subcycle<TPL, EPT, VEC>; }
 
 template <int TPL, int EPT, bool VEC>
 const void* fn_mg_res() { return (const void*)k_mg_res<TPL, EPT, VEC>; }
@@ -1248,8 +1348,19 @@ HpKernelLaunch desc_coef(const HpLaunchCfg& c, const HpDev& d) {
 HpKernelLaunch desc_delta(const HpLaunchCfg& c, const HpDev& d) {
     return {(const void*)k_delta, dim3(c.grid_cell), dim3(c.cta_cell), 0};
 }
+int diag_tpr_log2(int nr) {
+    int l = 0;
+    while ((1 << l) < nr && l < 8) ++l;
+    return l;                                   // threads per row = min(256, next power of two >= nr)
+}
 HpKernelLaunch desc_diag(const HpLaunchCfg& c, const HpDev& d) {
-    return {(const void*)k_diag, dim3(c.grid_cell), dim3(c.cta_cell), 0};
+    const int rpb = 256 >> diag_tpr_log2(d.nr);
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_diag, 256, 0) != cudaSuccess || occ < 1) occ = 1;
+    long long g = ((long long)d.nz + rpb - 1) / rpb, cap = (long long)c.num_sms * occ;
+    if (g > cap) g = cap;
+    if (g > HP_MAX_PARTIALS) g = HP_MAX_PARTIALS;
+    return {(const void*)k_diag, dim3((unsigned)(g < 1 ? 1 : g)), dim3(256), 0};
 }
 HpKernelLaunch desc_factor(const HpLaunchCfg& c, const HpDev& d) {
     return {(const void*)k_factor_rline, dim3(c.grid_factor), dim3(c.cta_factor), 0};
@@ -1276,6 +1387,21 @@ HpKernelLaunch desc_mg_line(const HpLaunchCfg& c, int nz_level) {
     HpLaunchCfg cl = c;
     cl.nz = nz_level;
     return {f, dim3(team_grid(f, cl, c.cta_threads, c.teams_per_cta, 1)), dim3(c.cta_threads), 0};
+}
+// the fused cycle needs the row teams of the residual and of the line solve to have the same shape (nr <= 1024)
+bool mg_subcycle_supported(const HpLaunchCfg& c) {
+    return c.tplA == c.tpl && c.eptA == c.ept && c.vecA == c.vec && c.ctaA == c.cta_threads;
+}
+HpKernelLaunch desc_mg_subcycle(const HpLaunchCfg& c) {
+    const void* f = nullptr;
+#define HP_X(T, E, V) f = fn_mg_subcycle<T, E, V>()
+    HP_DISPATCH_A(c, HP_X);
+#undef HP_X
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f, c.ctaA, 0) != cudaSuccess || occ < 1) occ = 1;
+    HpKernelLaunch k{f, dim3(c.num_sms * occ), dim3(c.ctaA), 0};
+    k.cooperative = true;
+    return k;
 }
 HpKernelLaunch desc_factor_levels(int total_coarse_rows) {
     return {(const void*)k_factor_levels, dim3((total_coarse_rows + 31) / 32), dim3(32), 0};

@@ -43,10 +43,16 @@ def run(config_file=None, *, t_end=101.0, dt=0.1, sweeps=1, has_old=False, h=5.0
         properties='temperature_dependent', gamma='snapshot', source='q_over_k', face_k='masked_at_Tface',
         radiation=False, measure_every=5, measure_times=None, mesh_params=None, T0=None,
         precond='auto', criterion='precond_inf', tol=1e-9, max_iter=5000, loop_mode='graph',
-        capture_properties=True, verbose=False, device=None):
+        capture_properties=True, verbose=False, device=None, sweep_tol=None, max_sweeps=50,
+        checkpoint=None, checkpoint_every=None, resume=None, extrapolate=True):
     """Transient conduction run.  Defaults = the reference's active code path (main.py:119-120,200-202:
     t_end=101 s, dt=0.1 s, one sweep per step with hasOld=False, h=5 W/m2K, temperature-dependent laws).
     The commented "sweep" variant (main.py:267-271) is ``sweeps=5, has_old=True``.
+
+    Extras beyond the reference: ``sweeps='auto'`` (or ``sweep_tol``) re-sweeps every step until FiPy's
+    pre-solve residual drops below ``sweep_tol`` (default 1e-8) or ``max_sweeps``; ``checkpoint=path`` writes an ``.npz``
+    (field, old field, step index, loop time, captured profiles) every ``checkpoint_every`` steps and at the end,
+    ``resume=path`` continues such a run (identical to solver tolerance; bit-identical with ``extrapolate=False``).
 
     Returns a dict: ``T`` (nz, nr) final field, ``times`` / ``profiles`` (top-wall axial temperature profiles,
     main.py:208-209), ``residuals`` (FiPy-style pre-solve residual at each capture), property profiles
@@ -67,7 +73,8 @@ def run(config_file=None, *, t_end=101.0, dt=0.1, sweeps=1, has_old=False, h=5.0
 
     solver = ConductionSolver(mesh, dimensions, parameters, constants, h=h, properties=properties, gamma=gamma,
                               source=source, face_k=face_k, radiation=radiation, precond=precond,
-                              criterion=criterion, tol=tol, max_iter=max_iter, loop_mode=loop_mode, device=device)
+                              criterion=criterion, tol=tol, max_iter=max_iter, loop_mode=loop_mode, device=device,
+                              extrapolate=extrapolate)
     try:
         if T0 is not None:
             solver.set_value(T0)
@@ -99,13 +106,53 @@ def run(config_file=None, *, t_end=101.0, dt=0.1, sweeps=1, has_old=False, h=5.0
             print(f"Simulating for {t_end} seconds...")                    # main.py:197
         start = time.time()
         done = 0
-        for step, t in captures:
-            solver.run(dt, step + 1 - done, sweeps=sweeps, has_old=has_old)
-            done = step + 1
-            capture(t)
-        if done < len(times):
-            solver.run(dt, len(times) - done, sweeps=sweeps, has_old=has_old)
+        auto = (sweeps == 'auto') or (sweep_tol is not None)
+        stol = 1e-8 if sweep_tol is None else float(sweep_tol)
+        sweep_counts = []
+        if resume is not None:
+            ck = np.load(resume, allow_pickle=False)
+            if tuple(ck['shape']) != tuple(mesh.shape) or float(ck['dt']) != float(dt):
+                raise ValueError("checkpoint does not match this mesh / dt")
+            solver.set_value(ck['T'])
+            done = int(ck['step'])
+            for key in out:
+                if 'ck_' + key in ck.files:
+                    out[key] = list(ck['ck_' + key])
+
+        def write_checkpoint(step_index):
+            np.savez(checkpoint, T=solver.value.reshape(mesh.shape), step=step_index, dt=dt, shape=np.array(mesh.shape),
+                     t=float(times[step_index - 1]) + dt if step_index else 0.0,
+                     **{'ck_' + k: np.array(v) for k, v in out.items() if k in ('times', 'residuals', 'profiles')})
+
+        def advance(n):
+            """n time steps; fixed sweep count = back-to-back graph launches, 'auto' = residual-controlled sweeps."""
+            if not auto:
+                solver.run(dt, n, sweeps=sweeps, has_old=has_old)
+                return
+            for _ in range(n):
+                solver.update_old()
+                k = 0
+                while True:
+                    res = solver.sweep(dt, has_old=True)
+                    k += 1
+                    if res <= stol or k >= max_sweeps:
+                        break
+                sweep_counts.append(k)
+
+        stops = sorted(set([s + 1 for s, _ in captures if s + 1 > done] + [len(times)] +
+                           (list(range(done + checkpoint_every, len(times), checkpoint_every)) if checkpoint and checkpoint_every else [])))
+        cap_at = {s + 1: t for s, t in captures}
+        for stop in stops:
+            if stop > done:
+                advance(stop - done)
+                done = stop
+            if stop in cap_at and (not out['times'] or out['times'][-1] < cap_at[stop]):
+                capture(cap_at[stop])
+            if checkpoint and checkpoint_every and stop % checkpoint_every == 0:
+                write_checkpoint(stop)
         solver.synchronize()
+        if checkpoint:
+            write_checkpoint(done)
         elapsed = time.time() - start
         if verbose:
             print(f"Simulated time: {t_end} seconds")                      # main.py:337
@@ -114,7 +161,8 @@ def run(config_file=None, *, t_end=101.0, dt=0.1, sweeps=1, has_old=False, h=5.0
         result = {k: (np.array(v) if k in ('times', 'residuals') else v) for k, v in out.items()}
         result['profiles'] = np.array(out['profiles'])
         result.update(T=solver.value.reshape(mesh.shape), n_steps=len(times), iterations=solver.total_iters,
-                      sweeps=solver.total_sweeps, elapsed=elapsed, mesh=mesh, kernel_launches=solver.kernel_launches)
+                      sweeps=solver.total_sweeps, elapsed=elapsed, mesh=mesh, kernel_launches=solver.kernel_launches,
+                      sweeps_per_step=np.array(sweep_counts))
         return result
     finally:
         solver.close()

@@ -242,6 +242,29 @@ def test_extrapolated_start_saves_iterations_same_answer(cfg):
     assert np.max(np.abs(T - o.T)) <= 6 * PER_STEP_TOL_K
 
 
+def test_checkpoint_resume_and_auto_sweeps(cfg, tmp_path):
+    """checkpoint / resume of (T, step) and the sweep-to-convergence controller."""
+    from heat_pipe_solver_b200.main import run
+    ck = str(tmp_path / 'ck.npz')
+    full = run(t_end=12.0, dt=0.1, capture_properties=False, extrapolate=False)
+    first = run(t_end=6.0, dt=0.1, capture_properties=False, checkpoint=ck, extrapolate=False)
+    assert first['n_steps'] == 60
+    second = run(t_end=12.0, dt=0.1, capture_properties=False, resume=ck, extrapolate=False)
+    assert np.array_equal(second['times'], full['times'])
+    assert np.max(np.abs(second['T'] - full['T'])) <= 1e-9
+    assert np.max(np.abs(second['profiles'] - full['profiles'])) <= 1e-9
+    # residual-controlled sweeps: stops early once the nonlinear residual is below the tolerance
+    auto = run(t_end=2.0, dt=0.5, sweeps='auto', sweep_tol=1e-7, capture_properties=False, T0=None)
+    assert len(auto['sweeps_per_step']) == 4 and 2 <= auto['sweeps_per_step'].max() <= 10
+    grid = fo.build_grid(cfg['mesh'], cfg['dimensions'])
+    o = fo.Oracle(grid, fo.case_from_config(), has_old=True)
+    for n in auto['sweeps_per_step']:
+        o.update_old()
+        for _ in range(int(n)):
+            o.sweep(0.5, solver='banded')
+    assert np.max(np.abs(auto['T'] - o.T)) <= END_TOL_K
+
+
 def test_simple_properties_run(cfg):
     """BASELINE configs[0]: constant rho, cp, k (main.py:41-46); linear problem."""
     from heat_pipe_solver_b200.main import run

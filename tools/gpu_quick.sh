@@ -1,12 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
 echo "== pytest gpu"; timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -8
-for e in 1 0; do
-echo "== bench extrapolate=$e"; HP_EXTRAP=$e timeout 900 python bench.py --steps ${STEPS:-20} --warmup 3 --no-cpu-baseline > gpurun_out/bench_e$e.json 2> gpurun_out/bench_e$e.err; echo rc=$?; tail -3 gpurun_out/bench_e$e.err
-python - <<PY
-import json
-d=json.loads([l for l in open('gpurun_out/bench_e$e.json') if l.startswith('{')][0])
-print('ms/step',d['ms_per_step'],'value %.4e'%d['value'],'e2e %.4e'%d['e2e']['value'],'its',d['config']['pcg_iterations_per_step'])
-print([ (s['iters'], '%.2e'%s['residual_l2']) for s in d['last_sweep_stats']])
-PY
-done
+echo "== bench"; python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2> gpurun_out/q.err | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); k=d['roofline']['all_kernels']
+print('ms/step %.3f value %.4e e2e %.4e its %.2f' % (d['ms_per_step'], d['value'], d['e2e']['value'], d['config']['pcg_iterations_per_step']))
+print({n:(k[n]['launches'], round(k[n]['avg_ms']*1e3,1)) for n in k})
+print({x:d['roofline'][x] for x in ('kernel','achieved','frac','traffic','share_of_step')})" || tail -5 gpurun_out/q.err
+echo "== ensemble"; python bench.py --workload ensemble:1024 --steps 10 --warmup 3 --precond rline 2> gpurun_out/q2.err | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('ensemble1024: ms/step %.3f value %.4e its %.1f' % (d['ms_per_step'], d['value'], d['config']['pcg_iterations_per_step']))" || tail -5 gpurun_out/q2.err
