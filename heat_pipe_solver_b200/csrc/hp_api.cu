@@ -112,6 +112,7 @@ struct hp_solver_s {
     std::vector<void*> ipc_opened;
     unsigned long long* gbar = nullptr;   // grid-barrier words of k_mg_subcycle
     bool mg_fused = true;
+    bool pdl = false;                 // programmatic dependent launch edges between the kernel nodes of the step graph
     bool have_prev = false;          // Told holds the field of the previous step start (extrapolated PCG start)
     bool ghost_dirty = true;         // ghost rows of T must be refreshed by an explicit exchange before the next sweep
     // L2 access-policy window over the contiguous (q, z) block
@@ -342,6 +343,9 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
     CK(cudaMallocHost((void**)&h->h_state, sizeof(HpState)));
 
     h->opts.precond = 1; h->opts.criterion = 0; h->opts.tol = 1e-9; h->opts.max_iter = 5000;
+    // measured on B200: programmatic edges make the step SLOWER (mgline 8.97 -> 10.70 ms, rline 18.2 -> 19.4 ms; the
+    // early-scheduled dependents compete for SM slots with the draining grid) -> opt-in only (HP_PDL=1)
+    { const char* e = getenv("HP_PDL"); h->pdl = (e && e[0] == '1'); }
     h->opts.loop_mode = 1; h->opts.poll_chunk = 8; h->opts.refactor_every = 1; h->opts.extrapolate = 1;
     h->opts.mg_levels = 6; h->opts.mg_coarse_sweeps = 2; h->opts.mg_omega = 0.7;
 
@@ -467,13 +471,29 @@ static int exchange_rows(hp_solver_s* h, double* field) {
 // ---- emission of the sweep either as plain stream launches or as CUDA-graph kernel nodes --------------------------------
 struct NodeChain {
     cudaGraph_t g; cudaGraphNode_t last = nullptr; int count = 0;
+    bool last_is_kernel = false;      // a programmatic (PDL) edge may only connect two kernel nodes
 };
 static int chain_kernel(NodeChain& c, const HpKernelLaunch& k, void** params, const hp_solver_s* h = nullptr) {
-    cudaKernelNodeParams np{};
-    np.func = (void*)k.func; np.gridDim = k.grid; np.blockDim = k.block; np.sharedMemBytes = (unsigned)k.smem;
-    np.kernelParams = params; np.extra = nullptr;
     cudaGraphNode_t n;
-    CK(cudaGraphAddKernelNode(&n, c.g, c.last ? &c.last : nullptr, c.last ? 1 : 0, &np));
+    const bool pdl = h && h->pdl && c.last && c.last_is_kernel && !k.cooperative;
+    if (pdl) {
+        // programmatic edge: the node may be scheduled while its predecessor drains; every kernel starts with
+        // griddepcontrol.wait (pdl_enter), which restores full completion + memory visibility
+        cudaGraphNodeParams gp{};
+        gp.type = cudaGraphNodeTypeKernel;
+        gp.kernel.func = (void*)k.func; gp.kernel.gridDim = k.grid; gp.kernel.blockDim = k.block;
+        gp.kernel.sharedMemBytes = (unsigned)k.smem; gp.kernel.kernelParams = params; gp.kernel.extra = nullptr;
+        cudaGraphEdgeData ed;
+        memset(&ed, 0, sizeof(ed));
+        ed.from_port = cudaGraphKernelNodePortProgrammatic;
+        ed.type = cudaGraphDependencyTypeProgrammatic;
+        CK(cudaGraphAddNode_v2(&n, c.g, &c.last, &ed, 1, &gp));
+    } else {
+        cudaKernelNodeParams np{};
+        np.func = (void*)k.func; np.gridDim = k.grid; np.blockDim = k.block; np.sharedMemBytes = (unsigned)k.smem;
+        np.kernelParams = params; np.extra = nullptr;
+        CK(cudaGraphAddKernelNode(&n, c.g, c.last ? &c.last : nullptr, c.last ? 1 : 0, &np));
+    }
     if (k.cooperative) {
         cudaKernelNodeAttrValue v;
         memset(&v, 0, sizeof(v));
@@ -487,6 +507,7 @@ static int chain_kernel(NodeChain& c, const HpKernelLaunch& k, void** params, co
         CK(cudaGraphKernelNodeSetAttribute(n, cudaKernelNodeAttributeAccessPolicyWindow, &v));
     }
     c.last = n; c.count++;
+    c.last_is_kernel = !k.cooperative;
     return 0;
 }
 
@@ -763,7 +784,7 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
         cudaGraphNode_t n;
         CK(cudaGraphAddMemcpyNode1D(&n, ge.graph, c.last ? &c.last : nullptr, c.last ? 1 : 0, d.Told, d.T,
                                     (size_t)(d.nz + 2) * d.nr * sizeof(double), cudaMemcpyDeviceToDevice));
-        c.last = n;
+        c.last = n; c.last_is_kernel = false;
     }
     for (int s = 0; s < sweeps; ++s) {
         HpKArgs a = make_args(h, dt, has_old);
@@ -778,7 +799,7 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
         cp.conditional.size = 1;
         cudaGraphNode_t wn;
         CK(cudaGraphAddNode(&wn, ge.graph, c.last ? &c.last : nullptr, c.last ? 1 : 0, &cp));
-        c.last = wn;
+        c.last = wn; c.last_is_kernel = false;
         NodeChain body{cp.conditional.phGraph_out[0]};
         Emitter eb{h, &body};
         if (emit_iteration(eb, a)) return -1;
@@ -787,11 +808,11 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
     ge.static_nodes = c.count;
     {
         cudaError_t ie = cudaGraphInstantiate(&ge.exec, ge.graph, 0);
-        if (ie != cudaSuccess && h->mg_fused && h->opts.precond == 2) {
-            // cooperative kernel nodes not accepted in this graph shape: rebuild with one launch per V-cycle stage
+        if (ie != cudaSuccess && (h->pdl || (h->mg_fused && h->opts.precond == 2))) {
+            // programmatic edges / cooperative nodes not accepted in this graph shape: rebuild without them
             cudaGetLastError();
             cudaGraphDestroy(ge.graph);
-            h->mg_fused = false;
+            if (h->pdl) h->pdl = false; else h->mg_fused = false;
             return get_graph(h, dt, sweeps, has_old, update_old, out);
         }
         CK(ie);

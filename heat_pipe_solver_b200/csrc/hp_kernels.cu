@@ -26,6 +26,15 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: inside the step graph consecutive kernel nodes are linked by programmatic edges, so a
+// kernel may be scheduled while its predecessor drains.  EVERY kernel starts with this: it blocks until the predecessor
+// grid has completed and its writes are visible, then lets its own successor be scheduled early.  Without the edge
+// (plain stream launches) both instructions are no-ops.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ void ld256(const double* p, double* v) {
     asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
@@ -255,6 +264,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // the same kernel sequence), then lane 0 combines the sums in rank order and advances the scalar recurrences.
 // A bounded wait (2 s): on timeout the sweep is aborted with flags bit3 instead of hanging the GPU.
 __global__ void k_wait(HpDev d, hp_phys ph, HpKArgs a, int fin_kind) {
+    pdl_enter();
     const int kind = (fin_kind == FIN_DIAG) ? HP_COMM_DIAG : (fin_kind == FIN_A ? HP_COMM_A : (fin_kind == FIN_MGFINAL ? HP_COMM_MG : HP_COMM_B));
     HpState* s = d.st;
     if ((fin_kind == FIN_A || fin_kind == FIN_B) && s->done) return;
@@ -291,6 +301,7 @@ __global__ void k_wait(HpDev d, hp_phys ph, HpKArgs a, int fin_kind) {
 }
 
 __global__ void k_finalize(HpDev d, hp_phys ph, HpKArgs a, int kind) {
+    pdl_enter();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if ((kind == FIN_A || kind == FIN_B) && d.st->done) return;
     if (kind == FIN_MGFINAL && d.st->mg_skip) return;
@@ -348,6 +359,7 @@ __device__ __forceinline__ double k_outface(const HpDev& d, const hp_phys& ph, i
 // k_snapshot_kout : k0_out[g] = k(outer face, T_amb[g])                       grid: rows
 // ------------------------------------------------------------------------------------------------
 __global__ void k_snapshot_kout(HpDev d, hp_phys ph, HpKArgs a, double* k0_out) {
+    pdl_enter();
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < d.nz + 2) k0_out[g] = k_outface(d, ph, g, d.Tamb_line[g]);
 }
@@ -359,6 +371,7 @@ __global__ void k_snapshot_kout(HpDev d, hp_phys ph, HpKArgs a, double* k0_out) 
 //   wf = r_v, wc = r_c on CylindricalGrid2D (areas / volumes per radian); 1 on a Cartesian Grid2D
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_coef(HpDev d, hp_phys ph, HpKArgs a) {
+    pdl_enter();
     const long long n = (long long)(d.nz + 1) * d.nr;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -389,6 +402,7 @@ __global__ void __launch_bounds__(256) k_coef(HpDev d, hp_phys ph, HpKArgs a) {
 //   r    = rhs - L T          (PCG start residual; FiPy's `res` = ||L T - rhs||_2) main.py:202
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_diag(HpDev d, hp_phys ph, HpKArgs a, int write_dinv_jacobi, int tpr_log2) {
+    pdl_enter();
     // rows over CTAs (and over row groups inside a CTA when a row is shorter than the CTA), columns over threads:
     // no integer division per cell, per-row quantities read once
     const int nr = d.nr;
@@ -495,6 +509,7 @@ __device__ __forceinline__ void factor_row(const double* __restrict__ dg, const 
 }
 
 __global__ void __launch_bounds__(32) k_factor_rline(HpDev d, hp_phys ph, HpKArgs a) {
+    pdl_enter();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= d.nz) return;
     const long long base = (long long)(j + 1) * d.nr;
@@ -606,6 +621,7 @@ __device__ __forceinline__ void line_solve(const double (&rv)[EPT], const double
 // last CTA: alpha = rz/pq, parity ^= 1, first = 0
 template <int TPL, int EPT, bool VEC, int MINB = TeamGeom<TPL>::minb_A(EPT)>
 __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, MINB) k_cg_A(HpDev d, hp_phys ph, HpKArgs a) {
+    pdl_enter();
     using G = TeamGeom<TPL>;
     const HpState s0 = *d.st;
     if (s0.done) return;
@@ -724,6 +740,7 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, MINB) k_cg_A(HpDev d, hp_p
 // last CTA: beta = rz_new/rz, iter++, convergence flag, sweep statistics, WHILE condition
 template <int TPL, int EPT, bool VEC, bool RLINE, bool INIT>
 __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT)) k_cg_B(HpDev d, hp_phys ph, HpKArgs a) {
+    pdl_enter();
     using G = TeamGeom<TPL>;
     const HpState s0 = *d.st;
     if (!INIT && s0.done) return;
@@ -819,6 +836,7 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT)
 // auxiliary kernels
 // ------------------------------------------------------------------------------------------------
 __global__ void k_eval_property(hp_phys ph, int id, const double* __restrict__ T, double* __restrict__ out, long long n) {
+    pdl_enter();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = hp::eval_property(ph, id, T[i]);
 }
@@ -826,6 +844,7 @@ __global__ void k_eval_property(hp_phys ph, int id, const double* __restrict__ T
 // rho, cp per owned cell; kavg = mean of k over the cell's 4 faces (main.py:243: k.value[cellFaceIDs] mean)
 __global__ void k_cell_fields(HpDev d, hp_phys ph, double* __restrict__ rho_o, double* __restrict__ cp_o,
                               double* __restrict__ kavg_o) {
+    pdl_enter();
     const long long n = (long long)d.nz * d.nr;
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(c / d.nr), i = (int)(c - (long long)j * d.nr), g = j + 1;
@@ -857,12 +876,14 @@ __global__ void k_cell_fields(HpDev d, hp_phys ph, double* __restrict__ rho_o, d
 
 // rhs (owned rows, compact nz*nr) from a ghost-inclusive scratch array
 __global__ void k_copy_owned(const double* __restrict__ src_ghost, double* __restrict__ dst, int nr, long long n) {
+    pdl_enter();
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x)
         dst[c] = src_ghost[c + nr];
 }
 
 // field[g,:] = Tamb_line[g] for all rows incl. ghosts  (main.py:34,152)
 __global__ void k_fill_rows(HpDev d, double* __restrict__ field) {
+    pdl_enter();
     const long long n = (long long)(d.nz + 2) * d.nr;
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x)
         field[c] = d.Tamb_line[(int)(c / d.nr)];
@@ -871,6 +892,7 @@ __global__ void k_fill_rows(HpDev d, double* __restrict__ field) {
 // z = T - Told on every row: the increment of the previous time step, used as the extrapolated start of the
 // first solve of the next step (x0 = T + (T - T_prev); the system itself is still assembled at T, like FiPy's)
 __global__ void __launch_bounds__(256) k_delta(HpDev d, hp_phys ph, HpKArgs a) {
+    pdl_enter();
     const long long n = (long long)(d.nz + 2) * d.nr;
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x)
         d.z[c] = d.T[c] - d.Told[c];
@@ -892,6 +914,7 @@ __device__ __forceinline__ void signal_all(const HpDev& d, int kind) {
 }
 
 __global__ void __launch_bounds__(256) k_gather_rows(HpDev d, HpGatherArgs g, const int* skip) {
+    pdl_enter();
     if (*skip) return;
     const long long per = (long long)g.nrows * d.nr, n = per * g.nsrc;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
@@ -918,6 +941,7 @@ __global__ void __launch_bounds__(256) k_gather_rows(HpDev d, HpGatherArgs g, co
 
 // wait (bounded) until every rank has signalled `kind` as often as this rank has
 __global__ void k_wait_flag(HpDev d, int kind, const int* skip) {
+    pdl_enter();
     if (*skip) return;
     const int lane = threadIdx.x;
     const HpComm* mine = d.comm_peer[d.rank];
@@ -948,6 +972,7 @@ __global__ void k_wait_flag(HpDev d, int kind, const int* skip) {
 // coarse level from a fine one:  cR_c = cR[2J] + cR[2J+1],  cZ_c = coupling of the pair's top row to the next pair,
 // diag_c = diag[2J] + diag[2J+1] - 2 cZ[2J]  (P^T A P with P = row-pair injection).      thread per coarse cell
 __global__ void __launch_bounds__(256) k_mg_coarsen(HpLevel f, HpLevel c, int nr, const int* skip) {
+    pdl_enter();
     if (*skip) return;
     const long long n = (long long)c.nz * nr;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
@@ -1081,6 +1106,7 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpLevel& L, co
 template <int TPL, int EPT, bool VEC>
 __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_A(EPT))
 k_mg_res(HpDev d, HpKArgs a, HpLevel L, HpMgResArgs m) {
+    pdl_enter();
     using G = TeamGeom<TPL>;
     if (d.st->mg_skip) return;
     mg_res_body<TPL, EPT, VEC>(d, L, m, (long long)blockIdx.x * G::LPC + threadIdx.x / TPL, (long long)gridDim.x * G::LPC);
@@ -1130,6 +1156,7 @@ __device__ __forceinline__ double mg_line_body(const HpDev& d, double omega, con
 template <int TPL, int EPT, bool VEC>
 __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT))
 k_mg_line(HpDev d, HpKArgs a, HpLevel L, HpMgLineArgs m) {
+    pdl_enter();
     using G = TeamGeom<TPL>;
     if (d.st->mg_skip) return;
     __shared__ double s_fA[G::LPC][G::NW], s_fB[G::LPC][G::NW], s_bA[G::LPC][G::NW], s_bB[G::LPC][G::NW];
@@ -1171,6 +1198,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
 template <int TPL, int EPT, bool VEC>
 __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_A(EPT))
 k_mg_subcycle(HpDev d, HpKArgs a, HpLevelSet ls, HpSubcycleArgs sc) {
+    pdl_enter();
     using G = TeamGeom<TPL>;
     if (d.st->mg_skip) return;
     __shared__ double s_fA[G::LPC][G::NW], s_fB[G::LPC][G::NW], s_bA[G::LPC][G::NW], s_bB[G::LPC][G::NW];
@@ -1232,6 +1260,7 @@ const void* fn_mg_line() { return (const void*)k_mg_line<TPL, EPT, VEC>; }
 // pivots of ALL coarse levels in one launch (thread per row of any level: the recurrence is a serial chain of nr
 // steps whatever the row count, so one launch costs the same latency as one level alone)
 __global__ void __launch_bounds__(32) k_factor_levels(HpLevelSet ls, int nr, const int* skip) {
+    pdl_enter();
     if (*skip) return;
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     for (int l = 1; l < ls.n; ++l) {
