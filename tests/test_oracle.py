@@ -124,3 +124,33 @@ def test_pcg_iteration_counts_are_modest_with_line_preconditioner(cfg):
     o2.sweep(0.1, solver='pcg_jacobi')
     assert o1.last_solver_info['iterations'] < 40 < 400 < o2.last_solver_info['iterations']
     assert np.max(np.abs(o1.T - o2.T)) <= 1e-7
+
+
+def test_mgline_twin_matches_direct_solve_and_needs_few_iterations(cfg):
+    """The oracle's twin of the GPU 'mgline' preconditioner (V-cycle, axial semi-coarsening by row pairs, damped
+    radial-line Jacobi): same answer as the direct solve, mesh-independent iteration counts, odd row counts handled."""
+    for shape, max_it in (((64, 4, 8, 20), 8), ((250, 8, 16, 40), 14), ((512, 16, 32, 80), 20)):
+        grid = fo.build_grid(fo.synthetic_mesh_params(*shape), cfg['dimensions'])
+        z = grid.z_c[:, None] / grid.z_v[-1]
+        T0 = 290.0 + 300.0 * np.exp(-((z - 0.1) / 0.35) ** 2) * np.ones((1, grid.nr))
+        ref = fo.Oracle(grid, fo.case_from_config(), T0=T0)
+        ref.sweep(0.1, solver='banded')
+        mg = fo.Oracle(grid, fo.case_from_config(), T0=T0)
+        mg.sweep(0.1, solver='pcg_mgline', tol=1e-9)
+        rl = fo.Oracle(grid, fo.case_from_config(), T0=T0)
+        rl.sweep(0.1, solver='pcg_rline', tol=1e-9)
+        assert np.max(np.abs(mg.T - ref.T)) <= 1e-7
+        assert mg.last_solver_info['iterations'] <= max_it
+        assert mg.last_solver_info['iterations'] <= rl.last_solver_info['iterations']
+    # the hierarchy: 250 -> 125 -> 63 -> 32 -> 16 rows
+    S = fo.Oracle(fo.build_grid(fo.synthetic_mesh_params(250, 8, 16, 40), cfg['dimensions']), fo.case_from_config()).assemble(0.1)
+    assert [lv.S.diag.shape[0] for lv in fo.mg_hierarchy(S)] == [250, 125, 63, 32, 16]
+    # Galerkin coarse operator = P^T A P for P = row-pair injection
+    lv = fo.mg_hierarchy(S, max_levels=2)
+    nz, nr = S.diag.shape
+    x = np.random.default_rng(1).standard_normal((lv[1].S.diag.shape[0], nr))
+    Px = np.repeat(x, 2, axis=0)[:nz]
+    A_Px = lv[0].S.matvec(Px)
+    PtAPx = A_Px[0::2].copy()
+    PtAPx[:nz // 2] += A_Px[1::2]
+    assert np.allclose(PtAPx, lv[1].S.matvec(x), rtol=1e-12, atol=1e-12 * np.abs(S.diag).max())
