@@ -528,8 +528,16 @@ struct TeamGeom {
     static constexpr int minb_A(int ept) { return TPL <= 256 ? 2 : 1; }
     static constexpr int minb_B(int ept) { return TPL <= 256 ? (ept >= 8 ? 2 : 3) : 1; }
     static constexpr int LPC = CTA / TPL;
-    static constexpr int NW = TPL / 32;       // warps per team
+    static constexpr int NW = (TPL >= 32) ? TPL / 32 : 1;   // warps per team
+    static constexpr int W = (TPL < 32) ? TPL : 32;         // lanes of a team inside one warp (sub-warp teams for nr <= 16)
 };
+
+// lanes of this thread's team inside its warp: shuffles of different teams in one warp must not wait for each other
+template <int TPL>
+__device__ __forceinline__ unsigned team_mask() {
+    if constexpr (TPL >= 32) return 0xffffffffu;
+    else return ((1u << TPL) - 1u) << ((threadIdx.x & 31) & ~(TPL - 1));
+}
 
 template <int TPL>
 __device__ __forceinline__ void team_barrier(int team_in_cta) {
@@ -550,11 +558,12 @@ template <int TPL, int EPT>
 __device__ __forceinline__ void line_solve(const double (&rv)[EPT], const double (&dv)[EPT], const double (&cr)[EPT],
                                            double m0_edge, int lane, int wt, int team_in_cta, double* s_fA, double* s_fB,
                                            double* s_bA, double* s_bB, double (&zv)[EPT]) {
-    constexpr int NW = TPL / 32;
+    constexpr int NW = TeamGeom<TPL>::NW, W = TeamGeom<TPL>::W;
+    const unsigned tm = team_mask<TPL>();
     double nb[EPT];     // cR_i * dinv_i : backward multiplier of cell i, forward multiplier of cell i+1
 #pragma unroll
     for (int e = 0; e < EPT; ++e) nb[e] = cr[e] * dv[e];
-    double m0 = __shfl_up_sync(0xffffffffu, nb[EPT - 1], 1);
+    double m0 = __shfl_up_sync(tm, nb[EPT - 1], 1, W);
     if (lane == 0) m0 = m0_edge;
     double Pe[EPT], ye[EPT];
     {
@@ -569,16 +578,16 @@ __device__ __forceinline__ void line_solve(const double (&rv)[EPT], const double
     }
     double A = Pe[EPT - 1], B = ye[EPT - 1];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double Ap = __shfl_up_sync(0xffffffffu, A, o);
-        const double Bp = __shfl_up_sync(0xffffffffu, B, o);
+    for (int o = 1; o < W; o <<= 1) {
+        const double Ap = __shfl_up_sync(tm, A, o, W);
+        const double Bp = __shfl_up_sync(tm, B, o, W);
         if (lane >= o) { B = fma(A, Bp, B); A *= Ap; }
     }
-    double Ax = __shfl_up_sync(0xffffffffu, A, 1), Bx = __shfl_up_sync(0xffffffffu, B, 1);
+    double Ax = __shfl_up_sync(tm, A, 1, W), Bx = __shfl_up_sync(tm, B, 1, W);
     if (lane == 0) { Ax = 1.0; Bx = 0.0; }
     double carry = 0.0;
     if constexpr (NW > 1) {
-        if (lane == 31) { s_fA[wt] = A; s_fB[wt] = B; }
+        if (lane == W - 1) { s_fA[wt] = A; s_fB[wt] = B; }
         team_barrier<TPL>(team_in_cta);
         for (int w = 0; w < wt; ++w) carry = fma(s_fA[w], carry, s_fB[w]);
     }
@@ -596,13 +605,13 @@ __device__ __forceinline__ void line_solve(const double (&rv)[EPT], const double
     }
     A = Pe[0]; B = zv[0];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double Ap = __shfl_down_sync(0xffffffffu, A, o);
-        const double Bp = __shfl_down_sync(0xffffffffu, B, o);
-        if (lane + o < 32) { B = fma(A, Bp, B); A *= Ap; }
+    for (int o = 1; o < W; o <<= 1) {
+        const double Ap = __shfl_down_sync(tm, A, o, W);
+        const double Bp = __shfl_down_sync(tm, B, o, W);
+        if (lane + o < W) { B = fma(A, Bp, B); A *= Ap; }
     }
-    Ax = __shfl_down_sync(0xffffffffu, A, 1); Bx = __shfl_down_sync(0xffffffffu, B, 1);
-    if (lane == 31) { Ax = 1.0; Bx = 0.0; }
+    Ax = __shfl_down_sync(tm, A, 1, W); Bx = __shfl_down_sync(tm, B, 1, W);
+    if (lane == W - 1) { Ax = 1.0; Bx = 0.0; }
     carry = 0.0;
     if constexpr (NW > 1) {
         if (lane == 0) { s_bA[wt] = A; s_bB[wt] = B; }
@@ -626,7 +635,7 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, MINB) k_cg_A(HpDev d, hp_p
     const HpState s0 = *d.st;
     if (s0.done) return;
     const int nr = d.nr, nz = d.nz;
-    const int team_in_cta = threadIdx.x / TPL, tl = threadIdx.x % TPL, lane = threadIdx.x & 31;
+    const int team_in_cta = threadIdx.x / TPL, tl = threadIdx.x % TPL, lane = threadIdx.x & (TeamGeom<TPL>::W - 1);
     // teams tile the mesh as (row chunk) x (column tile); neighbours in another tile / warp come from global memory
     const long long team = (long long)blockIdx.x * G::LPC + team_in_cta, nteams = (long long)gridDim.x * G::LPC;
     const int ncol = d.ncolA;
@@ -661,7 +670,7 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, MINB) k_cg_A(HpDev d, hp_p
     // radial neighbours that live in another warp: only lane 0 / lane 31 fetch them, one row AHEAD, together with
     // the row's vector loads (a dependent second round trip to DRAM per row would halve the streaming rate)
     const bool has_l = (lane == 0) && (i0 != 0) && (i0 < nr);
-    const bool has_r = (lane == 31) && (i0 + EPT < nr);
+    const bool has_r = (lane == TeamGeom<TPL>::W - 1) && (i0 + EPT < nr);
 
     double acc[1] = {0.0};
     if (jb > ja) {
@@ -697,11 +706,12 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, MINB) k_cg_A(HpDev d, hp_p
             const double pn_l = first ? zl : fma(beta, plo, zl);
             const double pn_r = first ? zr : fma(beta, pro, zr);
             // radial neighbours across thread boundaries
-            double pl = __shfl_up_sync(0xffffffffu, pc[EPT - 1], 1);
-            double crl = __shfl_up_sync(0xffffffffu, cr[EPT - 1], 1);
-            double pr = __shfl_down_sync(0xffffffffu, pc[0], 1);
+            const unsigned tm = team_mask<TPL>();
+            double pl = __shfl_up_sync(tm, pc[EPT - 1], 1, G::W);
+            double crl = __shfl_up_sync(tm, cr[EPT - 1], 1, G::W);
+            double pr = __shfl_down_sync(tm, pc[0], 1, G::W);
             if (lane == 0) { pl = pc_l; crl = crl_e; }      // zero when there is no left neighbour
-            if (lane == 31) pr = pc_r;
+            if (lane == G::W - 1) pr = pc_r;
             double qv[EPT];
 #pragma unroll
             for (int e = 0; e < EPT; ++e) {
@@ -746,7 +756,7 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT)
     if (!INIT && s0.done) return;
     __shared__ double s_fA[G::LPC][G::NW], s_fB[G::LPC][G::NW], s_bA[G::LPC][G::NW], s_bB[G::LPC][G::NW];
     const int nr = d.nr, nz = d.nz;
-    const int team_in_cta = threadIdx.x / TPL, tl = threadIdx.x % TPL, lane = threadIdx.x & 31;
+    const int team_in_cta = threadIdx.x / TPL, tl = threadIdx.x % TPL, lane = threadIdx.x & (TeamGeom<TPL>::W - 1);
     const int wt = tl >> 5;     // warp within team
     const int i0 = tl * EPT;
     const long long team = (long long)blockIdx.x * G::LPC + team_in_cta, nteams = (long long)gridDim.x * G::LPC;
@@ -996,7 +1006,7 @@ template <int TPL, int EPT, bool VEC>
 __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpLevel& L, const HpMgResArgs& m, long long team,
                                             long long nteams) {
     const int nr = d.nr, nz = L.nz;
-    const int tl = threadIdx.x % TPL, lane = threadIdx.x & 31;
+    const int tl = threadIdx.x % TPL, lane = threadIdx.x & (TeamGeom<TPL>::W - 1);
     const int ncol = d.ncolA;
     const long long nchunks = nteams / ncol;
     const long long chunk = team / ncol;
@@ -1010,7 +1020,7 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpLevel& L, co
         if (jb > nz) jb = nz;
     }
     const bool has_l = (lane == 0) && (i0 != 0) && (i0 < nr);
-    const bool has_r = (lane == 31) && (i0 + EPT < nr);
+    const bool has_r = (lane == TeamGeom<TPL>::W - 1) && (i0 + EPT < nr);
     const bool prolong = m.ec != nullptr;
     const double scale = m.scale;
     auto crow = [&](int g) {                       // coarse ghost-inclusive row of fine row g (clamped at the ends)
@@ -1064,11 +1074,13 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpLevel& L, co
 #pragma unroll
                 for (int k = 0; k < EPT; ++k) cz[k] = 0.0;     // rank-local: no coupling to the upper ghost row
             }
-            double xl = __shfl_up_sync(0xffffffffu, xc[EPT - 1], 1);
-            double crl = __shfl_up_sync(0xffffffffu, cr[EPT - 1], 1);
-            double xr = __shfl_down_sync(0xffffffffu, xc[0], 1);
+            const unsigned tm = team_mask<TPL>();
+            constexpr int W = TeamGeom<TPL>::W;
+            double xl = __shfl_up_sync(tm, xc[EPT - 1], 1, W);
+            double crl = __shfl_up_sync(tm, cr[EPT - 1], 1, W);
+            double xr = __shfl_down_sync(tm, xc[0], 1, W);
             if (lane == 0) { xl = xc_l; crl = crl_e; }
-            if (lane == 31) xr = xc_r;
+            if (lane == W - 1) xr = xc_r;
             double res[EPT];
 #pragma unroll
             for (int k = 0; k < EPT; ++k) {
@@ -1120,7 +1132,7 @@ __device__ __forceinline__ double mg_line_body(const HpDev& d, double omega, con
                                                long long team, long long nteams, double* s_fA, double* s_fB, double* s_bA,
                                                double* s_bB) {
     const int nr = d.nr, nz = L.nz;
-    const int team_in_cta = threadIdx.x / TPL, tl = threadIdx.x % TPL, lane = threadIdx.x & 31;
+    const int team_in_cta = threadIdx.x / TPL, tl = threadIdx.x % TPL, lane = threadIdx.x & (TeamGeom<TPL>::W - 1);
     const int wt = tl >> 5;
     const int i0 = tl * EPT;
     int ja = 0, jb = 0;
@@ -1284,7 +1296,8 @@ const void* fn_B(int rline, int init) {
 
 #define HP_DISPATCH(cfg, EXPR_T)                                                          \
     do {                                                                                  \
-        if (cfg.tpl == 32 && cfg.ept == 1) { EXPR_T(32, 1, false); }                      \
+        if (cfg.tpl == 16 && cfg.ept == 1) { EXPR_T(16, 1, false); }                      \
+        else if (cfg.tpl == 32 && cfg.ept == 1) { EXPR_T(32, 1, false); }                 \
         else if (cfg.tpl == 32 && cfg.ept == 4) { if (cfg.vec) { EXPR_T(32, 4, true); } else { EXPR_T(32, 4, false); } }       \
         else if (cfg.tpl == 128 && cfg.ept == 4) { if (cfg.vec) { EXPR_T(128, 4, true); } else { EXPR_T(128, 4, false); } }    \
         else if (cfg.tpl == 256 && cfg.ept == 4) { if (cfg.vec) { EXPR_T(256, 4, true); } else { EXPR_T(256, 4, false); } }    \
@@ -1296,7 +1309,8 @@ const void* fn_B(int rline, int init) {
 
 #define HP_DISPATCH_A(cfg, EXPR_T)                                                        \
     do {                                                                                  \
-        if (cfg.tplA == 32 && cfg.eptA == 1) { EXPR_T(32, 1, false); }                    \
+        if (cfg.tplA == 16 && cfg.eptA == 1) { EXPR_T(16, 1, false); }                    \
+        else if (cfg.tplA == 32 && cfg.eptA == 1) { EXPR_T(32, 1, false); }               \
         else if (cfg.tplA == 32 && cfg.eptA == 4) { if (cfg.vecA) { EXPR_T(32, 4, true); } else { EXPR_T(32, 4, false); } }    \
         else if (cfg.tplA == 128 && cfg.eptA == 4) { if (cfg.vecA) { EXPR_T(128, 4, true); } else { EXPR_T(128, 4, false); } } \
         else if (cfg.tplA == 256 && cfg.eptA == 4) { if (cfg.vecA) { EXPR_T(256, 4, true); } else { EXPR_T(256, 4, false); } } \
@@ -1312,7 +1326,8 @@ namespace hpk {
 bool pick_config(int nr, int nz, int num_sms, HpLaunchCfg* cfg, const char** err) {
     if (nr < 1 || nz < 1) { *err = "nr and nz must be >= 1"; return false; }
     int tpl, ept;
-    if (nr <= 32) { tpl = 32; ept = 1; }
+    if (nr <= 16) { tpl = 16; ept = 1; }
+    else if (nr <= 32) { tpl = 32; ept = 1; }
     else if (nr <= 128) { tpl = 32; ept = 4; }
     else if (nr <= 512) { tpl = 128; ept = 4; }
     else if (nr <= 1024) { tpl = 256; ept = 4; }
@@ -1323,7 +1338,7 @@ bool pick_config(int nr, int nz, int num_sms, HpLaunchCfg* cfg, const char** err
     if (const char* e = getenv("HP_TEAM")) {
         int t = 0, p = 0;
         if (sscanf(e, "%dx%d", &t, &p) == 2 && (long long)t * p >= nr &&
-            ((t == 32 && (p == 1 || p == 4)) || (t == 128 && (p == 4 || p == 8)) || (t == 256 && (p == 4 || p == 8)) ||
+            ((t == 16 && p == 1) || (t == 32 && (p == 1 || p == 4)) || (t == 128 && (p == 4 || p == 8)) || (t == 256 && (p == 4 || p == 8)) ||
              ((t == 512 || t == 1024) && p == 8))) { tpl = t; ept = p; }
     }
     cfg->tpl = tpl; cfg->ept = ept;
@@ -1331,7 +1346,8 @@ bool pick_config(int nr, int nz, int num_sms, HpLaunchCfg* cfg, const char** err
     cfg->cta_threads = tpl < 256 ? 256 : tpl;
     cfg->teams_per_cta = cfg->cta_threads / tpl;
     // k_cg_A: at most 256 threads x 4 cells per tile (three rows of the direction + five streams stay in <= 128 regs)
-    if (nr <= 32) { cfg->tplA = 32; cfg->eptA = 1; }
+    if (nr <= 16) { cfg->tplA = 16; cfg->eptA = 1; }
+    else if (nr <= 32) { cfg->tplA = 32; cfg->eptA = 1; }
     else if (nr <= 128) { cfg->tplA = 32; cfg->eptA = 4; }
     else if (nr <= 512) { cfg->tplA = 128; cfg->eptA = 4; }
     else { cfg->tplA = 256; cfg->eptA = 4; }
