@@ -47,7 +47,8 @@ class HpKernelTimes(C.Structure):
     _fields_ = [('count', C.c_int64 * 16), ('total_ms', C.c_double * 16)]
 
 
-KERNEL_KINDS = ('other', 'coef', 'diag', 'factor', 'cg_init', 'cg_A', 'cg_B', 'mg_res', 'mg_line', 'mg_coarse', 'mg_setup')
+KERNEL_KINDS = ('other', 'coef', 'diag', 'factor', 'cg_init', 'cg_A', 'cg_B', 'mg_res', 'mg_line', 'mg_coarse', 'mg_setup',
+                'mg_l1', 'mg_l2', 'mg_l3', 'mg_l4', 'mg_l5')
 
 # every symbol include/hp_solver.h declares: name -> (restype, argtypes)
 _H = C.c_void_p

@@ -112,6 +112,7 @@ struct hp_solver_s {
     std::vector<void*> ipc_opened;
     unsigned long long* gbar = nullptr;   // grid-barrier words of k_mg_subcycle
     bool mg_fused = true;
+    bool mg_upfused = true;      // coarse up-leg stages as one kernel (k_mg_up) instead of residual + line solve
     bool pdl = false;                 // programmatic dependent launch edges between the kernel nodes of the step graph
     bool have_prev = false;          // Told holds the field of the previous step start (extrapolated PCG start)
     bool ghost_dirty = true;         // ghost rows of T must be refreshed by an explicit exchange before the next sweep
@@ -215,6 +216,8 @@ static int setup_mg(hp_solver_s* h) {
         // measured on B200: inside the step graph the fused cycle (132 us) is no faster than its 21 separate launches
         // (~6 us each), both are bound by the chain of dependent row latencies -> off unless asked for
         h->mg_fused = (ef && ef[0] == '1') && hpk::mg_subcycle_supported(h->cfg);
+        const char* eu = getenv("HP_MG_UPFUSE");
+        h->mg_upfused = !(eu && eu[0] == '0') && hpk::mg_subcycle_supported(h->cfg) && h->cfg.ncolA == 1;
         h->nlev_alloc = 1;
     }
     for (int l = h->nlev_alloc; l < want; ++l) {
@@ -243,7 +246,7 @@ static HpKArgs make_args(const hp_solver_s* h, double dt, int has_old) {
 }
 
 enum { KIND_OTHER = 0, KIND_COEF, KIND_DIAG, KIND_FACTOR, KIND_INIT, KIND_A, KIND_B, KIND_MG_RES0, KIND_MG_LINE0, KIND_MG_COARSE,
-       KIND_MG_SETUP, KIND_COUNT };
+       KIND_MG_SETUP, KIND_MG_L1, KIND_MG_L2, KIND_MG_L3, KIND_MG_L4, KIND_MG_L5, KIND_COUNT };   // L5 = level 5 and deeper
 
 static int launch(hp_solver_s* h, const HpKernelLaunch& k, void** params, int kind = KIND_OTHER) {
     const bool prof = h->prof_on && h->prof_used < h->prof_ev.size() / 2;
@@ -584,33 +587,71 @@ static int emit_vcycle(Emitter& e, const HpKArgs& a_in, int init_phase) {
     HpKArgs a = a_in;
     a.init_phase = init_phase;
     const int nr = d.nr;
+    // profiling kind of a coarse stage: local levels 1..5+ separately, replicated global levels under "mg_coarse"
+    auto ckind = [&](const HpLevel& Lv) -> int {
+        const long long l = &Lv - h->lev;
+        if (l < 1 || l >= h->nlev) return KIND_MG_COARSE;
+        return KIND_MG_L1 + (int)(l > 5 ? 5 : l) - 1;
+    };
     auto res = [&](HpLevel& Lv, bool fine, const double* xin, const double* ec, int nzc, double* xout, double* resout,
                    double* crhs, double scale) -> int {
         HpMgResArgs m{xin, ec, xout, resout, crhs, scale, nzc};
         void* p[] = {&d, &a, &Lv, &m};
-        return emit(e, hpk::desc_mg_res(h->cfg, Lv.nz), p, fine ? KIND_MG_RES0 : KIND_MG_COARSE);
+        return emit(e, hpk::desc_mg_res(h->cfg, Lv.nz), p, fine ? KIND_MG_RES0 : ckind(Lv));
     };
     auto line = [&](HpLevel& Lv, bool fine, const double* rhs, const double* base, double* out, int fin) -> int {
         HpMgLineArgs m{rhs, base, out, fin};
         void* p[] = {&d, &a, &Lv, &m};
-        return emit(e, hpk::desc_mg_line(h->cfg, Lv.nz), p, fine ? KIND_MG_LINE0 : KIND_MG_COARSE);
+        return emit(e, hpk::desc_mg_line(h->cfg, Lv.nz), p, fine ? KIND_MG_LINE0 : ckind(Lv));
     };
-    // complete V-cycle on levels lo..n-1 of Ls (rhs of level lo given, correction left in Ls[lo].x)
-    auto subcycle = [&](HpLevel* Ls, int lo, int n) -> int {
-        const int c = n - 1;
-        for (int l = lo; l < c; ++l) {
-            if (line(Ls[l], false, Ls[l].rhs, nullptr, Ls[l].x, 0)) return -1;
-            if (res(Ls[l], false, Ls[l].x, nullptr, Ls[l + 1].nz, nullptr, nullptr, Ls[l + 1].rhs, 1.0)) return -1;
+    // fused up-leg stage: out = xt + omega M^-1 (rhs - L xt), xt = xin + P ec   (one launch instead of res + line)
+    auto up = [&](HpLevel& Lv, const double* xin, const double* ec, int nzc, double* out) -> int {
+        HpMgResArgs m{xin, ec, out, nullptr, nullptr, 1.0, nzc};
+        void* p[] = {&d, &a, &Lv, &m};
+        return emit(e, hpk::desc_mg_up(h->cfg, Lv.nz), p, ckind(Lv));
+    };
+    const bool upf = h->mg_upfused;
+    // down-leg stage of level Lv: residual of xin (scaled), restricted into Ln.rhs; with `presmooth` the pre-smoothing of
+    // the next level, Ln.x = omega M^-1 Ln.rhs, rides in the same launch when the fused kernels are usable
+    auto down = [&](HpLevel& Lv, bool fine, const double* xin, double scale, double* xout, HpLevel& Ln, bool presmooth) -> int {
+        if (upf && presmooth) {
+            HpMgResArgs m{xin, nullptr, xout, nullptr, Ln.rhs, scale, Ln.nz, Ln.dinv, Ln.cR, Ln.x};
+            void* p[] = {&d, &a, &Lv, &m};
+            return emit(e, hpk::desc_mg_down(h->cfg, Lv.nz), p, fine ? KIND_MG_RES0 : ckind(Lv));
         }
-        if (line(Ls[c], false, Ls[c].rhs, nullptr, Ls[c].x, 0)) return -1;
+        if (res(Lv, fine, xin, nullptr, Ln.nz, xout, nullptr, Ln.rhs, scale)) return -1;
+        return presmooth ? line(Ln, false, Ln.rhs, nullptr, Ln.x, 0) : 0;
+    };
+    // post-smoothing of level l with coarse correction ec; returns where the smoothed correction was left
+    auto up_leg = [&](HpLevel& Lv, const double* ec, int nzc) -> const double* {
+        if (upf) return up(Lv, Lv.x, ec, nzc, Lv.x2) ? nullptr : Lv.x2;
+        if (res(Lv, false, Lv.x, ec, nzc, Lv.x2, Lv.tmp, nullptr, 1.0)) return nullptr;
+        if (line(Lv, false, Lv.tmp, Lv.x2, Lv.x, 0)) return nullptr;
+        return Lv.x;
+    };
+    // complete V-cycle on levels lo..n-1 of Ls (rhs of level lo given, Ls[lo].x = omega M^-1 rhs too if `presmoothed`);
+    // *top = where the correction of level lo is left
+    auto subcycle = [&](HpLevel* Ls, int lo, int n, bool presmoothed, const double** top) -> int {
+        const int c = n - 1;
+        if (!presmoothed && line(Ls[lo], false, Ls[lo].rhs, nullptr, Ls[lo].x, 0)) return -1;
+        for (int l = lo; l < c; ++l)
+            if (down(Ls[l], false, Ls[l].x, 1.0, nullptr, Ls[l + 1], true)) return -1;
+        const double* cur = Ls[c].x;
         for (int k = 0; k < h->opts.mg_coarse_sweeps; ++k) {
-            if (res(Ls[c], false, Ls[c].x, nullptr, 1, nullptr, Ls[c].tmp, nullptr, 1.0)) return -1;
-            if (line(Ls[c], false, Ls[c].tmp, Ls[c].x, Ls[c].x, 0)) return -1;
+            if (upf) {
+                double* other = (cur == Ls[c].x) ? Ls[c].x2 : Ls[c].x;
+                if (up(Ls[c], cur, nullptr, 1, other)) return -1;
+                cur = other;
+            } else {
+                if (res(Ls[c], false, Ls[c].x, nullptr, 1, nullptr, Ls[c].tmp, nullptr, 1.0)) return -1;
+                if (line(Ls[c], false, Ls[c].tmp, Ls[c].x, Ls[c].x, 0)) return -1;
+            }
         }
         for (int l = c - 1; l >= lo; --l) {
-            if (res(Ls[l], false, Ls[l].x, Ls[l + 1].x, Ls[l + 1].nz, Ls[l].x2, Ls[l].tmp, nullptr, 1.0)) return -1;
-            if (line(Ls[l], false, Ls[l].tmp, Ls[l].x2, Ls[l].x, 0)) return -1;
+            cur = up_leg(Ls[l], cur, Ls[l + 1].nz);
+            if (!cur) return -1;
         }
+        *top = cur;
         return 0;
     };
     // same cycle in ONE cooperative launch (grid barriers instead of kernel boundaries) when the row-team shapes allow
@@ -625,19 +666,19 @@ static int emit_vcycle(Emitter& e, const HpKArgs& a_in, int init_phase) {
     HpLevel* L = h->lev;
     const int nl = h->nlev;
     // level 0 starts from omega * zline (its pre-smoothing is k_cg_B's line solve)
-    if (res(L[0], true, d.z, nullptr, L[1].nz, L[0].x2, nullptr, L[1].rhs, a.omega)) return -1;
+    const int s = nl - 1;                  // g_active: rows of local level s are one slice of the replicated global level 0
+    // level 1 is pre-smoothed here unless the cooperative cycle does it or it is the level handed to the global hierarchy
+    const bool pre1 = !h->mg_fused && !(h->g_active && s == 1);
+    if (down(L[0], true, d.z, a.omega, L[0].x2, L[1], pre1)) return -1;
     const double* ec0 = L[1].x;          // coarse correction seen by level 0
     if (!h->g_active) {
-        if (h->mg_fused ? fused(L, 1, nl, 0, nullptr) : subcycle(L, 1, nl)) return -1;
+        if (h->mg_fused ? fused(L, 1, nl, 0, nullptr) : subcycle(L, 1, nl, true, &ec0)) return -1;
     } else {
-        const int s = nl - 1;              // rows of local level s are one slice of the replicated global level 0
         if (h->mg_fused && s > 1) {
             if (fused(L, 1, nl, 1, nullptr)) return -1;
         } else {
-            for (int l = 1; l < s; ++l) {
-                if (line(L[l], false, L[l].rhs, nullptr, L[l].x, 0)) return -1;
-                if (res(L[l], false, L[l].x, nullptr, L[l + 1].nz, nullptr, nullptr, L[l + 1].rhs, 1.0)) return -1;
-            }
+            for (int l = 1; l < s; ++l)
+                if (down(L[l], false, L[l].x, 1.0, nullptr, L[l + 1], l + 1 < s)) return -1;
         }
         const int* skip = &d.st->mg_skip;
         HpGatherArgs g{};
@@ -649,16 +690,18 @@ static int emit_vcycle(Emitter& e, const HpKArgs& a_in, int init_phase) {
         int kind = HP_COMM_GRHS;
         void* pw[] = {&d, &kind, &skip};
         if (emit(e, hpk::desc_wait_flag(), pw, KIND_MG_COARSE)) return -1;
-        if (h->mg_fused ? fused(h->glev, 0, h->nglev, 0, nullptr) : subcycle(h->glev, 0, h->nglev)) return -1;
-        const double* mine = h->glev[0].x + (size_t)h->g_row0 * nr;      // my slice (ghost-inclusive indexing kept)
+        const double* gtop = h->glev[0].x;
+        if (h->mg_fused ? fused(h->glev, 0, h->nglev, 0, nullptr) : subcycle(h->glev, 0, h->nglev, false, &gtop)) return -1;
+        const double* mine = gtop + (size_t)h->g_row0 * nr;              // my slice (ghost-inclusive indexing kept)
         if (h->mg_fused && s > 1) {
             if (fused(L, 1, nl, 2, mine)) return -1;
         } else {
+            const double* cur = mine;
             for (int l = s - 1; l >= 1; --l) {
-                const double* ec = (l == s - 1) ? mine : L[l + 1].x;
-                if (res(L[l], false, L[l].x, ec, L[l + 1].nz, L[l].x2, L[l].tmp, nullptr, 1.0)) return -1;
-                if (line(L[l], false, L[l].tmp, L[l].x2, L[l].x, 0)) return -1;
+                cur = up_leg(L[l], cur, L[l + 1].nz);
+                if (!cur) return -1;
             }
+            if (s > 1) ec0 = cur;
         }
         if (s == 1) ec0 = mine;
     }

@@ -99,6 +99,7 @@ struct HpGatherArgs {
 struct HpMgResArgs {
     const double* xin; const double* ec; double* xout; double* resout; double* crhs;
     double scale; int nzc;
+    const double* c_dinv; const double* c_cR; double* c_x;     // k_mg_fused MODE 2: pivots / couplings / correction of level+1
 };
 struct HpMgLineArgs {
     const double* rhs; const double* base; double* out; int final_;
@@ -168,6 +169,8 @@ HpKernelLaunch desc_cg_A(const HpLaunchCfg&, const HpDev&);
 HpKernelLaunch desc_mg_coarsen(const HpLaunchCfg&, int nzc, int nr);
 HpKernelLaunch desc_mg_res(const HpLaunchCfg&, int nz_level);
 HpKernelLaunch desc_mg_line(const HpLaunchCfg&, int nz_level);
+HpKernelLaunch desc_mg_down(const HpLaunchCfg&, int nz_level);   // same args: residual + restriction + pre-smoothing of level+1
+HpKernelLaunch desc_mg_up(const HpLaunchCfg&, int nz_level);     // args: (HpDev, HpKArgs, HpLevel, HpMgResArgs): fused prolong+residual+smooth
 HpKernelLaunch desc_mg_subcycle(const HpLaunchCfg&);            // args: (HpDev, HpKArgs, HpLevelSet, HpSubcycleArgs); cooperative
 bool mg_subcycle_supported(const HpLaunchCfg&);
 HpKernelLaunch desc_factor_levels(int total_coarse_rows);   // args: (HpLevelSet, int nr, const int* skip)

@@ -1002,9 +1002,14 @@ __global__ void __launch_bounds__(256) k_mg_coarsen(HpLevel f, HpLevel c, int nr
 //   x(g)   = scale * xin(g) [+ ec(pair of g)]                          (PROLONG)
 //   res(g) = rhs(g) - (diag x - cR x_e - cR_w x_w - cZ x_n - cZ_s x_s) (couplings to ghost rows ignored)
 //   xout(g) = x(g) if xout;  resout(g) = res(g) if resout;  crhs(J) = res(2J) + res(2J+1) if crhs (RESTRICT)
-template <int TPL, int EPT, bool VEC>
+// MODE 1 fuses the post-smoothing step into the same pass:  xout(g) = x(g) + omega * M_L^-1 res(g)  (the line solve of
+// row g only needs the residual of row g).  MODE 2 fuses the pre-smoothing of the NEXT level into the restriction:
+// c_x(J) = omega * M_{L+1}^-1 crhs(J) as soon as the coarse row J = pair-sum of residual rows is complete.  Both need the
+// team to own whole rows (no column tiles).
+template <int TPL, int EPT, bool VEC, int MODE = 0>
 __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpLevel& L, const HpMgResArgs& m, long long team,
-                                            long long nteams) {
+                                            long long nteams, double omega = 0.0, double* s_fA = nullptr,
+                                            double* s_fB = nullptr, double* s_bA = nullptr, double* s_bB = nullptr) {
     const int nr = d.nr, nz = L.nz;
     const int tl = threadIdx.x % TPL, lane = threadIdx.x & (TeamGeom<TPL>::W - 1);
     const int ncol = d.ncolA;
@@ -1062,11 +1067,28 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpLevel& L, co
         for (int g = ja + 1; g <= jb; ++g) {
             const long long rb = (long long)g * nr;
             double cr[EPT], cz[EPT], dg[EPT], rh[EPT];
+            [[maybe_unused]] double dv[EPT];
             xrow(g + 1, xn);
             load_row<EPT, VEC>(L.cR + rb, i0, nr, cr);
             load_row<EPT, VEC>(L.cZ + rb, i0, nr, cz);
             load_row<EPT, VEC>(L.diag + rb, i0, nr, dg);
             load_row<EPT, VEC>(L.rhs + rb, i0, nr, rh);
+            [[maybe_unused]] double m0_edge = 0.0;
+            if constexpr (MODE == 1) {
+                load_row<EPT, VEC>(L.dinv + rb, i0, nr, dv);
+                if (lane == 0 && tl != 0 && i0 < nr) m0_edge = L.cR[rb + i0 - 1] * L.dinv[rb + i0 - 1];
+            }
+            [[maybe_unused]] double cdv[EPT], ccr[EPT];
+            const bool second = ((g - 1) & 1) != 0;
+            const bool crow_done = second || g == nz;                 // coarse row J = (g-1)/2 + 1 completes with this row
+            const long long cb = (long long)(((g - 1) >> 1) + 1) * nr;
+            if constexpr (MODE == 2) {
+                if (crow_done) {
+                    load_row<EPT, VEC>(m.c_dinv + cb, i0, nr, cdv);
+                    load_row<EPT, VEC>(m.c_cR + cb, i0, nr, ccr);
+                    if (lane == 0 && tl != 0 && i0 < nr) m0_edge = m.c_cR[cb + i0 - 1] * m.c_dinv[cb + i0 - 1];
+                }
+            }
             double xn_l = 0.0, xn_r = 0.0, crl_e = 0.0;
             if (has_l) { xn_l = xat(g + 1, i0 - 1); crl_e = L.cR[rb + i0 - 1]; }
             if (has_r) xn_r = xat(g + 1, i0 + EPT);
@@ -1094,15 +1116,29 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpLevel& L, co
                 t = fma(-czm[k], xm[k], t);
                 res[k] = rh[k] - t;
             }
-            if (m.xout) store_row<EPT, VEC>(m.xout + rb, i0, nr, xc);
-            if (m.resout) store_row<EPT, VEC>(m.resout + rb, i0, nr, res);
+            if constexpr (MODE == 1) {
+                double zv[EPT];
+                line_solve<TPL, EPT>(res, dv, cr, m0_edge, lane, tl >> 5, (int)(threadIdx.x / TPL), s_fA, s_fB, s_bA, s_bB, zv);
+#pragma unroll
+                for (int k = 0; k < EPT; ++k) zv[k] = fma(omega, zv[k], xc[k]);
+                store_row<EPT, VEC>(m.xout + rb, i0, nr, zv);
+            } else {
+                if (m.xout) store_row<EPT, VEC>(m.xout + rb, i0, nr, xc);
+                if (m.resout) store_row<EPT, VEC>(m.resout + rb, i0, nr, res);
+            }
             if (m.crhs) {
-                const bool second = ((g - 1) & 1) != 0;
-                if (second || g == nz) {
+                if (crow_done) {
                     double sum[EPT];
 #pragma unroll
                     for (int k = 0; k < EPT; ++k) sum[k] = second ? rprev[k] + res[k] : res[k];
-                    store_row<EPT, VEC>(m.crhs + (long long)(((g - 1) >> 1) + 1) * nr, i0, nr, sum);
+                    store_row<EPT, VEC>(m.crhs + cb, i0, nr, sum);
+                    if constexpr (MODE == 2) {
+                        double zc[EPT];
+                        line_solve<TPL, EPT>(sum, cdv, ccr, m0_edge, lane, tl >> 5, (int)(threadIdx.x / TPL), s_fA, s_fB, s_bA, s_bB, zc);
+#pragma unroll
+                        for (int k = 0; k < EPT; ++k) zc[k] *= omega;
+                        store_row<EPT, VEC>(m.c_x + cb, i0, nr, zc);
+                    }
                 } else {
 #pragma unroll
                     for (int k = 0; k < EPT; ++k) rprev[k] = res[k];
@@ -1123,6 +1159,24 @@ k_mg_res(HpDev d, HpKArgs a, HpLevel L, HpMgResArgs m) {
     if (d.st->mg_skip) return;
     mg_res_body<TPL, EPT, VEC>(d, L, m, (long long)blockIdx.x * G::LPC + threadIdx.x / TPL, (long long)gridDim.x * G::LPC);
 }
+
+// ---- k_mg_up : prolong + residual + post-smoothing of one coarse level in ONE pass (one stage instead of two in the
+// latency-bound coarse part of the cycle):  xout = xt + omega M_L^-1 (rhs - L xt),  xt = xin + P ec
+template <int TPL, int EPT, bool VEC, int MODE>
+__global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_A(EPT))
+k_mg_fused(HpDev d, HpKArgs a, HpLevel L, HpMgResArgs m) {
+    pdl_enter();
+    using G = TeamGeom<TPL>;
+    if (d.st->mg_skip) return;
+    __shared__ double s_fA[G::LPC][G::NW], s_fB[G::LPC][G::NW], s_bA[G::LPC][G::NW], s_bB[G::LPC][G::NW];
+    const int tic = threadIdx.x / TPL;
+    mg_res_body<TPL, EPT, VEC, MODE>(d, L, m, (long long)blockIdx.x * G::LPC + tic, (long long)gridDim.x * G::LPC, a.omega,
+                                     s_fA[tic], s_fB[tic], s_bA[tic], s_bB[tic]);
+}
+template <int TPL, int EPT, bool VEC>
+const void* fn_mg_up() { return (const void*)k_mg_fused<TPL, EPT, VEC, 1>; }
+template <int TPL, int EPT, bool VEC>
+const void* fn_mg_down() { return (const void*)k_mg_fused<TPL, EPT, VEC, 2>; }
 
 // ---- k_mg_line : out(g) = [base(g) +] omega * M_L^-1 rhs(g)       (row teams, same line solve as k_cg_B)
 // FINAL (level 0, end of the V-cycle): out is the preconditioned residual z of the PCG; accumulates r.z, pushes the
@@ -1423,6 +1477,24 @@ HpKernelLaunch desc_mg_res(const HpLaunchCfg& c, int nz_level) {
     HpLaunchCfg cl = c;
     cl.nz = (nz_level + 1) / 2;                      // chunks are whole row pairs
     return {f, dim3(team_grid(f, cl, c.ctaA, c.teams_per_ctaA, c.ncolA)), dim3(c.ctaA), 0};
+}
+HpKernelLaunch desc_mg_up(const HpLaunchCfg& c, int nz_level) {       // only when mg_subcycle_supported(c)
+    const void* f = nullptr;
+#define HP_X(T, E, V) f = fn_mg_up<T, E, V>()
+    HP_DISPATCH_A(c, HP_X);
+#undef HP_X
+    HpLaunchCfg cl = c;
+    cl.nz = (nz_level + 1) / 2;
+    return {f, dim3(team_grid(f, cl, c.ctaA, c.teams_per_ctaA, 1)), dim3(c.ctaA), 0};
+}
+HpKernelLaunch desc_mg_down(const HpLaunchCfg& c, int nz_level) {     // only when mg_subcycle_supported(c)
+    const void* f = nullptr;
+#define HP_X(T, E, V) f = fn_mg_down<T, E, V>()
+    HP_DISPATCH_A(c, HP_X);
+#undef HP_X
+    HpLaunchCfg cl = c;
+    cl.nz = (nz_level + 1) / 2;
+    return {f, dim3(team_grid(f, cl, c.ctaA, c.teams_per_ctaA, 1)), dim3(c.ctaA), 0};
 }
 HpKernelLaunch desc_mg_line(const HpLaunchCfg& c, int nz_level) {
     const void* f = nullptr;
