@@ -401,7 +401,8 @@ __global__ void __launch_bounds__(256) k_coef(HpDev d, hp_phys ph, HpKArgs a) {
 //   rhs  = cap*T_old (+ Robin*g + evaporator)                                     main.py:146-150
 //   r    = rhs - L T          (PCG start residual; FiPy's `res` = ||L T - rhs||_2) main.py:202
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_diag(HpDev d, hp_phys ph, HpKArgs a, int write_dinv_jacobi, int tpr_log2) {
+constexpr int DIAG_U = 4;      // cells per thread whose loads are issued before any of their (long, fp64) property chains
+__global__ void __launch_bounds__(256, 2) k_diag(HpDev d, hp_phys ph, HpKArgs a, int write_dinv_jacobi, int tpr_log2) {
     pdl_enter();
     // rows over CTAs (and over row groups inside a CTA when a row is shorter than the CTA), columns over threads:
     // no integer division per cell, per-row quantities read once
@@ -414,43 +415,56 @@ __global__ void __launch_bounds__(256) k_diag(HpDev d, hp_phys ph, HpKArgs a, in
         const long long rb = (long long)g * nr;
         const unsigned zf = d.zc_flags[g];
         const double dzg = d.dz[g];
-        for (int i = col0; i < nr; i += tpr) {
-            const long long idx = rb + i;
-            const double Tc = d.T[idx];
-            const double Told = a.has_old ? d.Told[idx] : Tc;
-            double rho, cp;
-            hp::rho_cp_region(ph, d.cell_band[i], zf, Tc, rho, cp);
-            const double vol = d.wc[i] * d.dr[i] * dzg;
-            const double cap = cp * rho * vol / a.dt;
-            const double cE = d.cR[idx], cW = d.cR[idx - 1], cN = d.cZ[idx], cS = d.cZ[idx - nr];
-            double dg = cap;
-            dg += cE; dg += cW; dg += cN; dg += cS;
-            double rhs = cap * Told;
-            if (i == nr - 1) {
-                const double kout = k_outface(d, ph, g, Tc);
-                const double k0 = (ph.gamma == 0) ? d.k0_out[g] : kout;
-                const double A_out = d.A_out_r * dzg;
-                const double h = d.h_line[g], Ta = d.Tamb_line[g];
-                if (zf & HP_ZF_BC_COND) {
-                    const double robin = kout * A_out / (h * d.d_out + k0);
-                    dg += robin * h;
-                    double gs = h * Ta;
-                    if (ph.radiation) gs += ph.sigma * d.eps_line[g] * (Ta * Ta * Ta * Ta - Tc * Tc * Tc * Tc);
-                    rhs += robin * gs;
-                }
-                if (zf & HP_ZF_BC_EVAP) {
-                    const double q = d.q_line[g];
-                    rhs += ((ph.source == 0) ? (q / kout) : q) * A_out;
-                }
+        for (int ib = col0; ib < nr; ib += tpr * DIAG_U) {
+            double Tc[DIAG_U], To[DIAG_U], cE[DIAG_U], cW[DIAG_U], cN[DIAG_U], cS[DIAG_U], Tnb[DIAG_U];
+#pragma unroll
+            for (int u = 0; u < DIAG_U; ++u) {
+                const int i = ib + u * tpr;
+                const long long idx = rb + (i < nr ? i : ib);          // out-of-row slots re-read a valid cell, never stored
+                Tc[u] = d.T[idx];
+                To[u] = a.has_old ? d.Told[idx] : Tc[u];
+                cE[u] = d.cR[idx]; cW[u] = d.cR[idx - 1]; cN[u] = d.cZ[idx]; cS[u] = d.cZ[idx - nr];
+                // off-diagonal part of L T (the diagonal term joins once diag is known)
+                Tnb[u] = cE[u] * d.T[idx + 1] + cW[u] * d.T[idx - 1] + cN[u] * d.T[idx + nr] + cS[u] * d.T[idx - nr];
             }
-            const double LT = dg * Tc - cE * d.T[idx + 1] - cW * d.T[idx - 1] - cN * d.T[idx + nr] - cS * d.T[idx - nr];
-            const double r0 = rhs - LT;
-            d.diag[idx] = dg;
-            d.r[idx] = r0;
-            if (write_dinv_jacobi) d.dinv[idx] = 1.0 / dg;
-            if (a.rhs_out) a.rhs_out[idx] = rhs;
-            acc[0] += r0 * r0;
-            acc[1] += rhs * rhs;
+#pragma unroll
+            for (int u = 0; u < DIAG_U; ++u) {
+                const int i = ib + u * tpr;
+                if (i >= nr) break;
+                const long long idx = rb + i;
+                double rho, cp;
+                hp::rho_cp_region(ph, d.cell_band[i], zf, Tc[u], rho, cp);
+                const double vol = d.wc[i] * d.dr[i] * dzg;
+                const double cap = cp * rho * vol / a.dt;
+                double dg = cap;
+                dg += cE[u]; dg += cW[u]; dg += cN[u]; dg += cS[u];
+                double rhs = cap * To[u];
+                if (i == nr - 1) {
+                    const double kout = k_outface(d, ph, g, Tc[u]);
+                    const double k0 = (ph.gamma == 0) ? d.k0_out[g] : kout;
+                    const double A_out = d.A_out_r * dzg;
+                    const double h = d.h_line[g], Ta = d.Tamb_line[g];
+                    if (zf & HP_ZF_BC_COND) {
+                        const double robin = kout * A_out / (h * d.d_out + k0);
+                        dg += robin * h;
+                        double gs = h * Ta;
+                        if (ph.radiation) gs += ph.sigma * d.eps_line[g] * (Ta * Ta * Ta * Ta - Tc[u] * Tc[u] * Tc[u] * Tc[u]);
+                        rhs += robin * gs;
+                    }
+                    if (zf & HP_ZF_BC_EVAP) {
+                        const double q = d.q_line[g];
+                        rhs += ((ph.source == 0) ? (q / kout) : q) * A_out;
+                    }
+                }
+                const double LT = dg * Tc[u] - Tnb[u];
+                const double r0 = rhs - LT;
+                d.diag[idx] = dg;
+                d.r[idx] = r0;
+                if (write_dinv_jacobi) d.dinv[idx] = 1.0 / dg;
+                if (a.rhs_out) a.rhs_out[idx] = rhs;
+                acc[0] += r0 * r0;
+                acc[1] += rhs * rhs;
+            }
         }
     }
     double tot[2];
