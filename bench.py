@@ -202,7 +202,7 @@ def run_gpu(args, rank, world, local_rank):
         loop_mode = 'host' if (world > 1 and args.comm == 'nccl' and not ensemble) else args.loop_mode
         if not ensemble:
             solver = make_solver_for_rank(mesh, cfg, rank, world, comm=args.comm, tol=args.tol, loop_mode=loop_mode,
-                                          extrapolate=os.environ.get('HP_EXTRAP', '1') != '0', precond=args.precond,
+                                          extrapolate=int(os.environ.get('HP_EXTRAP', '3')), precond=args.precond,
                                           mg_levels=args.mg_levels, mg_coarse_sweeps=args.mg_sweeps, mg_omega=args.mg_omega,
                                           refactor_every=args.refactor_every)
 

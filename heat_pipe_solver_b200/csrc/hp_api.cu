@@ -114,7 +114,8 @@ struct hp_solver_s {
     bool mg_fused = true;
     bool mg_upfused = true;      // coarse up-leg stages as one kernel (k_mg_up) instead of residual + line solve
     bool pdl = false;                 // programmatic dependent launch edges between the kernel nodes of the step graph
-    bool have_prev = false;          // Told holds the field of the previous step start (extrapolated PCG start)
+    int hist = 0;                    // completed steps since the field was last set: Told (and d1, d2) hold that much history
+    double hist_dt = 0.0;            // time step the history was taken with
     bool ghost_dirty = true;         // ghost rows of T must be refreshed by an explicit exchange before the next sweep
     // L2 access-policy window over the contiguous (q, z) block
     bool l2_on = false;
@@ -349,7 +350,7 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
     // measured on B200: programmatic edges make the step SLOWER (mgline 8.97 -> 10.70 ms, rline 18.2 -> 19.4 ms; the
     // early-scheduled dependents compete for SM slots with the draining grid) -> opt-in only (HP_PDL=1)
     { const char* e = getenv("HP_PDL"); h->pdl = (e && e[0] == '1'); }
-    h->opts.loop_mode = 1; h->opts.poll_chunk = 8; h->opts.refactor_every = 1; h->opts.extrapolate = 1;
+    h->opts.loop_mode = 1; h->opts.poll_chunk = 8; h->opts.refactor_every = 1; h->opts.extrapolate = 3;
     h->opts.mg_levels = 6; h->opts.mg_coarse_sweeps = 2; h->opts.mg_omega = 0.7;
 
     // initial field + snapshots (main.py:34,133,145,152)
@@ -403,6 +404,7 @@ int hp_set_opts(hp_handle h, const hp_solve_opts* o) {
     if (o->precond < 0 || o->precond > 2) return fail("hp_set_opts: precond must be 0 (jacobi), 1 (rline) or 2 (mgline)");
     if (o->criterion < 0 || o->criterion > 2) return fail("hp_set_opts: criterion must be 0, 1 or 2");
     if (!(o->tol > 0.0)) return fail("hp_set_opts: tol must be > 0");
+    if (o->extrapolate < 0 || o->extrapolate > 3) return fail("hp_set_opts: extrapolate must be 0 (off) .. 3 (cubic)");
     if (o->max_iter < 1) return fail("hp_set_opts: max_iter must be >= 1");
     if (o->loop_mode < 0 || o->loop_mode > 1) return fail("hp_set_opts: loop_mode must be 0 or 1");
     h->opts = *o;
@@ -425,7 +427,7 @@ int hp_set_T_dev(hp_handle h, const double* d_T) {
     if (!h || !d_T) return fail("hp_set_T_dev: null argument");
     CK(cudaMemcpyAsync(h->d.T + h->d.nr, d_T, owned_bytes(h), cudaMemcpyDeviceToDevice, h->stream));
     h->ghost_dirty = true;
-    h->have_prev = false;
+    h->hist = 0;
     return 0;
 }
 int hp_get_T_dev(hp_handle h, double* d_T) {
@@ -437,7 +439,7 @@ int hp_set_T_host(hp_handle h, const double* h_T) {
     if (!h || !h_T) return fail("hp_set_T_host: null argument");
     CK(cudaMemcpyAsync(h->d.T + h->d.nr, h_T, owned_bytes(h), cudaMemcpyHostToDevice, h->stream));
     h->ghost_dirty = true;
-    h->have_prev = false;
+    h->hist = 0;
     return 0;
 }
 int hp_get_T_host(hp_handle h, double* h_T) {
@@ -817,13 +819,15 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
     NodeChain c{ge.graph};
     Emitter e{h, &c};
     HpDev& d = h->d;
-    // update_old: 0 nothing, 1 Told <- T, 2 z <- T - Told (extrapolated start of the first solve) then Told <- T
-    if (update_old == 2) {
+    // update_old: 0 nothing, 1 Told <- T, 1 + k: z <- increment extrapolated at order k (start of the first solve) and
+    // Told <- T in one kernel
+    if (update_old >= 2) {
         HpKArgs a0 = make_args(h, dt, has_old);
+        a0.ext_order = update_old - 1;
         void* p0[] = {&d, &h->phys, &a0};
         if (chain_kernel(c, hpk::desc_delta(h->cfg, d), p0)) return -1;
     }
-    if (update_old) {
+    if (update_old == 1) {
         cudaGraphNode_t n;
         CK(cudaGraphAddMemcpyNode1D(&n, ge.graph, c.last ? &c.last : nullptr, c.last ? 1 : 0, d.Told, d.T,
                                     (size_t)(d.nz + 2) * d.nr * sizeof(double), cudaMemcpyDeviceToDevice));
@@ -834,7 +838,7 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
         cudaGraphConditionalHandle cond;
         CK(cudaGraphConditionalHandleCreate(&cond, ge.graph, 0, cudaGraphCondAssignDefault));
         a.use_cond = 1; a.cond = (unsigned long long)cond;
-        if (emit_sweep_head(e, a, (s % h->opts.refactor_every) == 0, update_old == 2 && s == 0)) return -1;
+        if (emit_sweep_head(e, a, (s % h->opts.refactor_every) == 0, update_old >= 2 && s == 0)) return -1;
         cudaGraphNodeParams cp{};
         cp.type = cudaGraphNodeTypeConditional;
         cp.conditional.handle = cond;
@@ -866,13 +870,31 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
 }
 
 // is_step = 0: a bare sweep (hp_sweep; the caller manages T_old).  is_step = 1: whole time steps (hp_step / hp_run):
-// Told <- T at the step start when has_old or extrapolate is set; with extrapolate and a completed previous step the
-// first solve starts from T + (T - T_prev).
+// Told <- T at the step start when has_old or extrapolate is set; with extrapolate and completed previous steps the
+// first solve starts from the field extrapolated from them (k_delta).
 static int run_steps(hp_solver_s* h, double dt, int n_steps, int sweeps, int has_old, int is_step) {
     if (!(dt > 0.0)) return fail("dt must be > 0");
     if (sweeps < 1) return fail("sweeps must be >= 1");
-    const bool ext = is_step && h->opts.extrapolate;
-    auto step_mode = [&]() { return !is_step ? 0 : (ext ? (h->have_prev ? 2 : 1) : (has_old ? 1 : 0)); };
+    const int max_order = is_step ? (h->opts.extrapolate > 3 ? 3 : h->opts.extrapolate) : 0;
+    const bool ext = max_order > 0;
+    if (ext && h->hist_dt != dt) { if (h->hist > 1) h->hist = 1; h->hist_dt = dt; }     // increments scale with dt
+    if (max_order >= 2 && !h->d.d1) {
+        const size_t bytes = h->field_elems * sizeof(double);
+        if (dev_alloc(h, (void**)&h->d.d1, bytes) || dev_alloc(h, (void**)&h->d.d2, bytes)) return -1;
+        CK(cudaMemsetAsync(h->d.d1, 0, bytes, h->stream));
+        CK(cudaMemsetAsync(h->d.d2, 0, bytes, h->stream));
+    }
+    // The order ramps up with the history: right after an impulsive start the higher differences are large and a
+    // high-order prediction is worse than a low-order one (measured with the oracle: quadratic pays from the 5th step,
+    // cubic from the 8th).  A poor prediction only costs PCG iterations, never accuracy.
+    auto order = [&]() {
+        int o = h->hist >= 1 ? 1 : 0;
+        if (max_order >= 2 && h->hist >= 4) o = 2;
+        if (max_order >= 3 && h->hist >= 7) o = 3;
+        return o;
+    };
+    auto step_mode = [&]() { return !is_step ? 0 : (ext ? 1 + order() : (has_old ? 1 : 0)); };
+    auto step_done = [&]() { if (ext && h->hist < 1000) h->hist++; };
     if (h->opts.loop_mode == 1 && (h->nranks == 1 || h->d.p2p) && !h->rhs_dbg && !h->prof_on) {
         if (h->nranks > 1 && h->ghost_dirty) { if (exchange_rows(h, h->d.T)) return -1; h->ghost_dirty = false; }
         for (int s = 0; s < n_steps; ++s) {
@@ -882,21 +904,21 @@ static int run_steps(hp_solver_s* h, double dt, int n_steps, int sweeps, int has
             h->launches_host += g->static_nodes;
             h->graph_body_nodes = g->body_nodes;
             h->sweeps_host += sweeps;
-            if (ext) h->have_prev = true;
+            step_done();
         }
         return 0;
     }
     for (int s = 0; s < n_steps; ++s) {
         const int mode = step_mode();
-        if (mode == 2) {
+        if (mode >= 2) {
             HpKArgs a0 = make_args(h, dt, has_old);
+            a0.ext_order = mode - 1;
             void* p0[] = {&h->d, &h->phys, &a0};
             if (launch(h, hpk::desc_delta(h->cfg, h->d), p0, KIND_OTHER)) return -1;
-        }
-        if (mode && hp_update_old(h)) return -1;
+        } else if (mode == 1 && hp_update_old(h)) return -1;
         for (int k = 0; k < sweeps; ++k)
-            if (sweep_stream(h, dt, has_old, (k % h->opts.refactor_every) == 0, mode == 2 && k == 0)) return -1;
-        if (ext) h->have_prev = true;
+            if (sweep_stream(h, dt, has_old, (k % h->opts.refactor_every) == 0, mode >= 2 && k == 0)) return -1;
+        step_done();
     }
     return 0;
 }
@@ -927,9 +949,9 @@ int hp_run_host(hp_handle h, const double* h_T_in, double* h_T_out, double dt, i
     if (!h || !h_T_in || !h_T_out) return fail("hp_run_host: null argument");
     // the uploaded field continues the transient: the previous step start kept in Told stays the history of the
     // extrapolated PCG start (it only seeds the solver; a stale history costs iterations, never accuracy)
-    const bool keep = h->have_prev;
+    const int keep = h->hist;
     if (hp_set_T_host(h, h_T_in)) return -1;
-    h->have_prev = keep;
+    h->hist = keep;
     if (hp_run(h, dt, n_steps, sweeps, has_old)) return -1;
     return hp_get_T_host(h, h_T_out);
 }

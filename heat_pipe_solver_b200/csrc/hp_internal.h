@@ -57,6 +57,7 @@ struct HpDev {
     double d_out;            // r_v[nr]-r_c[nr-1]
     // fields, (nz+2)*nr each, row g at g*nr
     double *T, *Told, *cR, *cZ, *diag, *dinv, *r, *q, *z, *p0, *p1;
+    double *d1, *d2;      // increments of the two steps before the last one (higher-order extrapolated start); may be null
     HpState* st;
     hp_sweep_stat* stats;    // ring of HP_STATS_CAP
     double* partials;        // [HP_NRED * HP_MAX_PARTIALS]
@@ -127,6 +128,7 @@ struct HpKArgs {
                                //    produces z, r.z and advances the recurrences
     int32_t init_phase;        // 1: this kernel sits in the INIT position of the sweep (no beta, iteration count kept)
     double omega;              // damping of the line smoother in the V-cycle
+    int32_t ext_order;         // k_delta: order of the extrapolated increment (1 linear, 2 quadratic, 3 cubic in the step index)
     int32_t shift;             // 1: this (A, B) pair moves the start of the solve to x0 + z (z = extrapolated increment):
                                //    alpha := 1, and k_cg_B finalises like the INIT kernel
     unsigned long long cond;   // cudaGraphConditionalHandle of the enclosing WHILE node (use_cond != 0)
@@ -159,7 +161,7 @@ bool pick_config(int nr, int nz, int num_sms, HpLaunchCfg* cfg, const char** err
 // variables with exactly these types/order (documented next to each kernel in hp_kernels.cu).
 HpKernelLaunch desc_snapshot_kout(const HpLaunchCfg&, const HpDev&);
 HpKernelLaunch desc_coef(const HpLaunchCfg&, const HpDev&);
-HpKernelLaunch desc_delta(const HpLaunchCfg&, const HpDev&);   // z = T - Told on every row (ghosts included)
+HpKernelLaunch desc_delta(const HpLaunchCfg&, const HpDev&);   // z = extrapolated increment, Told <- T, on every row (ghosts included)
 HpKernelLaunch desc_diag(const HpLaunchCfg&, const HpDev&);     // args: (HpDev, hp_phys, HpKArgs, int write_dinv, int tpr_log2)
 int diag_tpr_log2(int nr);
 HpKernelLaunch desc_factor(const HpLaunchCfg&, const HpDev&);

@@ -913,16 +913,32 @@ __global__ void k_fill_rows(HpDev d, double* __restrict__ field) {
         field[c] = d.Tamb_line[(int)(c / d.nr)];
 }
 
-// z = T - Told on every row: the increment of the previous time step, used as the extrapolated start of the
-// first solve of the next step (x0 = T + (T - T_prev); the system itself is still assembled at T, like FiPy's)
+// Start of a time step with an extrapolated first solve: with D_n = T - Told the increment of the step just finished and
+// d1 = D_{n-1}, d2 = D_{n-2} those of the steps before,
+//   z = D_n                       (order 1: x0 = 2 T_n - T_{n-1})
+//   z = 2 D_n - d1                (order 2: x0 = 3 T_n - 3 T_{n-1} + T_{n-2})
+//   z = 3 D_n - 3 d1 + d2         (order 3: x0 = 4 T_n - 6 T_{n-1} + 4 T_{n-2} - T_{n-3})
+// is the predicted increment of the next step (the system itself is still assembled at T, like FiPy's; the prediction only
+// seeds the PCG).  The history shifts (d2 <- d1 <- D_n) and Told <- T (`T.updateOld()`, main.py:269) in the same pass.
 __global__ void __launch_bounds__(256) k_delta(HpDev d, hp_phys ph, HpKArgs a) {
     pdl_enter();
     const long long n = (long long)(d.nz + 2) * d.nr;
-    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x)
-        d.z[c] = d.T[c] - d.Told[c];
+    const int ord = a.ext_order;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+        const double Tc = d.T[c];
+        const double dn = Tc - d.Told[c];
+        double z = dn;
+        if (d.d1) {
+            const double p1 = d.d1[c];
+            if (ord == 2) z = 2.0 * dn - p1;
+            else if (ord == 3) z = 3.0 * (dn - p1) + d.d2[c];
+            d.d2[c] = p1;
+            d.d1[c] = dn;
+        }
+        d.z[c] = z;
+        d.Told[c] = Tc;
+    }
 }
-
-
 
 // ---- replicated global coarse levels under slabs ---------------------------------------------------------------------
 // signal `kind` to every rank (sequence flag, release at system scope); called by ONE thread after the data stores of the

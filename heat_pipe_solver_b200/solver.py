@@ -176,7 +176,8 @@ class ConductionSolver:
         o.tol, o.max_iter = float(cur['tol']), int(cur['max_iter'])
         o.loop_mode = _choice(LOOP_MODE, cur['loop_mode'], 'loop_mode')
         o.poll_chunk, o.refactor_every = int(cur['poll_chunk']), int(cur['refactor_every'])
-        o.extrapolate = 1 if cur['extrapolate'] else 0
+        e = cur['extrapolate']                      # True = highest order (cubic), False = off, 1..3 = maximum order
+        o.extrapolate = (3 if e else 0) if isinstance(e, bool) else int(e)
         o.mg_levels, o.mg_coarse_sweeps, o.mg_omega = int(cur['mg_levels']), int(cur['mg_coarse_sweeps']), float(cur['mg_omega'])
         _lib.check(self.lib.hp_set_opts(self._h, C.byref(o)), 'hp_set_opts')
         self.options = cur

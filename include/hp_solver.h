@@ -73,8 +73,10 @@ typedef struct hp_solve_opts {
     int32_t loop_mode;      /* 0 host-polled chunks of poll_chunk iterations; 1 CUDA graph, device-side WHILE */
     int32_t poll_chunk;
     int32_t refactor_every; /* re-factor the line preconditioner every k-th sweep (1 = every sweep) */
-    int32_t extrapolate;    /* 1: hp_step/hp_run start the first solve of a step from T + (T - T_prev) (the system is still
-                               assembled at T and `res` is still FiPy's pre-solve residual; only the PCG start changes) */
+    int32_t extrapolate;    /* 0 off; k = 1..3: hp_step/hp_run start the first solve of a step from the field extrapolated from
+                               the last k+1 step values (1: T + (T - T_prev); 2 / 3: quadratic / cubic in the step index, used
+                               once enough steps of history exist).  The system is still assembled at T and `res` is still
+                               FiPy's pre-solve residual; only the PCG start changes */
     int32_t mg_levels;      /* mgline: maximum number of levels (>= 2) */
     int32_t mg_coarse_sweeps; /* mgline: extra smoothing sweeps on the coarsest level */
     int32_t _pad;

@@ -242,6 +242,31 @@ def test_extrapolated_start_saves_iterations_same_answer(cfg):
     assert np.max(np.abs(T - o.T)) <= 6 * PER_STEP_TOL_K
 
 
+def test_extrapolation_order_ramp(cfg):
+    """extrapolate = 1..3 caps the order of the predicted start (quadratic from the 5th step of history, cubic from the
+    8th): same field as the oracle at every order, the dt change drops back to the linear start, and the high order
+    never needs more iterations than the linear one on a smooth transient."""
+    n1, n2 = 16, 4
+    got = {}
+    for order in (1, 2, 3):
+        s, o = make_pair(cfg, SHAPES['s96x100'], has_old=True, solver_kw=dict(extrapolate=order))
+        with s:
+            s.run(0.1, n1, sweeps=2, has_old=True)
+            s.run(0.05, n2, sweeps=2, has_old=True)          # history taken with another dt is not reused
+            got[order] = (s.value.reshape(o.T.shape), s.total_iters)
+    for dt, n in ((0.1, n1), (0.05, n2)):
+        for _ in range(n):
+            o.update_old()
+            for _ in range(2):
+                o.sweep(dt, solver='banded')
+    for order in (1, 2, 3):
+        assert np.max(np.abs(got[order][0] - o.T)) <= (n1 + n2) * 2 * PER_STEP_TOL_K, order
+    assert got[3][1] <= 1.02 * got[1][1], (got[3][1], got[1][1])
+    assert got[2][1] <= 1.02 * got[1][1], (got[2][1], got[1][1])
+    with pytest.raises(Exception):
+        make_pair(cfg, SHAPES['s64x32'], solver_kw=dict(extrapolate=4))
+
+
 def test_checkpoint_resume_and_auto_sweeps(cfg, tmp_path):
     """checkpoint / resume of (T, step) and the sweep-to-convergence controller."""
     from heat_pipe_solver_b200.main import run
