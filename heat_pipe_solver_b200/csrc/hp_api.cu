@@ -116,6 +116,8 @@ struct hp_solver_s {
     bool pdl = false;                 // programmatic dependent launch edges between the kernel nodes of the step graph
     int hist = 0;                    // completed steps since the field was last set: Told (and d1, d2) hold that much history
     double hist_dt = 0.0;            // time step the history was taken with
+    bool c2_on = true;               // track the re-sweep correction (predicted start of the second sweep); HP_SWEEP2=0 disables
+    bool c2_stashed = false;         // d.c2 holds the first-sweep solution of the step just finished
     bool ghost_dirty = true;         // ghost rows of T must be refreshed by an explicit exchange before the next sweep
     // L2 access-policy window over the contiguous (q, z) block
     bool l2_on = false;
@@ -350,6 +352,7 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
     // measured on B200: programmatic edges make the step SLOWER (mgline 8.97 -> 10.70 ms, rline 18.2 -> 19.4 ms; the
     // early-scheduled dependents compete for SM slots with the draining grid) -> opt-in only (HP_PDL=1)
     { const char* e = getenv("HP_PDL"); h->pdl = (e && e[0] == '1'); }
+    { const char* e = getenv("HP_SWEEP2"); h->c2_on = !(e && e[0] == '0'); }
     h->opts.loop_mode = 1; h->opts.poll_chunk = 8; h->opts.refactor_every = 1; h->opts.extrapolate = 3;
     h->opts.mg_levels = 6; h->opts.mg_coarse_sweeps = 2; h->opts.mg_omega = 0.7;
 
@@ -427,7 +430,7 @@ int hp_set_T_dev(hp_handle h, const double* d_T) {
     if (!h || !d_T) return fail("hp_set_T_dev: null argument");
     CK(cudaMemcpyAsync(h->d.T + h->d.nr, d_T, owned_bytes(h), cudaMemcpyDeviceToDevice, h->stream));
     h->ghost_dirty = true;
-    h->hist = 0;
+    h->hist = 0; h->c2_stashed = false;
     return 0;
 }
 int hp_get_T_dev(hp_handle h, double* d_T) {
@@ -439,7 +442,7 @@ int hp_set_T_host(hp_handle h, const double* h_T) {
     if (!h || !h_T) return fail("hp_set_T_host: null argument");
     CK(cudaMemcpyAsync(h->d.T + h->d.nr, h_T, owned_bytes(h), cudaMemcpyHostToDevice, h->stream));
     h->ghost_dirty = true;
-    h->hist = 0;
+    h->hist = 0; h->c2_stashed = false;
     return 0;
 }
 int hp_get_T_host(hp_handle h, double* h_T) {
@@ -775,13 +778,21 @@ static int emit_sweep_head(Emitter& e, HpKArgs& a, bool refactor, bool shift) {
 // ---- one sweep with plain stream launches, host-polled PCG loop ------------------------------------------
 // Under axial slabs (nranks > 1): ghost rows of T before assembly, ghost rows of z before every direction
 // update, and the CG scalars combined over ranks after every reducing kernel.
-static int sweep_stream(hp_solver_s* h, double dt, int has_old, bool refactor, bool shift = false) {
+// stash: 0 no, 1 second sweep of a step: c2 <- T, 2 the same and start from T + c2 (predicted correction)
+static int sweep_stream(hp_solver_s* h, double dt, int has_old, bool refactor, bool shift = false, int stash = 0) {
     HpDev& d = h->d;
     HpKArgs a = make_args(h, dt, has_old);
     a.rhs_out = h->rhs_dbg;
     Emitter e{h, nullptr};
     if (apply_l2_to_stream(h)) return -1;
     if (h->nranks > 1 && (!d.p2p || h->ghost_dirty)) { if (exchange_rows(h, d.T)) return -1; h->ghost_dirty = false; }
+    if (stash) {
+        HpKArgs as = a;
+        as.c2_valid = stash == 2;
+        void* ps[] = {&d, &h->phys, &as};
+        if (launch(h, hpk::desc_stash(h->cfg, d), ps, KIND_OTHER)) return -1;
+        if (stash == 2) shift = true;
+    }
     if (emit_sweep_head(e, a, refactor, shift)) return -1;
     int launched = 0;
     while (true) {
@@ -821,13 +832,17 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
     HpDev& d = h->d;
     // update_old: 0 nothing, 1 Told <- T, 1 + k: z <- increment extrapolated at order k (start of the first solve) and
     // Told <- T in one kernel
-    if (update_old >= 2) {
+    // bit 3: c2 holds the first-sweep solution of the previous step; bit 4: this step tracks it (k_stash at its second sweep)
+    const int base = update_old & 7;
+    const bool c2v = (update_old & 8) != 0, track = (update_old & 16) != 0;
+    if (base >= 2) {
         HpKArgs a0 = make_args(h, dt, has_old);
-        a0.ext_order = update_old - 1;
+        a0.ext_order = base - 1;
+        a0.c2_valid = c2v ? 1 : 0;
         void* p0[] = {&d, &h->phys, &a0};
         if (chain_kernel(c, hpk::desc_delta(h->cfg, d), p0)) return -1;
     }
-    if (update_old == 1) {
+    if (base == 1) {
         cudaGraphNode_t n;
         CK(cudaGraphAddMemcpyNode1D(&n, ge.graph, c.last ? &c.last : nullptr, c.last ? 1 : 0, d.Told, d.T,
                                     (size_t)(d.nz + 2) * d.nr * sizeof(double), cudaMemcpyDeviceToDevice));
@@ -838,7 +853,13 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
         cudaGraphConditionalHandle cond;
         CK(cudaGraphConditionalHandleCreate(&cond, ge.graph, 0, cudaGraphCondAssignDefault));
         a.use_cond = 1; a.cond = (unsigned long long)cond;
-        if (emit_sweep_head(e, a, (s % h->opts.refactor_every) == 0, update_old >= 2 && s == 0)) return -1;
+        if (track && s == 1) {
+            HpKArgs as = a;
+            as.c2_valid = c2v ? 1 : 0;
+            void* ps[] = {&d, &h->phys, &as};
+            if (chain_kernel(c, hpk::desc_stash(h->cfg, d), ps)) return -1;
+        }
+        if (emit_sweep_head(e, a, (s % h->opts.refactor_every) == 0, (base >= 2 && s == 0) || (track && c2v && s == 1))) return -1;
         cudaGraphNodeParams cp{};
         cp.type = cudaGraphNodeTypeConditional;
         cp.conditional.handle = cond;
@@ -893,8 +914,20 @@ static int run_steps(hp_solver_s* h, double dt, int n_steps, int sweeps, int has
         if (max_order >= 3 && h->hist >= 7) o = 3;
         return o;
     };
-    auto step_mode = [&]() { return !is_step ? 0 : (ext ? 1 + order() : (has_old ? 1 : 0)); };
-    auto step_done = [&]() { if (ext && h->hist < 1000) h->hist++; };
+    // re-sweep correction tracking (see k_delta / k_stash): needs a second sweep to stash the first-sweep solution at
+    const bool track = ext && sweeps >= 2 && h->c2_on;
+    if (track && !h->d.c2) {
+        const size_t bytes = h->field_elems * sizeof(double);
+        if (dev_alloc(h, (void**)&h->d.c2, bytes)) return -1;
+        CK(cudaMemsetAsync(h->d.c2, 0, bytes, h->stream));
+    }
+    if (!track) h->c2_stashed = false;
+    // bits 0-2: 0 nothing, 1 Told <- T, 1 + k extrapolated start of order k; bit 3: c2 usable; bit 4: tracking on
+    auto step_mode = [&]() {
+        const int base = !is_step ? 0 : (ext ? 1 + order() : (has_old ? 1 : 0));
+        return base | ((track && h->c2_stashed && base >= 2) ? 8 : 0) | (track ? 16 : 0);
+    };
+    auto step_done = [&]() { if (ext && h->hist < 1000) h->hist++; h->c2_stashed = track; };
     if (h->opts.loop_mode == 1 && (h->nranks == 1 || h->d.p2p) && !h->rhs_dbg && !h->prof_on) {
         if (h->nranks > 1 && h->ghost_dirty) { if (exchange_rows(h, h->d.T)) return -1; h->ghost_dirty = false; }
         for (int s = 0; s < n_steps; ++s) {
@@ -909,15 +942,18 @@ static int run_steps(hp_solver_s* h, double dt, int n_steps, int sweeps, int has
         return 0;
     }
     for (int s = 0; s < n_steps; ++s) {
-        const int mode = step_mode();
+        const int key = step_mode(), mode = key & 7;
+        const bool c2v = (key & 8) != 0;
         if (mode >= 2) {
             HpKArgs a0 = make_args(h, dt, has_old);
             a0.ext_order = mode - 1;
+            a0.c2_valid = c2v ? 1 : 0;
             void* p0[] = {&h->d, &h->phys, &a0};
             if (launch(h, hpk::desc_delta(h->cfg, h->d), p0, KIND_OTHER)) return -1;
         } else if (mode == 1 && hp_update_old(h)) return -1;
         for (int k = 0; k < sweeps; ++k)
-            if (sweep_stream(h, dt, has_old, (k % h->opts.refactor_every) == 0, mode >= 2 && k == 0)) return -1;
+            if (sweep_stream(h, dt, has_old, (k % h->opts.refactor_every) == 0, mode >= 2 && k == 0,
+                             (track && k == 1) ? (c2v ? 2 : 1) : 0)) return -1;
         step_done();
     }
     return 0;
@@ -950,8 +986,9 @@ int hp_run_host(hp_handle h, const double* h_T_in, double* h_T_out, double dt, i
     // the uploaded field continues the transient: the previous step start kept in Told stays the history of the
     // extrapolated PCG start (it only seeds the solver; a stale history costs iterations, never accuracy)
     const int keep = h->hist;
+    const bool keep_c2 = h->c2_stashed;
     if (hp_set_T_host(h, h_T_in)) return -1;
-    h->hist = keep;
+    h->hist = keep; h->c2_stashed = keep_c2;
     if (hp_run(h, dt, n_steps, sweeps, has_old)) return -1;
     return hp_get_T_host(h, h_T_out);
 }

@@ -58,6 +58,7 @@ struct HpDev {
     // fields, (nz+2)*nr each, row g at g*nr
     double *T, *Told, *cR, *cZ, *diag, *dinv, *r, *q, *z, *p0, *p1;
     double *d1, *d2;      // increments of the two steps before the last one (higher-order extrapolated start); may be null
+    double *c2;           // first-sweep solution of the running step / correction the later sweeps added to it; may be null
     HpState* st;
     hp_sweep_stat* stats;    // ring of HP_STATS_CAP
     double* partials;        // [HP_NRED * HP_MAX_PARTIALS]
@@ -129,6 +130,7 @@ struct HpKArgs {
     int32_t init_phase;        // 1: this kernel sits in the INIT position of the sweep (no beta, iteration count kept)
     double omega;              // damping of the line smoother in the V-cycle
     int32_t ext_order;         // k_delta: order of the extrapolated increment (1 linear, 2 quadratic, 3 cubic in the step index)
+    int32_t c2_valid;          // k_delta / k_stash: d.c2 holds usable history
     int32_t shift;             // 1: this (A, B) pair moves the start of the solve to x0 + z (z = extrapolated increment):
                                //    alpha := 1, and k_cg_B finalises like the INIT kernel
     unsigned long long cond;   // cudaGraphConditionalHandle of the enclosing WHILE node (use_cond != 0)
@@ -161,6 +163,7 @@ bool pick_config(int nr, int nz, int num_sms, HpLaunchCfg* cfg, const char** err
 // variables with exactly these types/order (documented next to each kernel in hp_kernels.cu).
 HpKernelLaunch desc_snapshot_kout(const HpLaunchCfg&, const HpDev&);
 HpKernelLaunch desc_coef(const HpLaunchCfg&, const HpDev&);
+HpKernelLaunch desc_stash(const HpLaunchCfg&, const HpDev&);   // second sweep of a step: z <- c2 (predicted correction), c2 <- T
 HpKernelLaunch desc_delta(const HpLaunchCfg&, const HpDev&);   // z = extrapolated increment, Told <- T, on every row (ghosts included)
 HpKernelLaunch desc_diag(const HpLaunchCfg&, const HpDev&);     // args: (HpDev, hp_phys, HpKArgs, int write_dinv, int tpr_log2)
 int diag_tpr_log2(int nr);

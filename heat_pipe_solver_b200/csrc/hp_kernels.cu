@@ -920,13 +920,22 @@ __global__ void k_fill_rows(HpDev d, double* __restrict__ field) {
 //   z = 3 D_n - 3 d1 + d2         (order 3: x0 = 4 T_n - 6 T_{n-1} + 4 T_{n-2} - T_{n-3})
 // is the predicted increment of the next step (the system itself is still assembled at T, like FiPy's; the prediction only
 // seeds the PCG).  The history shifts (d2 <- d1 <- D_n) and Told <- T (`T.updateOld()`, main.py:269) in the same pass.
+// With re-sweeps the first solve of a step does not produce the step's final field F_n but S1_n, short of it by the
+// correction C_n = F_n - S1_n the later sweeps add (property update; ~1e-6 K, smooth in time).  k_stash keeps S1_n in c2;
+// here C_n is formed, the history is built from the first-sweep increments D_n = S1_n - F_{n-1} (so the prediction aims
+// at S1_{n+1}, what the first solve actually converges to), and c2 <- C_n is the predicted start of the second sweep.
 __global__ void __launch_bounds__(256) k_delta(HpDev d, hp_phys ph, HpKArgs a) {
     pdl_enter();
     const long long n = (long long)(d.nz + 2) * d.nr;
     const int ord = a.ext_order;
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
         const double Tc = d.T[c];
-        const double dn = Tc - d.Told[c];
+        double dn = Tc - d.Told[c];
+        if (d.c2 && a.c2_valid) {
+            const double cn = Tc - d.c2[c];
+            d.c2[c] = cn;
+            dn -= cn;
+        }
         double z = dn;
         if (d.d1) {
             const double p1 = d.d1[c];
@@ -937,6 +946,17 @@ __global__ void __launch_bounds__(256) k_delta(HpDev d, hp_phys ph, HpKArgs a) {
         }
         d.z[c] = z;
         d.Told[c] = Tc;
+    }
+}
+
+// head of the second sweep of a step (T = S1_n, every row incl. ghosts): z <- C_{n-1} as the predicted increment of this
+// sweep (applied by the shift pair), c2 <- S1_n for k_delta of the next step
+__global__ void __launch_bounds__(256) k_stash(HpDev d, hp_phys ph, HpKArgs a) {
+    pdl_enter();
+    const long long n = (long long)(d.nz + 2) * d.nr;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+        if (a.c2_valid) d.z[c] = d.c2[c];
+        d.c2[c] = d.T[c];
     }
 }
 
@@ -1473,6 +1493,9 @@ HpKernelLaunch desc_snapshot_kout(const HpLaunchCfg& c, const HpDev& d) {
 }
 HpKernelLaunch desc_coef(const HpLaunchCfg& c, const HpDev& d) {
     return {(const void*)k_coef, dim3(c.grid_cell), dim3(c.cta_cell), 0};
+}
+HpKernelLaunch desc_stash(const HpLaunchCfg& c, const HpDev& d) {
+    return {(const void*)k_stash, dim3(c.grid_cell), dim3(c.cta_cell), 0};
 }
 HpKernelLaunch desc_delta(const HpLaunchCfg& c, const HpDev& d) {
     return {(const void*)k_delta, dim3(c.grid_cell), dim3(c.cta_cell), 0};
