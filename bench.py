@@ -40,7 +40,8 @@ RADIAL_SPLIT = {1024: (128, 256, 640), 4096: (512, 1024, 2560), 512: (64, 128, 3
 DT, SWEEPS, HAS_OLD = 0.1, 5, True
 # algorithmic bytes per cell and launch (fp64; DESIGN.md "Kernels"): reads + writes of full-size fields
 BYTES_PER_CELL = {'cg_A': 56, 'cg_B': 72, 'cg_init': 32, 'diag': 48, 'factor': 24, 'coef': 24,
-                  'mg_res': 56, 'mg_line': 48}      # fine-level V-cycle kernels (down 52 / up 60 B per cell; final line solve 48)
+                  'mg_res': 62, 'mg_line': 48}      # fine-level V-cycle kernels (down 64 incl. the fused level-1 pre-smoothing / up 60
+                                                    # B per cell; final line solve 48)
 
 
 def parse_workload(s):
@@ -271,9 +272,11 @@ def run_gpu(args, rank, world, local_rank):
             peak, peak_src = measured_peak()
             tot_ms = sum(v[1] for v in kt.values())
             dom = max((k for k in kt if k in BYTES_PER_CELL), key=lambda k: kt[k][1])
-            cnt, tms = kt[dom]
+            # per-launch duration over the launches that did the kernel's work ("full": >= half the longest launch of the
+            # kind) -- launches that return at once in an already converged sweep do not move the algorithmic bytes
+            cnt, tms, fcnt, fms = kt[dom]
             bytes_per_launch = BYTES_PER_CELL.get(dom, 0) * n_cells
-            achieved = bytes_per_launch / (tms / cnt * 1e-3) / 1e9 if cnt else 0.0
+            achieved = bytes_per_launch / (fms / fcnt * 1e-3) / 1e9 if fcnt else 0.0
             traffic = None
             tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
             if os.path.exists(tp):
@@ -283,11 +286,12 @@ def run_gpu(args, rank, world, local_rank):
                     traffic = None
             roof = {'bound': 'hbm', 'kernel': 'k_' + dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                     'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                    'algorithmic_bytes_per_launch': bytes_per_launch, 'avg_launch_ms': tms / cnt if cnt else None,
+                    'algorithmic_bytes_per_launch': bytes_per_launch, 'avg_launch_ms': fms / fcnt if fcnt else None,
+                    'launches_timed': fcnt, 'launches_returning_at_once': cnt - fcnt,
                     'share_of_step': tms / tot_ms if tot_ms else None,
-                    'all_kernels': {k: {'launches': c, 'avg_ms': (m / c if c else None),
-                                        'GBps': (BYTES_PER_CELL.get(k, 0) * n_cells / (m / c * 1e-3) / 1e9 if c else None)}
-                                    for k, (c, m) in kt.items() if c}}
+                    'all_kernels': {k: {'launches': c, 'total_ms': m, 'full_launches': fc, 'avg_ms': (fm / fc if fc else None),
+                                        'GBps': (BYTES_PER_CELL.get(k, 0) * n_cells / (fm / fc * 1e-3) / 1e9 if fc else None)}
+                                    for k, (c, m, fc, fm) in kt.items() if c}}
         solver.close()
         # strong-scaling reference: the same 16384x4096 workload on ONE GPU (rank 0, after the slab handles are gone)
         strong = None

@@ -44,7 +44,8 @@ class HpSweepStat(C.Structure):
 
 
 class HpKernelTimes(C.Structure):
-    _fields_ = [('count', C.c_int64 * 16), ('total_ms', C.c_double * 16)]
+    _fields_ = [('count', C.c_int64 * 16), ('total_ms', C.c_double * 16),
+                ('full_count', C.c_int64 * 16), ('full_ms', C.c_double * 16)]
 
 
 KERNEL_KINDS = ('other', 'coef', 'diag', 'factor', 'cg_init', 'cg_A', 'cg_B', 'mg_res', 'mg_line', 'mg_coarse', 'mg_setup',

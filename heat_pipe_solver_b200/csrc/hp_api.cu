@@ -1200,12 +1200,18 @@ int hp_profile_end(hp_handle h, hp_kernel_times* out) {
     h->prof_on = false;
     CK(cudaStreamSynchronize(h->stream));
     memset(out, 0, sizeof(*out));
+    std::vector<float> ms(h->prof_used, 0.f);
+    float longest[16] = {0};
     for (size_t k = 0; k < h->prof_used; ++k) {
-        float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, h->prof_ev[2 * k], h->prof_ev[2 * k + 1]));
+        CK(cudaEventElapsedTime(&ms[k], h->prof_ev[2 * k], h->prof_ev[2 * k + 1]));
         int kind = h->prof_kind[k];
         out->count[kind] += 1;
-        out->total_ms[kind] += ms;
+        out->total_ms[kind] += ms[k];
+        if (ms[k] > longest[kind]) longest[kind] = ms[k];
+    }
+    for (size_t k = 0; k < h->prof_used; ++k) {
+        int kind = h->prof_kind[k];
+        if (ms[k] >= 0.5f * longest[kind]) { out->full_count[kind] += 1; out->full_ms[kind] += ms[k]; }
     }
     return 0;
 }

@@ -292,10 +292,12 @@ class ConductionSolver:
         _lib.check(self.lib.hp_profile_begin(self._h, int(max_launches)), 'hp_profile_begin')
 
     def profile_end(self):
-        """-> {kind: (launches, total_ms)}"""
+        """-> {kind: (launches, total_ms, full_launches, full_ms)}; "full" = launches that did the work of the kind
+        (duration >= half the longest one), i.e. without those that return at once because the sweep is converged."""
         kt = _lib.HpKernelTimes()
         _lib.check(self.lib.hp_profile_end(self._h, C.byref(kt)), 'hp_profile_end')
-        return {name: (int(kt.count[i]), float(kt.total_ms[i])) for i, name in enumerate(_lib.KERNEL_KINDS)}
+        return {name: (int(kt.count[i]), float(kt.total_ms[i]), int(kt.full_count[i]), float(kt.full_ms[i]))
+                for i, name in enumerate(_lib.KERNEL_KINDS)}
 
     def assemble_debug(self, dt, has_old=False):
         """The assembled 5-point system at the current iterate, as (nz, nr) CUDA tensors."""

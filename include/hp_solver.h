@@ -147,8 +147,11 @@ int hp_eval_cell_fields(hp_handle h, double* d_rho, double* d_cp, double* d_kavg
  * 9 mg kernels of the replicated (multi-GPU) coarse levels, 10 mg setup (coarsening + coarse pivots),
  * 11..15 mg kernels of local coarse level 1..5 (15 = level 5 and deeper) */
 typedef struct hp_kernel_times {
-    int64_t count[16];
+    int64_t count[16];          /* every launch of the kind */
     double total_ms[16];
+    int64_t full_count[16];     /* launches that did the work of the kind: duration >= half the longest one.  Launches   */
+    double full_ms[16];         /* that return at once (sweep already converged, iterations past the end of a polled   */
+                                /* chunk) would otherwise pull the per-launch average -- the roofline numerator -- down */
 } hp_kernel_times;
 int hp_profile_begin(hp_handle h, int max_launches);
 int hp_profile_end(hp_handle h, hp_kernel_times* out);

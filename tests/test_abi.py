@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.HpMeshDesc) == 4 * 4 + 12 * 8
     assert C.sizeof(_lib.HpSolveOpts) == 56
     assert C.sizeof(_lib.HpSweepStat) == 32
-    assert C.sizeof(_lib.HpKernelTimes) == 256
+    assert C.sizeof(_lib.HpKernelTimes) == 512
 
 
 def test_no_cpu_fallback(built_lib, cfg):

@@ -61,13 +61,13 @@ idx = [h.index(k) for k in keep if k in h]
 traffic = {}
 with open(os.path.join(P, f'{tag}_ncu_cg_metrics.csv'), 'w', newline='') as f:
     w = csv.writer(f)
-    w.writerow(['# ncu --set full --clock-control none --import-source on -k regex:k_cg_ -s 600 -c 4 (cold cache per replay: the L2 window does not show here)'])
+    w.writerow(['# ncu --set full --clock-control none --import-source on -k regex:k_cg_A|k_cg_B|k_mg_res|k_mg_line|k_mg_fused -s 5666 -c 16 = one PCG iteration of the first sweep of a step (cold cache per replay: the L2 window does not show here)'])
     w.writerow([h[i] for i in idx])
     w.writerow([units[i] for i in idx])
     for r in body:
         w.writerow([r[i] for i in idx])
         kname = r[h.index('Kernel Name')]
-        name = next((v for k, v in (('k_cg_A', 'cg_A'), ('k_cg_B', 'cg_B'), ('k_mg_res', 'mg_res'), ('k_mg_line', 'mg_line')) if k in kname), 'other')
+        name = next((v for k, v in (('k_cg_A', 'cg_A'), ('k_cg_B', 'cg_B'), ('k_mg_res', 'mg_res'), ('k_mg_fused', 'mg_res'), ('k_mg_line', 'mg_line')) if k in kname), 'other')
 
         def tobytes(col):
             v, u = float(r[h.index(col)].replace(',', '')), units[h.index(col)]
