@@ -721,6 +721,10 @@ static int emit_iteration(Emitter& e, HpKArgs& a) {
     hp_solver_s* h = e.h;
     HpDev& d = h->d;
     void* params[] = {&d, &h->phys, &a};
+    // mgline: the cycle that turns z_line (left by the INIT kernel, the shift pair or the previous k_cg_B) into the
+    // preconditioned residual OPENS the body: a sweep that is converged at its INIT decision, and the pass after the last
+    // k_cg_B, launch no V-cycle kernels at all
+    if (a.mg && emit_vcycle(e, a, 0)) return -1;
     if (h->nranks > 1 && !d.p2p) {                       // p2p: the producer stored the rows into the ghosts itself
         if (e.chain) return fail("NCCL slab exchange cannot be captured");
         if (exchange_rows(h, d.z)) return -1;
@@ -729,7 +733,6 @@ static int emit_iteration(Emitter& e, HpKArgs& a) {
     if (emit_combine(e, a, 1)) return -1;
     if (emit(e, hpk::desc_cg_B(h->cfg, d, h->opts.precond != 0, h->opts.criterion), params, KIND_B)) return -1;
     if (emit_combine(e, a, 2)) return -1;
-    if (a.mg && emit_vcycle(e, a, 0)) return -1;
     return 0;
 }
 
@@ -765,12 +768,10 @@ static int emit_sweep_head(Emitter& e, HpKArgs& a, bool refactor, bool shift) {
         if (emit(e, hpk::desc_cg_B(h->cfg, d, h->opts.precond != 0, h->opts.criterion), ps, KIND_B)) return -1;
         if (emit_combine(e, as, 3)) return -1;
         if (a.mg && refactor && emit_mg_setup(e, h->opts.refactor_every > 1)) return -1;
-        if (a.mg && emit_vcycle(e, as, 1)) return -1;
     } else {
         if (emit(e, hpk::desc_cg_init(h->cfg, d, h->opts.precond != 0, h->opts.criterion), params, KIND_INIT)) return -1;
         if (emit_combine(e, a, 3)) return -1;
         if (a.mg && refactor && emit_mg_setup(e, h->opts.refactor_every > 1)) return -1;
-        if (a.mg && emit_vcycle(e, a, 1)) return -1;      // skipped on the device if the sweep is already converged
     }
     return 0;
 }

@@ -28,7 +28,7 @@ struct HpState {
     int32_t first;       // 1 -> next direction update uses beta = 0 (p := z)
     int32_t parity;      // which p buffer holds the current search direction
     int32_t flags;       // hp_sweep_stat.flags of the current sweep
-    int32_t _pad;
+    int32_t mg_init;     // 1 -> the next V-cycle is the first of its sweep (its last kernel starts the rz recurrence: no beta)
     unsigned int ticket; // last-CTA election
     unsigned int _pad2;
     long long sweep_count;
@@ -127,7 +127,7 @@ struct HpKArgs {
     int32_t prefetch;          // bit0: k_cg_A, bit1: k_cg_B issue bulk L2 prefetches of the next row
     int32_t mg;                // 1: 'mgline' preconditioner: k_cg_B only decides convergence, the V-cycle's last kernel
                                //    produces z, r.z and advances the recurrences
-    int32_t init_phase;        // 1: this kernel sits in the INIT position of the sweep (no beta, iteration count kept)
+    int32_t init_phase;        // (unused since the V-cycle opens the loop body: HpState.mg_init tells the first cycle of a sweep)
     double omega;              // damping of the line smoother in the V-cycle
     int32_t ext_order;         // k_delta: order of the extrapolated increment (1 linear, 2 quadratic, 3 cubic in the step index)
     int32_t c2_valid;          // k_delta / k_stash: d.c2 holds usable history

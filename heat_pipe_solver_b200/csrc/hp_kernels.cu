@@ -194,6 +194,10 @@ __device__ __forceinline__ void finalize_B(const HpDev& d, const HpKArgs& a, boo
     int flags = s->flags;
     int done = 0;
     hp_sweep_stat* stt = &d.stats[(s->sweep_count - 1) % HP_STATS_CAP];
+    // mgline: the V-cycle opens the loop body, so the same kernel nodes serve the first cycle of a sweep (after the INIT
+    // kernel / the shift pair) and the later ones: the INIT-position decision leaves the mark, the cycle's end consumes it
+    if (stage == 1 && init) s->mg_init = 1;
+    if (stage == 2) { init = s->mg_init != 0; s->mg_init = 0; }
     if (stage != 1) {
         if (init) {
             s->rz = rz_new;
