@@ -400,3 +400,28 @@ def test_full_size_sweep_residual_property(cfg):
     r = S.rhs - S.matvec(T)
     assert np.max(np.abs(r / S.diag)) <= 1e-7
     assert np.isfinite(T).all() and T.min() > 280.0 and T.max() < 800.0
+
+
+@pytest.mark.parametrize('name', ['simple_1sweep', 'tdep_5sweeps', 'intended_physics'])
+def test_cuda_path_matches_committed_snapshots(cfg, name):
+    """The CUDA path against the committed field snapshots (tests/golden/oracle_golden.npz, written by the oracle with
+    direct solves): no oracle code runs in this test, only the fixture is read."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sp = importlib.util.spec_from_file_location('make_oracle_golden', os.path.join(root, 'tests', 'golden', 'make_oracle_golden.py'))
+    mod = importlib.util.module_from_spec(sp)
+    sp.loader.exec_module(mod)
+    spec = mod.CASES[name]
+    gold = np.load(os.path.join(root, 'tests', 'golden', 'oracle_golden.npz'))
+    from heat_pipe_solver_b200 import ConductionSolver, generate_composite_mesh
+    mesh, _ = generate_composite_mesh(dict(cfg['mesh']), cfg['dimensions'])
+    with ConductionSolver(mesh, cfg['dimensions'], cfg['parameters'], cfg['constants'], **spec['modes']) as s:
+        s.run(spec['dt'], spec['steps'], sweeps=spec['sweeps'], has_old=spec['has_old'])
+        T = s.value.reshape(gold[name + '_T'].shape)
+        res = np.array([st['residual_l2'] for st in s.stats(spec['steps'] * spec['sweeps'])])
+    n_solves = spec['steps'] * spec['sweeps']
+    assert np.max(np.abs(T - gold[name + '_T'])) <= min(END_TOL_K, n_solves * PER_STEP_TOL_K)
+    ref = gold[name + '_res'][-len(res):]
+    big = ref > 1e-5
+    assert np.allclose(res[big], ref[big], rtol=1e-4)

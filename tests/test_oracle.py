@@ -2,11 +2,15 @@
 coarse read-offs of the reference's committed plots, analytic known answers, and
 internal consistency (direct vs iterative solvers, symmetry, conservation).  FiPy cannot run here, so the
 assembled solve itself stays "parity unpinned" (see oracle/fv_oracle.py header)."""
+import os
+
 import numpy as np
 import pytest
 from scipy import optimize, special
 
 from oracle import fv_oracle as fo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope='module')
@@ -154,3 +158,18 @@ def test_mgline_twin_matches_direct_solve_and_needs_few_iterations(cfg):
     PtAPx = A_Px[0::2].copy()
     PtAPx[:nz // 2] += A_Px[1::2]
     assert np.allclose(PtAPx, lv[1].S.matvec(x), rtol=1e-12, atol=1e-12 * np.abs(S.diag).max())
+
+
+@pytest.mark.parametrize('name', ['simple_1sweep', 'tdep_5sweeps', 'intended_physics'])
+def test_oracle_reproduces_committed_snapshots(name):
+    """Regression fixtures written by tests/golden/make_oracle_golden.py (the oracle pinned to itself: the reference has
+    no golden vectors for the assembled solve)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('make_oracle_golden', os.path.join(ROOT, 'tests', 'golden', 'make_oracle_golden.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'oracle_golden.npz'))
+    T, res = mod.run_case(mod.CASES[name])
+    assert np.max(np.abs(T - gold[name + '_T'])) <= 1e-9
+    big = gold[name + '_res'] > 1e-7          # residuals at round-off level are not reproducible across BLAS builds
+    assert np.allclose(res[big], gold[name + '_res'][big], rtol=1e-6)
