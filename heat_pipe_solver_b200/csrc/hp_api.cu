@@ -245,6 +245,10 @@ static HpKArgs make_args(const hp_solver_s* h, double dt, int has_old) {
     static const int pf = [] { const char* e = getenv("HP_PREFETCH"); return e ? atoi(e) : 0; }();
     a.prefetch = pf;
     a.mg = (h->opts.precond == 2) ? 1 : 0; a.init_phase = 0; a.omega = h->opts.mg_omega; a.shift = 0;   // measured slower on B200 (profiles/): off unless asked for
+    // repeated converged sweeps as bookkeeping only (HpState.noop_ok); under slabs the reducing kernels must run on every
+    // rank for the flag protocol, so single GPU only.  HP_NOOP=0 disables (A/B measurements).
+    static const int noop = [] { const char* e = getenv("HP_NOOP"); return (e && e[0] == '0') ? 0 : 1; }();
+    a.noop_enable = (noop && h->nranks == 1) ? 1 : 0;
     return a;
 }
 
@@ -402,6 +406,13 @@ int hp_set_stream(hp_handle h, void* stream) {
     return 0;
 }
 
+// anything the host changes that a sweep depends on (T, T_old, solver options) ends the "next sweep repeats the last one"
+// state kept on the device
+static int invalidate_noop(hp_solver_s* h) {
+    if (h->d.st) CK(cudaMemsetAsync(&h->d.st->noop_ok, 0, sizeof(int32_t), h->stream));
+    return 0;
+}
+
 int hp_set_opts(hp_handle h, const hp_solve_opts* o) {
     if (!h || !o) return fail("hp_set_opts: null argument");
     if (o->precond < 0 || o->precond > 2) return fail("hp_set_opts: precond must be 0 (jacobi), 1 (rline) or 2 (mgline)");
@@ -421,17 +432,18 @@ int hp_set_opts(hp_handle h, const hp_solve_opts* o) {
         if (setup_mg(h)) return -1;
         if (h->nlev < 2) h->opts.precond = 1;          // mesh too short to coarsen: plain line preconditioner
     }
-    return 0;
+    return invalidate_noop(h);
 }
 
 static size_t owned_bytes(hp_handle h) { return (size_t)h->d.nz * h->d.nr * sizeof(double); }
+
 
 int hp_set_T_dev(hp_handle h, const double* d_T) {
     if (!h || !d_T) return fail("hp_set_T_dev: null argument");
     CK(cudaMemcpyAsync(h->d.T + h->d.nr, d_T, owned_bytes(h), cudaMemcpyDeviceToDevice, h->stream));
     h->ghost_dirty = true;
     h->hist = 0; h->c2_stashed = false;
-    return 0;
+    return invalidate_noop(h);
 }
 int hp_get_T_dev(hp_handle h, double* d_T) {
     if (!h || !d_T) return fail("hp_get_T_dev: null argument");
@@ -443,7 +455,7 @@ int hp_set_T_host(hp_handle h, const double* h_T) {
     CK(cudaMemcpyAsync(h->d.T + h->d.nr, h_T, owned_bytes(h), cudaMemcpyHostToDevice, h->stream));
     h->ghost_dirty = true;
     h->hist = 0; h->c2_stashed = false;
-    return 0;
+    return invalidate_noop(h);
 }
 int hp_get_T_host(hp_handle h, double* h_T) {
     if (!h || !h_T) return fail("hp_get_T_host: null argument");
@@ -456,7 +468,7 @@ const double* hp_T_ptr(hp_handle h) { return h ? h->d.T + h->d.nr : nullptr; }
 int hp_update_old(hp_handle h) {
     if (!h) return fail("null handle");
     CK(cudaMemcpyAsync(h->d.Told, h->d.T, (size_t)(h->d.nz + 2) * h->d.nr * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    return 0;
+    return invalidate_noop(h);
 }
 
 // ---- slab halo exchange / scalar all-gather (NCCL) ----------------------------------------------------
@@ -848,6 +860,12 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
         CK(cudaGraphAddMemcpyNode1D(&n, ge.graph, c.last ? &c.last : nullptr, c.last ? 1 : 0, d.Told, d.T,
                                     (size_t)(d.nz + 2) * d.nr * sizeof(double), cudaMemcpyDeviceToDevice));
         c.last = n; c.last_is_kernel = false;
+        // T_old moved: the first sweep of this step is not a repeat of the last sweep of the previous one
+        cudaMemsetParams mp{};
+        mp.dst = &d.st->noop_ok; mp.value = 0; mp.elementSize = 4; mp.width = 1; mp.height = 1; mp.pitch = 4;
+        cudaGraphNode_t mn;
+        CK(cudaGraphAddMemsetNode(&mn, ge.graph, &c.last, 1, &mp));
+        c.last = mn;
     }
     for (int s = 0; s < sweeps; ++s) {
         HpKArgs a = make_args(h, dt, has_old);

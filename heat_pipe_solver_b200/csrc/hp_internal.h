@@ -33,6 +33,11 @@ struct HpState {
     unsigned int _pad2;
     long long sweep_count;
     long long total_iters;
+    // A sweep that converged at its INIT decision (no iteration, no shifted start) left T, r, diag and the decision inputs
+    // untouched: an identical sweep right after it (same dt / has_old, T_old untouched) is pure bookkeeping
+    int32_t noop_ok;
+    int32_t noop_has_old;
+    double noop_dt;
 };
 
 // Geometry / region / boundary arrays (device, 1-D) + field arrays (device, ghost-inclusive rows).
@@ -131,6 +136,7 @@ struct HpKArgs {
     double omega;              // damping of the line smoother in the V-cycle
     int32_t ext_order;         // k_delta: order of the extrapolated increment (1 linear, 2 quadratic, 3 cubic in the step index)
     int32_t c2_valid;          // k_delta / k_stash: d.c2 holds usable history
+    int32_t noop_enable;       // k_diag / INIT kernel may take the bookkeeping-only path (single GPU, no debug outputs, no shift)
     int32_t shift;             // 1: this (A, B) pair moves the start of the solve to x0 + z (z = extrapolated increment):
                                //    alpha := 1, and k_cg_B finalises like the INIT kernel
     unsigned long long cond;   // cudaGraphConditionalHandle of the enclosing WHILE node (use_cond != 0)

@@ -185,6 +185,13 @@ __device__ __forceinline__ void finalize_A(const HpDev& d, const HpKArgs& a, dou
     s->first = 0;
 }
 
+// true when this sweep repeats the previous one exactly (see HpState.noop_ok): k_diag and the INIT kernel then only redo
+// the bookkeeping (sweep count, statistics entry, WHILE condition) from the values kept in the state
+__device__ __forceinline__ bool sweep_is_noop(const HpDev& d, const HpKArgs& a) {
+    const HpState* s = d.st;
+    return a.noop_enable && !a.shift && !a.rhs_out && s->noop_ok && s->noop_dt == a.dt && s->noop_has_old == a.has_old;
+}
+
 // stage 0: plain PCG (k_cg_B produced z = M^-1 r and r.z).  'mgline': stage 1 after k_cg_B (x, r updated, the
 // line-preconditioned residual measures convergence; the V-cycle only runs if the solve goes on), stage 2 after the
 // last kernel of the V-cycle (z and r.z are final: beta / rz recurrences).
@@ -222,6 +229,9 @@ __device__ __forceinline__ void finalize_B(const HpDev& d, const HpKArgs& a, boo
     else if (s->iter >= a.max_iter) { done = 1; flags |= 2; }
     s->done = done; s->flags = flags;
     s->mg_skip = done;
+    // converged before any iteration, from the un-shifted start: nothing of the sweep's inputs or outputs moved
+    if (init && !a.shift && flags == 1 && s->iter == 0) { s->noop_ok = 1; s->noop_dt = a.dt; s->noop_has_old = a.has_old; }
+    else s->noop_ok = 0;
     stt->crit = (a.criterion == 2) ? sqrt(rr) : crit;
     stt->iters = s->iter;
     stt->flags = flags;
@@ -411,6 +421,10 @@ __global__ void __launch_bounds__(256, 2) k_diag(HpDev d, hp_phys ph, HpKArgs a,
     // rows over CTAs (and over row groups inside a CTA when a row is shorter than the CTA), columns over threads:
     // no integer division per cell, per-row quantities read once
     const int nr = d.nr;
+    if (sweep_is_noop(d, a)) {          // same T, T_old, dt as the sweep before: diag, r and both sums are what they were
+        if (blockIdx.x == 0 && threadIdx.x == 0) finalize_diag(d, a, d.st->res2, d.st->b2);
+        return;
+    }
     const int tpr = 1 << tpr_log2, rpb = blockDim.x >> tpr_log2;
     const int col0 = threadIdx.x & (tpr - 1), rsub = threadIdx.x >> tpr_log2;
     double acc[2] = {0.0, 0.0};
@@ -772,6 +786,12 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT)
     using G = TeamGeom<TPL>;
     const HpState s0 = *d.st;
     if (!INIT && s0.done) return;
+    if constexpr (INIT) {
+        if (sweep_is_noop(d, a)) {      // z, r.z, r.r and the criterion are those of the sweep before: same decision
+            if (blockIdx.x == 0 && threadIdx.x == 0) finalize_B(d, a, true, s0.rz, s0.rr, s0.crit, a.mg ? 1 : 0);
+            return;
+        }
+    }
     __shared__ double s_fA[G::LPC][G::NW], s_fB[G::LPC][G::NW], s_bA[G::LPC][G::NW], s_bB[G::LPC][G::NW];
     const int nr = d.nr, nz = d.nz;
     const int team_in_cta = threadIdx.x / TPL, tl = threadIdx.x % TPL, lane = threadIdx.x & (TeamGeom<TPL>::W - 1);
@@ -932,6 +952,7 @@ __global__ void __launch_bounds__(256) k_delta(HpDev d, hp_phys ph, HpKArgs a) {
     pdl_enter();
     const long long n = (long long)(d.nz + 2) * d.nr;
     const int ord = a.ext_order;
+    if (blockIdx.x == 0 && threadIdx.x == 0) d.st->noop_ok = 0;         // T_old moves
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
         const double Tc = d.T[c];
         double dn = Tc - d.Told[c];
