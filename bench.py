@@ -205,7 +205,7 @@ def run_gpu(args, rank, world, local_rank):
             solver = make_solver_for_rank(mesh, cfg, rank, world, comm=args.comm, tol=args.tol, loop_mode=loop_mode,
                                           extrapolate=int(os.environ.get('HP_EXTRAP', '3')), precond=args.precond,
                                           mg_levels=args.mg_levels, mg_coarse_sweeps=args.mg_sweeps, mg_omega=args.mg_omega,
-                                          refactor_every=args.refactor_every)
+                                          refactor_every=args.refactor_every, reuse_converged=args.reuse_converged)
 
         def barrier():
             stream.synchronize()
@@ -334,7 +334,7 @@ def run_gpu(args, rank, world, local_rank):
                        'parallelism': 'single GPU' if world == 1 else (f'members sharded over {world} ranks, no collective' if ensemble else f'axial slabs x{world}, ' + ('NVLink peer-memory halo rows + CG scalars fused into the PCG kernels, one CUDA graph per step' if args.comm == 'p2p' else 'NCCL send/recv halo + all-gathered CG scalars, host-driven loop')),
                        'l2': 'working set (11 fp64 fields) exceeds the 126 MB L2; no flush needed',
                        'pcg_iterations_per_step': iters / args.steps, 'loop_mode': loop_mode,
-                       'refactor_every_sweeps': args.refactor_every,
+                       'refactor_every_sweeps': args.refactor_every, 'reuse_converged_sweeps': bool(args.reuse_converged),
                        'pcg_start': f"extrapolated from the step history, max order {os.environ.get('HP_EXTRAP', '3')}",
                        'steps_timed': f'time steps {args.warmup + 1}..{args.warmup + args.steps} of the transient from the ambient field '
                                       '(both the device-resident and the end-to-end region)'},
@@ -370,6 +370,8 @@ def main():
     ap.add_argument('--mg-levels', type=int, default=6)
     ap.add_argument('--mg-sweeps', type=int, default=2)
     ap.add_argument('--mg-omega', type=float, default=0.7)
+    ap.add_argument('--reuse-converged', action='store_true',
+                    help='sweeps that exactly repeat a converged sweep only redo the bookkeeping (off: every sweep assembles, like the reference)')
     ap.add_argument('--comm', default='p2p', choices=['p2p', 'nccl'], help='slab exchange: NVLink peer stores fused into the kernels, or NCCL calls')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))

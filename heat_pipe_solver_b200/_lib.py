@@ -34,7 +34,7 @@ class HpMeshDesc(C.Structure):
 class HpSolveOpts(C.Structure):
     _fields_ = [('precond', C.c_int32), ('criterion', C.c_int32), ('tol', C.c_double), ('max_iter', C.c_int32),
                 ('loop_mode', C.c_int32), ('poll_chunk', C.c_int32), ('refactor_every', C.c_int32),
-                ('extrapolate', C.c_int32), ('mg_levels', C.c_int32), ('mg_coarse_sweeps', C.c_int32), ('_pad', C.c_int32),
+                ('extrapolate', C.c_int32), ('mg_levels', C.c_int32), ('mg_coarse_sweeps', C.c_int32), ('reuse_converged', C.c_int32),
                 ('mg_omega', C.c_double)]
 
 

@@ -245,10 +245,9 @@ static HpKArgs make_args(const hp_solver_s* h, double dt, int has_old) {
     static const int pf = [] { const char* e = getenv("HP_PREFETCH"); return e ? atoi(e) : 0; }();
     a.prefetch = pf;
     a.mg = (h->opts.precond == 2) ? 1 : 0; a.init_phase = 0; a.omega = h->opts.mg_omega; a.shift = 0;   // measured slower on B200 (profiles/): off unless asked for
-    // repeated converged sweeps as bookkeeping only (HpState.noop_ok); under slabs the reducing kernels must run on every
-    // rank for the flag protocol, so single GPU only.  HP_NOOP=0 disables (A/B measurements).
-    static const int noop = [] { const char* e = getenv("HP_NOOP"); return (e && e[0] == '0') ? 0 : 1; }();
-    a.noop_enable = (noop && h->nranks == 1) ? 1 : 0;
+    // repeated converged sweeps as bookkeeping only (HpState.noop_ok, opt-in); under slabs the reducing kernels must run
+    // on every rank for the flag protocol, so single GPU only
+    a.noop_enable = (h->opts.reuse_converged && h->nranks == 1) ? 1 : 0;
     return a;
 }
 
@@ -358,7 +357,7 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
     { const char* e = getenv("HP_PDL"); h->pdl = (e && e[0] == '1'); }
     { const char* e = getenv("HP_SWEEP2"); h->c2_on = !(e && e[0] == '0'); }
     h->opts.loop_mode = 1; h->opts.poll_chunk = 8; h->opts.refactor_every = 1; h->opts.extrapolate = 3;
-    h->opts.mg_levels = 6; h->opts.mg_coarse_sweeps = 2; h->opts.mg_omega = 0.7;
+    h->opts.mg_levels = 6; h->opts.mg_coarse_sweeps = 2; h->opts.mg_omega = 0.7; h->opts.reuse_converged = 0;
 
     // initial field + snapshots (main.py:34,133,145,152)
     CK(hpk::launch_fill_rows(d, d.T, h->stream));
@@ -827,7 +826,8 @@ static int sweep_stream(hp_solver_s* h, double dt, int has_old, bool refactor, b
 static bool same_opts(const hp_solve_opts& a, const hp_solve_opts& b) {
     return a.precond == b.precond && a.criterion == b.criterion && a.tol == b.tol && a.max_iter == b.max_iter &&
            a.loop_mode == b.loop_mode && a.refactor_every == b.refactor_every && a.extrapolate == b.extrapolate &&
-           a.mg_levels == b.mg_levels && a.mg_coarse_sweeps == b.mg_coarse_sweeps && a.mg_omega == b.mg_omega;
+           a.mg_levels == b.mg_levels && a.mg_coarse_sweeps == b.mg_coarse_sweeps && a.mg_omega == b.mg_omega &&
+           a.reuse_converged == b.reuse_converged;
 }
 
 static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int update_old, GraphEntry** out) {

@@ -44,7 +44,7 @@ def run(config_file=None, *, t_end=101.0, dt=0.1, sweeps=1, has_old=False, h=5.0
         radiation=False, measure_every=5, measure_times=None, mesh_params=None, T0=None,
         precond='auto', criterion='precond_inf', tol=1e-9, max_iter=5000, loop_mode='graph',
         capture_properties=True, verbose=False, device=None, sweep_tol=None, max_sweeps=50,
-        checkpoint=None, checkpoint_every=None, resume=None, extrapolate=True):
+        checkpoint=None, checkpoint_every=None, resume=None, extrapolate=True, reuse_converged=False):
     """Transient conduction run.  Defaults = the reference's active code path (main.py:119-120,200-202:
     t_end=101 s, dt=0.1 s, one sweep per step with hasOld=False, h=5 W/m2K, temperature-dependent laws).
     The commented "sweep" variant (main.py:267-271) is ``sweeps=5, has_old=True``.
@@ -74,7 +74,7 @@ def run(config_file=None, *, t_end=101.0, dt=0.1, sweeps=1, has_old=False, h=5.0
     solver = ConductionSolver(mesh, dimensions, parameters, constants, h=h, properties=properties, gamma=gamma,
                               source=source, face_k=face_k, radiation=radiation, precond=precond,
                               criterion=criterion, tol=tol, max_iter=max_iter, loop_mode=loop_mode, device=device,
-                              extrapolate=extrapolate)
+                              extrapolate=extrapolate, reuse_converged=reuse_converged)
     try:
         if T0 is not None:
             solver.set_value(T0)

@@ -102,6 +102,7 @@ class ConductionSolver:
                  face_k='masked_at_Tface', radiation=False, axial_break=None, rows=None,
                  precond='auto', criterion='precond_inf', tol=1e-9, max_iter=5000, loop_mode='graph',
                  poll_chunk=8, refactor_every=1, extrapolate=True, mg_levels=6, mg_coarse_sweeps=2, mg_omega=0.7,
+                 reuse_converged=False,
                  device=None, simple=(7200.0, 440.5, 55.0),
                  layout=None, regions=None):
         import torch
@@ -158,13 +159,14 @@ class ConductionSolver:
             precond = 'mgline' if (self.nz >= 256 and self.nz * self.nr >= 262144) else 'rline'
         self.set_options(precond=precond, criterion=criterion, tol=tol, max_iter=max_iter, loop_mode=loop_mode,
                          poll_chunk=poll_chunk, refactor_every=refactor_every, extrapolate=extrapolate,
-                         mg_levels=mg_levels, mg_coarse_sweeps=mg_coarse_sweeps, mg_omega=mg_omega)
+                         mg_levels=mg_levels, mg_coarse_sweeps=mg_coarse_sweeps, mg_omega=mg_omega,
+                         reuse_converged=reuse_converged)
 
     # ------------------------------------------------------------------ options
     def set_options(self, **kw):
         cur = getattr(self, 'options', dict(precond='rline', criterion='precond_inf', tol=1e-9, max_iter=5000,
                                             loop_mode='graph', poll_chunk=8, refactor_every=1, extrapolate=True,
-                                            mg_levels=6, mg_coarse_sweeps=2, mg_omega=0.7))
+                                            mg_levels=6, mg_coarse_sweeps=2, mg_omega=0.7, reuse_converged=False))
         cur = dict(cur)
         for k, v in kw.items():
             if k not in cur:
@@ -179,6 +181,7 @@ class ConductionSolver:
         e = cur['extrapolate']                      # True = highest order (cubic), False = off, 1..3 = maximum order
         o.extrapolate = (3 if e else 0) if isinstance(e, bool) else int(e)
         o.mg_levels, o.mg_coarse_sweeps, o.mg_omega = int(cur['mg_levels']), int(cur['mg_coarse_sweeps']), float(cur['mg_omega'])
+        o.reuse_converged = 1 if cur['reuse_converged'] else 0
         _lib.check(self.lib.hp_set_opts(self._h, C.byref(o)), 'hp_set_opts')
         self.options = cur
 

@@ -79,7 +79,9 @@ typedef struct hp_solve_opts {
                                FiPy's pre-solve residual; only the PCG start changes */
     int32_t mg_levels;      /* mgline: maximum number of levels (>= 2) */
     int32_t mg_coarse_sweeps; /* mgline: extra smoothing sweeps on the coarsest level */
-    int32_t _pad;
+    int32_t reuse_converged;  /* 1: a sweep that exactly repeats a sweep which converged before its first iteration (T, T_old, dt
+                                 untouched since) only redoes the bookkeeping -- same residual / statistics, no assembly.
+                                 Single GPU only.  0 (default): every sweep assembles, like the reference */
     double mg_omega;        /* mgline: damping of the line smoother */
 } hp_solve_opts;
 

@@ -425,3 +425,27 @@ def test_cuda_path_matches_committed_snapshots(cfg, name):
     ref = gold[name + '_res'][-len(res):]
     big = ref > 1e-5
     assert np.allclose(res[big], ref[big], rtol=1e-4)
+
+
+def test_reuse_converged_sweeps_is_exact(cfg):
+    """reuse_converged=True: a sweep that repeats a converged sweep (T, T_old, dt untouched) is bookkeeping only -- the field
+    and every reported residual / iteration count are bit-identical to the run that assembles every sweep; host-side changes
+    of T, T_old or the options end the reuse."""
+    got = {}
+    for reuse in (False, True):
+        s, o = make_pair(cfg, SHAPES['s96x100'], has_old=True, solver_kw=dict(reuse_converged=reuse, extrapolate=False))
+        with s:
+            s.run(0.1, 6, sweeps=6, has_old=True)
+            st = s.stats(36)
+            # bare sweeps after the run, then T_old moved by the host, then the field replaced
+            r1 = s.sweep(0.1, has_old=True)
+            r2 = s.sweep(0.1, has_old=True)
+            s.update_old()
+            r3 = s.sweep(0.1, has_old=True)
+            s.set_value(s.value + 0.25)
+            r4 = s.sweep(0.1, has_old=True)
+            got[reuse] = (s.value.copy(), [(x['residual_l2'], x['iters'], x['crit']) for x in st], (r1, r2, r3, r4))
+    assert np.array_equal(got[True][0], got[False][0])
+    assert got[True][1] == got[False][1]
+    assert got[True][2] == got[False][2]
+    assert any(it == 0 for _, it, _ in got[True][1])          # the case the option is about did occur
