@@ -4,10 +4,10 @@ Python surface mirrors the reference's modules (`params`, `mesh`, `material_prop
 the arithmetic lives in `libhpsolver.so` (hand-written sm_100a CUDA behind the C ABI of
 `include/hp_solver.h`).  Importing this package does not need a GPU; computing does.
 """
-from . import params, mesh, material_properties, regions  # noqa: F401
+from . import params, mesh, material_properties, regions, report  # noqa: F401
 from .mesh import generate_composite_mesh, generate_mesh_2d, StructuredGrid2D  # noqa: F401
 
-__all__ = ['params', 'mesh', 'material_properties', 'regions', 'generate_composite_mesh', 'generate_mesh_2d',
+__all__ = ['params', 'mesh', 'material_properties', 'regions', 'report', 'generate_composite_mesh', 'generate_mesh_2d',
            'StructuredGrid2D', 'ConductionSolver', 'run']
 
 

@@ -177,7 +177,17 @@ if __name__ == '__main__':
     ap.add_argument('--sweeps', type=int, default=1)
     ap.add_argument('--has-old', action='store_true')
     ap.add_argument('--simple', action='store_true')
+    ap.add_argument('--save', default=None, help='write <path>.npz (fields, profiles) and <path>_profiles.csv')
+    ap.add_argument('--experiment', action='append', default=[], metavar='TIME_S=CSV',
+                    help='measured wall temperatures (x,y columns) to compare the snapshot at TIME_S with (main.py:372-405)')
     a = ap.parse_args()
     r = run(a.config, t_end=a.t_end, dt=a.dt, sweeps=a.sweeps, has_old=a.has_old,
             properties='simple' if a.simple else 'temperature_dependent', verbose=True)
     print(f"peak top-wall temperature: {r['profiles'][-1].max() if len(r['profiles']) else float('nan'):.3f} K")
+    if a.save:
+        from . import report
+        print("wrote", report.save_results(r, a.save), report.write_profiles_csv(r, a.save + '_profiles.csv'))
+    if a.experiment:
+        from . import report
+        files = {float(e.split('=', 1)[0]): e.split('=', 1)[1] for e in a.experiment}
+        print(report.format_comparison(report.compare_with_experiment(r, files, time_tolerance=a.dt)))
