@@ -8,7 +8,7 @@ from . import params, mesh, material_properties, regions, report  # noqa: F401
 from .mesh import generate_composite_mesh, generate_mesh_2d, StructuredGrid2D  # noqa: F401
 
 __all__ = ['params', 'mesh', 'material_properties', 'regions', 'report', 'generate_composite_mesh', 'generate_mesh_2d',
-           'StructuredGrid2D', 'ConductionSolver', 'run']
+           'StructuredGrid2D', 'ConductionSolver', 'run', 'run_adaptive']
 
 
 def __getattr__(name):
@@ -18,4 +18,7 @@ def __getattr__(name):
     if name == 'run':
         from .main import run
         return run
+    if name == 'run_adaptive':
+        from .main import run_adaptive
+        return run_adaptive
     raise AttributeError(name)

@@ -168,6 +168,72 @@ def run(config_file=None, *, t_end=101.0, dt=0.1, sweeps=1, has_old=False, h=5.0
         solver.close()
 
 
+
+def run_adaptive(config_file=None, *, t_end=101.0, dt0=0.1, dt_min=1e-3, dt_max=10.0, target_dT=0.5, reject_factor=2.0,
+                 grow=1.5, sweeps=5, h=5.0, measure_times=(), mesh_params=None, T0=None, verbose=False, max_steps=1000000,
+                 **solver_kw):
+    """Implicit Euler with a step-size controller (not in the reference, whose dt is fixed at main.py:37).
+
+    The controller keeps the largest temperature change of a step near ``target_dT`` [K]: a step that moved some cell by
+    more than ``reject_factor * target_dT`` is undone (field restored) and retried with half the dt; after an accepted step
+    the next dt is ``dt * clip(target_dT / max|dT|, 0.5, grow)``, kept inside [dt_min, dt_max] and shortened to land exactly on
+    the next entry of ``measure_times`` and on ``t_end``.  Every step is ``T.updateOld()`` + ``sweeps`` re-sweeps
+    (main.py:267-271) on the GPU; only max|dT| (one device reduction) comes back to the host per step.
+
+    Returns ``T`` (nz, nr), ``t`` and ``dt`` of every accepted step, ``max_dT``, ``n_rejected``, ``times`` / ``profiles``
+    (top-wall profiles at ``measure_times``), ``iterations``, ``elapsed``, ``mesh``.
+    """
+    if not (0.0 < dt_min <= dt0 <= dt_max):
+        raise ValueError("need 0 < dt_min <= dt0 <= dt_max")
+    if not (target_dT > 0.0 and reject_factor > 1.0 and grow > 1.0):
+        raise ValueError("need target_dT > 0, reject_factor > 1, grow > 1")
+    cfg = params_mod.load_config(config_file)
+    parameters, dimensions, constants = dict(cfg['parameters']), dict(cfg['dimensions']), dict(cfg['constants'])
+    mparams = dict(cfg['mesh']) if mesh_params is None else dict(mesh_params)
+    mesh, _ = generate_composite_mesh(mparams, dimensions)
+    stops = sorted(float(m) for m in measure_times if 0.0 < float(m) < t_end) + [float(t_end)]
+    solver = ConductionSolver(mesh, dimensions, parameters, constants, h=h, **solver_kw)
+    try:
+        if T0 is not None:
+            solver.set_value(T0)
+        top_is_wall = solver.regions.cell_band[-1] == BAND_WALL
+        t, dt = 0.0, float(dt0)
+        ts, dts, dTs, times, profiles = [], [], [], [], []
+        rejected = 0
+        start = time.time()
+        nxt = 0
+        while nxt < len(stops) and len(ts) < max_steps:
+            room = stops[nxt] - t
+            step = min(dt, room)
+            if room - step < 0.5 * dt_min:               # do not leave a sliver before the stop
+                step = room
+            before = solver.value_tensor()
+            solver.step(step, sweeps=sweeps, has_old=True)
+            moved = float((solver.value_tensor() - before).abs().max().item())
+            if moved > reject_factor * target_dT and step > dt_min * (1 + 1e-12):
+                solver.set_value(before)                 # undo: the step is repeated from the same field with half the dt
+                dt = max(dt_min, 0.5 * step)
+                rejected += 1
+                continue
+            t = stops[nxt] if step == room else t + step
+            ts.append(t); dts.append(step); dTs.append(moved)
+            if verbose:
+                print(f"t = {t:.4f} s, dt = {step:.4g} s, max|dT| = {moved:.3e} K")
+            if step == room:
+                if nxt < len(stops) - 1 or stops[nxt] in [float(m) for m in measure_times]:
+                    times.append(t)
+                    profiles.append(solver.value_tensor()[:, -1].cpu().numpy() if top_is_wall else np.empty(0))
+                nxt += 1
+            factor = grow if moved <= 0.0 else min(grow, max(0.5, target_dT / moved))
+            dt = min(dt_max, max(dt_min, (dt if step < dt else step) * factor))
+        solver.synchronize()
+        return dict(T=solver.value.reshape(mesh.shape), t=np.array(ts), dt=np.array(dts), max_dT=np.array(dTs),
+                    n_rejected=rejected, times=np.array(times), profiles=np.array(profiles), iterations=solver.total_iters,
+                    sweeps=solver.total_sweeps, elapsed=time.time() - start, mesh=mesh, n_steps=len(ts))
+    finally:
+        solver.close()
+
+
 if __name__ == '__main__':
     import argparse
     ap = argparse.ArgumentParser(description="heat-pipe transient conduction (B200)")

@@ -449,3 +449,32 @@ def test_reuse_converged_sweeps_is_exact(cfg):
     assert got[True][1] == got[False][1]
     assert got[True][2] == got[False][2]
     assert any(it == 0 for _, it, _ in got[True][1])          # the case the option is about did occur
+
+
+@pytest.mark.parametrize('start', ['gentle', 'rejecting'])
+def test_adaptive_dt_driver_matches_oracle_on_its_own_step_sequence(cfg, start):
+    """the step-size controller lands exactly on the requested times, keeps max|dT| per step near the target,
+    undoes rejected steps exactly -- the final field equals the oracle's when the oracle takes the same dt sequence."""
+    from heat_pipe_solver_b200.main import run_adaptive
+    kw = dict(dt0=0.1, target_dT=0.2) if start == 'gentle' else dict(dt0=4.0, target_dT=0.05)
+    r = run_adaptive(t_end=12.0, dt_max=4.0, sweeps=3, measure_times=(5.0,), **kw)
+    assert r['t'][-1] == 12.0 and 5.0 in r['t'] and list(r['times']) == [5.0]
+    assert np.isclose(r['dt'].sum(), 12.0, rtol=0, atol=1e-9)
+    assert np.all(r['dt'] <= 4.0 + 1e-12) and np.all(r['dt'] >= 1e-3 - 1e-15)
+    assert np.all(r['max_dT'] <= 2.0 * kw['target_dT'] + 1e-12)
+    assert r['n_steps'] < 120                                   # fewer steps than the fixed 0.1 s grid
+    if start == 'gentle':
+        assert r['dt'][-1] > r['dt'][0]
+    else:
+        assert r['n_rejected'] >= 1 and r['dt'][0] < 4.0
+    grid = fo.build_grid(dict(cfg['mesh']), cfg['dimensions'])
+    o = fo.Oracle(grid, fo.case_from_config(), has_old=True)
+    at5 = None
+    for t, dt in zip(r['t'], r['dt']):
+        o.update_old()
+        for _ in range(3):
+            o.sweep(float(dt), solver='banded')
+        if t == 5.0:
+            at5 = o.T[:, -1].copy()
+    assert np.max(np.abs(r['T'] - o.T)) <= 3 * len(r['dt']) * PER_STEP_TOL_K
+    assert np.max(np.abs(r['profiles'][0] - at5)) <= 3 * len(r['dt']) * PER_STEP_TOL_K
