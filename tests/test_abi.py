@@ -71,3 +71,33 @@ def test_product_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 text = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in text and 'from oracle' not in text, f
+
+
+def test_struct_field_offsets_match_the_c_compiler(tmp_path):
+    """Every field of every ABI struct sits where a C compiler puts it for include/hp_solver.h (name, offset and size),
+    so the ctypes mirror in _lib.py cannot drift from the header unnoticed."""
+    import shutil
+    import subprocess
+    from heat_pipe_solver_b200 import _lib
+    cc = shutil.which('gcc') or shutil.which('cc')
+    if cc is None:
+        pytest.skip("no C compiler")
+    structs = {'hp_phys': _lib.HpPhys, 'hp_mesh_desc': _lib.HpMeshDesc, 'hp_solve_opts': _lib.HpSolveOpts,
+               'hp_sweep_stat': _lib.HpSweepStat, 'hp_kernel_times': _lib.HpKernelTimes}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "hp_solver.h"', 'int main(void) {']
+    for cname, ct in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu %zu\\n", offsetof({cname}, {fname}), sizeof((({cname}*)0)->{fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.run([cc, '-std=c11', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    got = dict((ln.split()[0], tuple(int(v) for v in ln.split()[1:])) for ln in
+               subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in structs.items():
+        assert got[cname] == (C.sizeof(ct),), cname
+        for fname, ftype in ct._fields_:
+            fld = getattr(ct, fname)
+            assert got[f'{cname}.{fname}'] == (fld.offset, fld.size), f'{cname}.{fname}'
