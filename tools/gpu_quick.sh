@@ -1,12 +1,15 @@
 #!/bin/bash
+# quick validation on one B200: parity tests (subset via $K), one bench line with the per-kernel table, [ensemble line]
 mkdir -p gpurun_out
-echo "== pytest gpu"; timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -8
-echo "== bench"; python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2> gpurun_out/q.err | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); k=d['roofline']['all_kernels']
-print('ms/step %.3f value %.4e e2e %.4e its %.2f' % (d['ms_per_step'], d['value'], d['e2e']['value'], d['config']['pcg_iterations_per_step']))
-print({n:(k[n]['launches'], round(k[n]['avg_ms']*1e3,1)) for n in k})
-print({x:d['roofline'][x] for x in ('kernel','achieved','frac','traffic','share_of_step')})" || tail -5 gpurun_out/q.err
-echo "== ensemble"; python bench.py --workload ensemble:1024 --steps 10 --warmup 3 --precond rline 2> gpurun_out/q2.err | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('ensemble1024: ms/step %.3f value %.4e its %.1f' % (d['ms_per_step'], d['value'], d['config']['pcg_iterations_per_step']))" || tail -5 gpurun_out/q2.err
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu ${K:+-k "$K"} > gpurun_out/q_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/q_tests.log
+timeout 300 python bench.py --steps ${STEPS:-20} --warmup 3 --no-cpu-baseline ${BENCH_ARGS} > gpurun_out/q_bench.json 2> gpurun_out/q_bench.err; echo "bench rc=$?"
+python - <<PY
+import json
+j=json.loads([x for x in open('gpurun_out/q_bench.json') if x.startswith('{')][-1])
+print('ms/step %.3f value %.4e e2e %.4e its/step %.2f launches %d' % (j['ms_per_step'], j['value'], j['e2e']['value'], j['config']['pcg_iterations_per_step'], j['gpu_launches']))
+for k,d in j['roofline']['all_kernels'].items():
+    print(f"  {k:10s} launches={d['launches']:5d} full={d['full_launches']:5d} avg(full)={d['avg_ms']*1e3:8.2f}us total={d['total_ms']:8.3f}ms GB/s={d['GBps']:.0f}")
+PY
+if [ "${ENSEMBLE:-0}" = "1" ]; then
+timeout 300 python bench.py --workload ensemble:1024 --steps 10 --warmup 3 --precond rline --no-cpu-baseline 2> gpurun_out/q2.err | cut -c1-400
+fi
