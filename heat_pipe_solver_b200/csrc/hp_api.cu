@@ -889,8 +889,12 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
         c.last = wn; c.last_is_kernel = false;
         NodeChain body{cp.conditional.phGraph_out[0]};
         Emitter eb{h, &body};
-        if (emit_iteration(eb, a)) return -1;
-        ge.body_nodes = body.count;
+        // HP_UNROLL=U (experiment, default 1): U iterations per pass of the WHILE node -- the evaluation of the node costs
+        // ~18 us, the kernels of iterations past convergence return at once (the protocol of the host-polled chunks)
+        static const int unroll = [] { const char* e = getenv("HP_UNROLL"); int u = e ? atoi(e) : 1; return u < 1 ? 1 : (u > 8 ? 8 : u); }();
+        for (int u = 0; u < unroll; ++u)
+            if (emit_iteration(eb, a)) return -1;
+        ge.body_nodes = body.count / unroll;
     }
     ge.static_nodes = c.count;
     {
