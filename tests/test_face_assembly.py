@@ -122,3 +122,31 @@ def test_structured_oracle_equals_face_list_assembly(shape, state):
     assert np.max(np.abs(S.rhs.ravel() - b) / np.maximum(np.abs(b), 1e-300)) <= 1e-11
     # and the off-diagonal pattern is exactly FiPy's: interior faces only
     assert (A != 0).sum() == (L != 0).sum()
+
+
+@pytest.mark.parametrize('has_old', [False, True])
+def test_sweep_sequence_equals_face_list_solves(has_old):
+    """`res = eq.sweep(var=T, dt=dt)` (main.py:202) and the `T.updateOld()` + re-sweep variant (main.py:267-271): the oracle's
+    sweeps against direct solves of the face-list system -- pre-solve residual and field, step after step."""
+    import scipy.sparse.linalg as spla
+    cfg = params.load_config()
+    mparams = dict(cfg['mesh'])
+    mparams.update(nx_wall=40, nx_wick=40, nx_vc=40)
+    mesh, _ = generate_composite_mesh(dict(mparams), cfg['dimensions'])
+    grid = fo.build_grid(dict(mparams), cfg['dimensions'])
+    o = fo.Oracle(grid, fo.case_from_config(), has_old=has_old)
+    T = np.full(mesh.numberOfCells, cfg['parameters']['T_amb'])
+    T_old = T.copy()
+    dt = 2.0
+    for step in range(3):
+        if has_old:
+            o.update_old()
+            T_old = T.copy()
+        for _ in range(2 if has_old else 1):
+            L, b = face_list_system(mesh, cfg, T, T_old if has_old else T, dt)
+            res = np.linalg.norm(L @ T - b)
+            T = spla.spsolve(L.tocsc(), b)
+            res_o = o.sweep(dt, solver='banded')
+            assert abs(res - res_o) <= 1e-9 * max(res_o, 1e-30) + 1e-12
+            assert np.max(np.abs(T - o.T.ravel())) <= 1e-9
+    assert T.max() > cfg['parameters']['T_amb'] + 0.5            # the evaporator did heat the wall
