@@ -295,29 +295,53 @@ def run_gpu(args, rank, world, local_rank):
                                         'GBps': (BYTES_PER_CELL.get(k, 0) * n_cells / (fm / fc * 1e-3) / 1e9 if fc else None)}
                                     for k, (c, m, fc, fm) in kt.items() if c}}
         solver.close()
-        # strong-scaling reference: the same 16384x4096 workload on ONE GPU (rank 0, after the slab handles are gone)
-        strong = None
-        if world > 1 and not ensemble:
-            barrier()
-            if rank == 0 and not args.no_single_gpu_ref:
-                one = make_solver_for_rank(mesh, cfg, 0, 1, tol=args.tol, loop_mode=args.loop_mode, precond=args.precond,
-                                           refactor_every=args.refactor_every,
-                                           mg_levels=args.mg_levels, mg_coarse_sweeps=args.mg_sweeps, mg_omega=args.mg_omega)
-                one.run(DT, 3, sweeps=SWEEPS, has_old=HAS_OLD)
+        # strong-scaling reference: the same 16384x4096 workload on ONE GPU (rank 0, after the slab handles are gone), over
+        # the SAME time steps (the cost of a step falls along the transient, so the step indices must match)
+        def single_gpu_run(big_mesh):
+            one = make_solver_for_rank(big_mesh, cfg, 0, 1, tol=args.tol, loop_mode=args.loop_mode, precond=args.precond,
+                                       extrapolate=int(os.environ.get('HP_EXTRAP', '3')), refactor_every=args.refactor_every,
+                                       mg_levels=args.mg_levels, mg_coarse_sweeps=args.mg_sweeps, mg_omega=args.mg_omega,
+                                       reuse_converged=args.reuse_converged)
+            try:
+                one.run(DT, args.warmup, sweeps=SWEEPS, has_old=HAS_OLD)
                 stream.synchronize()
                 s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 it1 = one.total_iters
                 s0.record(stream)
-                one.run(DT, 3, sweeps=SWEEPS, has_old=HAS_OLD)
+                one.run(DT, args.steps, sweeps=SWEEPS, has_old=HAS_OLD)
                 s1.record(stream)
                 stream.synchronize()
-                ms1 = s0.elapsed_time(s1) / 3
-                strong = {'single_gpu_ms_per_step': ms1, 'single_gpu_value': n_cells / (ms1 * 1e-3),
-                          'single_gpu_pcg_iterations_per_step': (one.total_iters - it1) / 3,
-                          'speedup_vs_single_gpu': ms1 / (ms / args.steps),
-                          'note': 'same 16384x4096 workload on one B200, 3 timed steps after 3 warm-up steps, measured in this run'}
+                return s0.elapsed_time(s1) / args.steps, (one.total_iters - it1) / args.steps
+            finally:
                 one.close()
+
+        strong = None
+        if world > 1 and not ensemble:
             barrier()
+            if rank == 0 and not args.no_single_gpu_ref:
+                try:
+                    ms1, its1 = single_gpu_run(mesh)
+                    strong = {'single_gpu_ms_per_step': ms1, 'single_gpu_value': n_cells / (ms1 * 1e-3),
+                              'single_gpu_pcg_iterations_per_step': its1,
+                              'speedup_vs_single_gpu': ms1 / (ms / args.steps),
+                              'note': f'same {nz}x{nr} workload on one B200 over the same time steps ({args.warmup} warm-up + '
+                                      f'{args.steps} timed), measured in this run'}
+                except Exception as exc:      # the other ranks wait at the barrier below: never leave them there
+                    strong = {'error': repr(exc)[:300]}
+            barrier()
+        # N = 1: the line of the 4096x1024 workload also carries the one-GPU number of the multi-GPU workload, so that the
+        # N > 1 lines (16384x4096, strong scaling) have their denominator in the same series of runs
+        scaling_ref = None
+        if world == 1 and not ensemble and args.workload is None and not args.no_single_gpu_ref:
+            try:
+                bnz, bnr = 16384, 4096
+                big, _ = generate_composite_mesh(mesh_params_for(bnz, bnr), cfg['dimensions'])
+                ms1, its1 = single_gpu_run(big)
+                scaling_ref = {'workload': f'synthetic composite mesh {bnz}x{bnr}, same physics / sweeps / solver, one B200',
+                               'ms_per_step': ms1, 'value': bnz * bnr / (ms1 * 1e-3), 'unit': 'cell-timesteps/s',
+                               'pcg_iterations_per_step': its1, 'steps': args.steps, 'warmup': args.warmup}
+            except Exception as exc:          # never let the extra measurement cost the headline line
+                scaling_ref = {'error': repr(exc)[:300]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not ensemble:
@@ -344,6 +368,7 @@ def run_gpu(args, rank, world, local_rank):
             'e2e': {'value': e2e_value, 'unit': 'cell-timesteps/s', 'h2d_bytes_per_step': 8 * n_cells,
                     'd2h_bytes_per_step': 8 * n_cells, 'ms_per_step': e2e_ms / args.steps},
             'gpu_launches': int(launches), 'clocks': clk, 'strong_scaling': strong if world > 1 else None,
+            'multi_gpu_workload_on_one_gpu': scaling_ref,
             'roofline': roof, 'cpu_baseline': cpu,
             'last_sweep_stats': stats[-SWEEPS:],
         }
@@ -363,7 +388,7 @@ def main():
     ap.add_argument('--tol', type=float, default=1e-9)
     ap.add_argument('--loop-mode', default='graph', choices=['graph', 'host'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-single-gpu-ref', action='store_true', help='N>1: skip the one-GPU run of the same workload')
+    ap.add_argument('--no-single-gpu-ref', action='store_true', help='skip the one-GPU run of the 16384x4096 multi-GPU workload (N>1: strong-scaling denominator; N=1: extra key)')
     ap.add_argument('--precond', default='mgline', choices=['rline', 'mgline', 'jacobi'],
                     help='PCG preconditioner: mgline (V-cycle over radial-line smoothing, default), rline (the radial-line '
                          'tridiagonal preconditioner alone), jacobi')

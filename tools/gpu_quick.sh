@@ -2,7 +2,7 @@
 # quick validation on one B200: parity tests (subset via $K), one bench line with the per-kernel table, [ensemble line]
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu ${K:+-k "$K"} > gpurun_out/q_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/q_tests.log
-timeout 300 python bench.py --steps ${STEPS:-20} --warmup 3 --no-cpu-baseline ${BENCH_ARGS} > gpurun_out/q_bench.json 2> gpurun_out/q_bench.err; echo "bench rc=$?"
+timeout 300 python bench.py --steps ${STEPS:-20} --warmup 3 --no-cpu-baseline --no-single-gpu-ref ${BENCH_ARGS} > gpurun_out/q_bench.json 2> gpurun_out/q_bench.err; echo "bench rc=$?"
 python - <<PY
 import json
 j=json.loads([x for x in open('gpurun_out/q_bench.json') if x.startswith('{')][-1])

@@ -12,16 +12,16 @@ echo "== bench reference arm"; timeout 900 python bench.py --impl reference --st
 fi
 if [ "${NCU:-list}" = "list" ]; then
 echo "== ncu launch list (stream-launch mode so that every kernel is a separate launch)"
-timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --loop-mode host > gpurun_out/plain.log 2>&1 && \
+timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-single-gpu-ref --loop-mode host > gpurun_out/plain.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches.csv \
-   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --loop-mode host > gpurun_out/ncu1.log 2>&1
+   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-single-gpu-ref --loop-mode host > gpurun_out/ncu1.log 2>&1
 echo rc=$?
 fi
 # one profiler pass per gpurun call: NCU=full (alone, with TESTS=0) after the plain run of the same command passed
 if [ "${NCU:-list}" = "full" ]; then
 echo "== ncu full"
-timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --loop-mode host > gpurun_out/plain.log 2>&1 && \
+timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-single-gpu-ref --loop-mode host > gpurun_out/plain.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_cg_A|k_cg_B|k_mg_res|k_mg_line|k_mg_fused' -s 500 -c 40 -f -o gpurun_out/prof_cg \
-   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --loop-mode host > gpurun_out/ncu2.log 2>&1
+   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-single-gpu-ref --loop-mode host > gpurun_out/ncu2.log 2>&1
 echo rc=$?
 fi

@@ -34,7 +34,7 @@ for r in data:
     c[1] += v
 tot = sum(v[1] for v in agg.values())
 with open(os.path.join(P, f'{tag}_launches_summary.txt'), 'w') as f:
-    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --loop-mode host` (default preconditioner)\n")
+    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-single-gpu-ref --loop-mode host` (default preconditioner)\n")
     f.write("# (cold-cache, serialised launches: compare SHARES, not absolutes)\n")
     f.write(f"{'kernel':58s} {'launches':>8s} {'total ms':>10s} {'avg us':>9s} {'share':>7s}\n")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
