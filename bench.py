@@ -329,10 +329,10 @@ def run_gpu(args, rank, world, local_rank):
                 except Exception as exc:      # the other ranks wait at the barrier below: never leave them there
                     strong = {'error': repr(exc)[:300]}
             barrier()
-        # N = 1: the line of the 4096x1024 workload also carries the one-GPU number of the multi-GPU workload, so that the
-        # N > 1 lines (16384x4096, strong scaling) have their denominator in the same series of runs
+        # N = 1 with --scaling-ref: the line of the 4096x1024 workload also carries the one-GPU number of the multi-GPU
+        # workload (the N > 1 lines measure that denominator themselves: `strong_scaling`)
         scaling_ref = None
-        if world == 1 and not ensemble and args.workload is None and not args.no_single_gpu_ref:
+        if world == 1 and not ensemble and args.workload is None and args.scaling_ref:
             try:
                 bnz, bnr = 16384, 4096
                 big, _ = generate_composite_mesh(mesh_params_for(bnz, bnr), cfg['dimensions'])
@@ -388,7 +388,9 @@ def main():
     ap.add_argument('--tol', type=float, default=1e-9)
     ap.add_argument('--loop-mode', default='graph', choices=['graph', 'host'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-single-gpu-ref', action='store_true', help='skip the one-GPU run of the 16384x4096 multi-GPU workload (N>1: strong-scaling denominator; N=1: extra key)')
+    ap.add_argument('--scaling-ref', action='store_true',
+                    help='N=1: also time the 16384x4096 multi-GPU workload on this one GPU (extra key multi_gpu_workload_on_one_gpu)')
+    ap.add_argument('--no-single-gpu-ref', action='store_true', help='N>1: skip the one-GPU run of the same workload (strong-scaling denominator)')
     ap.add_argument('--precond', default='mgline', choices=['rline', 'mgline', 'jacobi'],
                     help='PCG preconditioner: mgline (V-cycle over radial-line smoothing, default), rline (the radial-line '
                          'tridiagonal preconditioner alone), jacobi')
