@@ -27,13 +27,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # stdout must carry exactly ONE JSON line, but libraries chat on it (NCCL prints its version banner there at
 # NCCL_DEBUG=VERSION/WARN): keep a private copy of the real stdout for the result and point fd 1 at stderr meanwhile
-_REAL_STDOUT = os.fdopen(os.dup(1), 'w')
-os.dup2(2, 1)
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """Called once by main(): fd 1 -> stderr for everything but the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
 
 
 def emit_line(obj):
-    _REAL_STDOUT.write(json.dumps(obj) + '\n')
-    _REAL_STDOUT.flush()
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + '\n')
+    out.flush()
 
 
 RADIAL_SPLIT = {1024: (128, 256, 640), 4096: (512, 1024, 2560), 512: (64, 128, 320), 256: (32, 64, 160), 128: (16, 32, 80)}
@@ -54,6 +62,23 @@ def parse_workload(s):
 def mesh_params_for(nz, nr):
     a, b, c = RADIAL_SPLIT[nr]
     return dict(nx_wall=nz, nr_wall=c, nx_wick=nz, nr_wick=b, nx_vc=nz, nr_vc=a)
+
+
+def workload_config(kind, nz, nr, world, members=0, sample=None):
+    """`config` of the JSON line: built from the workload alone, so the B200 arm and the reference arm print the SAME dict
+    when they run the same workload (run-specific facts -- iterations, loop mode, solver options -- go under `run`)."""
+    if kind == 'ensemble':
+        w = (f'ensemble of {members} independent Faghri pipes (native {nz}x{nr} mesh each), T-dependent properties, literal mode, '
+             f'dt={DT}s, updateOld + {SWEEPS} sweeps/step, member m: q~U(0.5,1.5)*26770 W/m2, h~U(2,20), T_amb~U(280,300) K, rng(1234)')
+    else:
+        w = (f'synthetic composite mesh {nz}x{nr} (axial x radial), T-dependent properties, literal mode, dt={DT}s, '
+             f'updateOld + {SWEEPS} sweeps/step, linear solves to 1e-9 K')
+    if sample:
+        w += f'; {sample}'
+    return {'workload': w,
+            'l2': 'working set (>= 11 fp64 fields) exceeds the 126 MB L2; no flush needed' if kind != 'ensemble' or members * nz * nr * 88 > 126e6
+                  else 'working set fits the L2 (latency-bound workload)',
+            'time_steps': 'steps W+1..W+K of the transient from the ambient field'}
 
 
 class ClockSampler:
@@ -114,43 +139,111 @@ def measured_peak():
 # ------------------------------------------------------------------------------------------------------------
 # oracle timing (cpu_baseline leg and --impl reference)
 # ------------------------------------------------------------------------------------------------------------
-def oracle_steps(nz, nr, n_steps, warmup=0, precond='mgline'):
-    """Time n_steps implicit-Euler steps (updateOld + 5 sweeps, the same PCG + preconditioner + tolerance as the GPU arm)
-    of the oracle."""
+def oracle_steps(nz, nr, n_steps, warmup=0, precond='mgline', solver=None):
+    """Time n_steps implicit-Euler steps (updateOld + 5 sweeps) of the oracle: by default the same PCG + preconditioner +
+    tolerance as the GPU arm; solver='splu' = SuperLU direct solve per sweep (closest to FiPy's scipy LinearLUSolver)."""
     from oracle import fv_oracle as fo
     cfg = fo.load_config()
     grid = fo.build_grid(mesh_params_for(nz, nr), cfg['dimensions'])
     o = fo.Oracle(grid, fo.case_from_config(), has_old=HAS_OLD)
-    solver = 'banded' if nr <= 64 else ('pcg_mgline' if precond == 'mgline' else 'pcg_rline')
+    if solver is None:
+        solver = 'banded' if nr <= 64 else ('pcg_mgline' if precond == 'mgline' else 'pcg_rline')
+    its = []
 
     def one():
         o.update_old()
         for _ in range(SWEEPS):
-            o.sweep(DT, solver=solver, tol=1e-9, criterion='precond_inf') if solver != 'banded' else o.sweep(DT, solver=solver)
+            if solver.startswith('pcg'):
+                o.sweep(DT, solver=solver, tol=1e-9, criterion='precond_inf')
+                its.append(o.last_solver_info.get('iterations', 0))
+            else:
+                o.sweep(DT, solver=solver)
+    for _ in range(warmup):
+        one()
+    its.clear()
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        one()
+    dt = time.perf_counter() - t0
+    return grid.n_cells * n_steps / dt, dt, (sum(its) / max(n_steps, 1) if its else None)
+
+
+def oracle_ensemble_steps(members, n_steps, warmup=0):
+    """The oracle on `members` independent native-mesh pipes (banded direct solves), one after the other."""
+    import numpy as np
+    from oracle import fv_oracle as fo
+    cfg = fo.load_config()
+    grid = fo.build_grid(dict(cfg['mesh']), cfg['dimensions'])
+    rng = np.random.default_rng(1234)
+    q = cfg['parameters']['Q_input_flux'] * rng.uniform(0.5, 1.5, 1024)
+    hh = rng.uniform(2.0, 20.0, 1024)
+    Ta = rng.uniform(280.0, 300.0, 1024)
+    orcs = []
+    for m in range(members):
+        case = fo.case_from_config(h=float(hh[m]))
+        case.parameters['Q_input_flux'] = float(q[m])
+        case.parameters['T_amb'] = float(Ta[m])
+        orcs.append(fo.Oracle(grid, case, has_old=HAS_OLD))
+
+    def one():
+        for o in orcs:
+            o.update_old()
+            for _ in range(SWEEPS):
+                o.sweep(DT, solver='banded')
     for _ in range(warmup):
         one()
     t0 = time.perf_counter()
     for _ in range(n_steps):
         one()
     dt = time.perf_counter() - t0
-    return grid.n_cells * n_steps / dt, dt
+    return members * grid.n_cells * n_steps / dt, dt
+
+
+REF_SAMPLE = (4096, 1024)      # largest mesh of the workload's recipe the oracle steps through in ~10 s per step
 
 
 def run_reference(args, rank, world):
+    """The reference's CPU path on this box's host cores.  FiPy is not installable, so this is the oracle port.
+    N = 1: the SAME workload as the B200 arm (4096x1024, same steps / warm-up).  N > 1: the 16384x4096 workload does not fit
+    the time box on a CPU (>= 5 min per step), so each step is a 4096x1024 sample of it -- named in config.workload."""
     if rank != 0:
         return
-    nz, nr = parse_workload(args.workload or ('4096x1024' if world == 1 else '16384x4096'))
-    snz, snr = 1024, 256      # bounded sample: same mesh recipe and physics, 1/16 (or 1/256) of the cells per step
-    value, secs = oracle_steps(snz, snr, args.steps, args.warmup, args.precond)
-    sample = (f"{args.steps} steps (after {args.warmup} warm-up) of the oracle on a synthetic composite mesh {snz}x{snr} "
-              f"(same recipe as {nz}x{nr}, T-dependent, updateOld + {SWEEPS} sweeps, PCG/{args.precond} tol 1e-9 K); FiPy itself is not installable")
+    ensemble = (args.workload or '').startswith('ensemble')
+    if ensemble:
+        M = int(args.workload.split(':')[1]) if ':' in args.workload else 1024
+        sm = min(M, 8)
+        value, secs = oracle_ensemble_steps(sm, args.steps, args.warmup)
+        from oracle import fv_oracle as fo
+        mcfg = fo.load_config()['mesh']
+        nz, nr = int(mcfg['nx_wall']), int(mcfg['nr_vc'] + mcfg['nr_wick'] + mcfg['nr_wall'])
+        config = workload_config('ensemble', nz, nr, world, members=M,
+                                 sample=None if sm == M else f'reference arm: {sm} of the {M} members per step (members are independent: per-cell rate)')
+        sample = f'{args.steps} steps (after {args.warmup} warm-up) of the oracle (banded direct solves) on {sm} members, one after the other'
+        its, splu = None, None
+    else:
+        nz, nr = parse_workload(args.workload or ('4096x1024' if world == 1 else '16384x4096'))
+        snz, snr = (nz, nr) if nz * nr <= REF_SAMPLE[0] * REF_SAMPLE[1] else REF_SAMPLE
+        value, secs, its = oracle_steps(snz, snr, args.steps, args.warmup, args.precond)
+        config = workload_config('mesh', nz, nr, world,
+                                 sample=None if (snz, snr) == (nz, nr) else
+                                 f'reference arm: each step is a {snz}x{snr} sample of it (same recipe and physics, 1/{nz * nr // (snz * snr)} of the cells)')
+        sample = (f'{args.steps} steps (after {args.warmup} warm-up) of the numpy/scipy oracle (FiPy restatement) on the {snz}x{snr} synthetic '
+                  f'composite mesh, PCG/{args.precond} to 1e-9 K like the B200 arm; FiPy itself is not installable')
+        # SuperLU direct solve per sweep = FiPy's scipy LinearLUSolver (BASELINE.md section 3): one step on a 1024x256 mesh
+        # of the same recipe (a factorisation at 4096x1024 takes minutes)
+        splu = None
+        if not args.no_splu:
+            v2, s2, _ = oracle_steps(1024, 256, 1, 0, args.precond, solver='splu')
+            splu = {'value': v2, 'unit': 'cell-timesteps/s', 'cores': 1, 'kind': 'port',
+                    'sample': f'1 step (5 SuperLU factorisations + solves) on a 1024x256 mesh of the same recipe, {s2:.1f} s'}
     line = {
         'impl': 'reference', 'metric': 'cell-timesteps/s (incl. sweeps)', 'value': value, 'unit': 'cell-timesteps/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * secs / max(args.steps, 1),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f'synthetic composite mesh {nz}x{nr} (axial x radial), T-dependent properties, dt={DT}s, '
-                               f'updateOld + {SWEEPS} sweeps/step', 'sample_mesh': f'{snz}x{snr}'},
+        'config': config,
+        'run': {'pcg_iterations_per_step': its, 'host_cores': os.cpu_count(), 'threads_used': 1},
         'cpu_baseline': {'value': value, 'unit': 'cell-timesteps/s', 'cores': 1, 'kind': 'port', 'sample': sample},
+        'cpu_baseline_splu': splu,
         'e2e': {'value': value, 'unit': 'cell-timesteps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -265,7 +358,7 @@ def run_gpu(args, rank, world, local_rank):
 
         # ---- per-kernel CUDA-event times (stream-launch mode, same workload continuing) ----------------------
         roof = None
-        if world == 1 and not ensemble:
+        if world == 1:
             solver.profile_begin(16384)
             solver.run(DT, max(1, min(3, args.steps)), sweeps=SWEEPS, has_old=HAS_OLD)
             kt = solver.profile_end()
@@ -294,6 +387,13 @@ def run_gpu(args, rank, world, local_rank):
                     'all_kernels': {k: {'launches': c, 'total_ms': m, 'full_launches': fc, 'avg_ms': (fm / fc if fc else None),
                                         'GBps': (BYTES_PER_CELL.get(k, 0) * n_cells / (fm / fc * 1e-3) / 1e9 if fc else None)}
                                     for k, (c, m, fc, fm) in kt.items() if c}}
+        slab_field = None
+        if world > 1 and not ensemble and not args.no_single_gpu_ref:
+            # field after the end-to-end region = W + K steps from the ambient field, the state the one-GPU run ends in
+            from heat_pipe_solver_b200.distributed import gather_field
+            full = gather_field(solver.value_tensor())
+            slab_field = full if rank == 0 else None
+            del full
         solver.close()
         # strong-scaling reference: the same 16384x4096 workload on ONE GPU (rank 0, after the slab handles are gone), over
         # the SAME time steps (the cost of a step falls along the transient, so the step indices must match)
@@ -311,7 +411,10 @@ def run_gpu(args, rank, world, local_rank):
                 one.run(DT, args.steps, sweeps=SWEEPS, has_old=HAS_OLD)
                 s1.record(stream)
                 stream.synchronize()
-                return s0.elapsed_time(s1) / args.steps, (one.total_iters - it1) / args.steps
+                diff = None
+                if slab_field is not None and tuple(slab_field.shape) == (one.nz, one.nr):
+                    diff = float((one.value_tensor() - slab_field).abs().max().item())
+                return s0.elapsed_time(s1) / args.steps, (one.total_iters - it1) / args.steps, diff
             finally:
                 one.close()
 
@@ -320,8 +423,9 @@ def run_gpu(args, rank, world, local_rank):
             barrier()
             if rank == 0 and not args.no_single_gpu_ref:
                 try:
-                    ms1, its1 = single_gpu_run(mesh)
+                    ms1, its1, fdiff = single_gpu_run(mesh)
                     strong = {'single_gpu_ms_per_step': ms1, 'single_gpu_value': n_cells / (ms1 * 1e-3),
+                              'max_abs_T_slabs_minus_single_gpu_K': fdiff,
                               'single_gpu_pcg_iterations_per_step': its1,
                               'speedup_vs_single_gpu': ms1 / (ms / args.steps),
                               'note': f'same {nz}x{nr} workload on one B200 over the same time steps ({args.warmup} warm-up + '
@@ -336,7 +440,7 @@ def run_gpu(args, rank, world, local_rank):
             try:
                 bnz, bnr = 16384, 4096
                 big, _ = generate_composite_mesh(mesh_params_for(bnz, bnr), cfg['dimensions'])
-                ms1, its1 = single_gpu_run(big)
+                ms1, its1, _ = single_gpu_run(big)
                 scaling_ref = {'workload': f'synthetic composite mesh {bnz}x{bnr}, same physics / sweeps / solver, one B200',
                                'ms_per_step': ms1, 'value': bnz * bnr / (ms1 * 1e-3), 'unit': 'cell-timesteps/s',
                                'pcg_iterations_per_step': its1, 'steps': args.steps, 'warmup': args.warmup}
@@ -344,27 +448,33 @@ def run_gpu(args, rank, world, local_rank):
                 scaling_ref = {'error': repr(exc)[:300]}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and not ensemble:
-        snz, snr = 2048, 512
-        n_cpu = 5
-        v, secs = oracle_steps(snz, snr, n_cpu, 0, args.precond)
-        cpu = {'value': v, 'unit': 'cell-timesteps/s', 'cores': 1, 'kind': 'port',
-               'sample': f'{n_cpu} steps of the numpy/scipy oracle (FiPy restatement, PCG/{args.precond} tol 1e-9 K) on a {snz}x{snr} synthetic '
-                         f'composite mesh, same physics and sweeps ({secs:.1f} s); host has {os.cpu_count()} cores, the port uses 1'}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if ensemble:
+            sm, n_cpu = 8, 4
+            v, secs = oracle_ensemble_steps(sm, n_cpu, 0)
+            cpu = {'value': v, 'unit': 'cell-timesteps/s', 'cores': 1, 'kind': 'port',
+                   'sample': f'{n_cpu} steps of the numpy/scipy oracle (banded direct solves) on {sm} of the members, one after the other '
+                             f'({secs:.1f} s; members are independent, so the per-cell rate carries over); host has {os.cpu_count()} cores, the port uses 1'}
+        else:
+            snz, snr = 2048, 512
+            n_cpu = 5
+            v, secs, its_cpu = oracle_steps(snz, snr, n_cpu, 0, args.precond)
+            cpu = {'value': v, 'unit': 'cell-timesteps/s', 'cores': 1, 'kind': 'port',
+                   'sample': f'{n_cpu} steps of the numpy/scipy oracle (FiPy restatement, PCG/{args.precond} tol 1e-9 K, {its_cpu:.1f} it/step) on a {snz}x{snr} synthetic '
+                             f'composite mesh, same physics and sweeps ({secs:.1f} s); host has {os.cpu_count()} cores, the port uses 1; the full-size run is `--impl reference`'}
     if rank == 0:
         line = {
             'metric': 'cell-timesteps/s (incl. sweeps)', 'value': value, 'unit': 'cell-timesteps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak' if (world == 1 or ensemble) else 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': (f'ensemble of {args.workload.split(":")[1] if ":" in args.workload else 1024} independent Faghri pipes (500x9 each, stacked), ' if ensemble else f'synthetic composite mesh {nz}x{nr} (axial x radial), ') +
-                                   f'T-dependent properties, literal mode, dt={DT}s, updateOld + {SWEEPS} sweeps/step, PCG ({args.precond}) tol {args.tol:g} K',
-                       'parallelism': 'single GPU' if world == 1 else (f'members sharded over {world} ranks, no collective' if ensemble else f'axial slabs x{world}, ' + ('NVLink peer-memory halo rows + CG scalars fused into the PCG kernels, one CUDA graph per step' if args.comm == 'p2p' else 'NCCL send/recv halo + all-gathered CG scalars, host-driven loop')),
-                       'l2': 'working set (11 fp64 fields) exceeds the 126 MB L2; no flush needed',
-                       'pcg_iterations_per_step': iters / args.steps, 'loop_mode': loop_mode,
-                       'refactor_every_sweeps': args.refactor_every, 'reuse_converged_sweeps': bool(args.reuse_converged),
-                       'pcg_start': f"extrapolated from the step history, max order {os.environ.get('HP_EXTRAP', '3')}",
-                       'steps_timed': f'time steps {args.warmup + 1}..{args.warmup + args.steps} of the transient from the ambient field '
-                                      '(both the device-resident and the end-to-end region)'},
+            'config': workload_config('ensemble' if ensemble else 'mesh', nz, nr, world,
+                                      members=(int(args.workload.split(':')[1]) if ensemble and ':' in args.workload else 1024)),
+            'run': {'parallelism': 'single GPU' if world == 1 else (f'members sharded over {world} ranks, no collective' if ensemble else f'axial slabs x{world}, ' + ('NVLink peer-memory halo rows + CG scalars fused into the kernels, one CUDA graph per step' if args.comm == 'p2p' else 'NCCL send/recv halo + all-gathered CG scalars, host-driven loop')),
+                    'solver': f'PCG ({args.precond}) tol {args.tol:g} K', 'pcg_iterations_per_step': iters / args.steps, 'loop_mode': loop_mode,
+                    'refactor_every_sweeps': args.refactor_every, 'reuse_converged_sweeps': bool(args.reuse_converged),
+                    'pcg_start': f"extrapolated from the step history, max order {os.environ.get('HP_EXTRAP', '3')}",
+                    'e2e_note': 'hp_run_host uploads the field every step but keeps the solver-side step history (T_old, increments) for the '
+                                'predicted PCG start; a caller uploading an unrelated field pays first-step iteration counts'},
             'e2e': {'value': e2e_value, 'unit': 'cell-timesteps/s', 'h2d_bytes_per_step': 8 * n_cells,
                     'd2h_bytes_per_step': 8 * n_cells, 'ms_per_step': e2e_ms / args.steps},
             'gpu_launches': int(launches), 'clocks': clk, 'strong_scaling': strong if world > 1 else None,
@@ -388,6 +498,7 @@ def main():
     ap.add_argument('--tol', type=float, default=1e-9)
     ap.add_argument('--loop-mode', default='graph', choices=['graph', 'host'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-splu', action='store_true', help='--impl reference: skip the SuperLU variant (cpu_baseline_splu)')
     ap.add_argument('--scaling-ref', action='store_true',
                     help='N=1: also time the 16384x4096 multi-GPU workload on this one GPU (extra key multi_gpu_workload_on_one_gpu)')
     ap.add_argument('--no-single-gpu-ref', action='store_true', help='N>1: skip the one-GPU run of the same workload (strong-scaling denominator)')
@@ -404,6 +515,7 @@ def main():
                     help='sweeps that exactly repeat a converged sweep only redo the bookkeeping (off: every sweep assembles, like the reference)')
     ap.add_argument('--comm', default='p2p', choices=['p2p', 'nccl'], help='slab exchange: NVLink peer stores fused into the kernels, or NCCL calls')
     args = ap.parse_args()
+    guard_stdout()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))

@@ -39,6 +39,41 @@ import scipy.sparse.linalg as spla
 
 from . import properties as P
 
+# Optional row-block threading of the heavy array passes (numpy / LAPACK release the GIL on large blocks): the reference
+# arm of bench.py uses the host's cores with it.  Results are bit-identical to the serial path -- every block computes
+# exactly the entries the serial expression computes.
+_POOL = None
+_NTHREADS = 1
+
+
+def set_threads(n):
+    """Row-block threads for matvec / line solves / property evaluation (1 = serial)."""
+    global _POOL, _NTHREADS
+    from concurrent.futures import ThreadPoolExecutor
+    n = max(1, int(n))
+    if _POOL is not None:
+        _POOL.shutdown()
+        _POOL = None
+    _NTHREADS = n
+    if n > 1:
+        _POOL = ThreadPoolExecutor(max_workers=n)
+
+
+def _row_blocks(nz, min_rows=64):
+    nb = min(_NTHREADS, max(1, nz // min_rows))
+    edges = [nz * k // nb for k in range(nb + 1)]
+    return [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+
+
+def _par_rows(fn, nz, min_rows=64):
+    """fn(a, b) on row blocks [a, b) covering [0, nz), threaded when set_threads(n > 1)."""
+    blocks = _row_blocks(nz, min_rows)
+    if _POOL is None or len(blocks) == 1:
+        for a, b in blocks:
+            fn(a, b)
+        return
+    list(_POOL.map(lambda ab: fn(*ab), blocks))
+
 # z-flag bits (cells / radial faces use z_c[j]; axial faces use z_v[j+1])
 ZF_VC_EVAPCOND = 1   # z < L_e  or  z > L_e+L_a                 main.py:65,87
 ZF_VC_ADIAB = 2      # L_e < z < L_e+L_a                         main.py:66,88
@@ -278,6 +313,31 @@ def face_conductivities(case: Case, grid: Grid, masks: Masks, T):
     return k_r, k_z, k_out
 
 
+def _properties(case: Case, grid: Grid, masks: Masks, T):
+    """(k_r, k_z, k_out, rho, cp) at T; evaluated per row block on the thread pool when set_threads(n > 1) (each block is
+    the same expression on a sub-grid of whole rows, so the values are those of the serial evaluation)."""
+    if _POOL is None:
+        k_r, k_z, k_out = face_conductivities(case, grid, masks, T)
+        rho, cp = rho_cp_cells(case, masks, T)
+        return k_r, k_z, k_out, rho, cp
+    nz, nr = T.shape
+    k_r, k_z, k_out = np.empty((nz, nr - 1)), np.empty((nz - 1, nr)), np.empty(nz)
+    rho, cp = np.empty((nz, nr)), np.empty((nz, nr))
+
+    def block(a, b):
+        b2 = min(b + 1, nz)
+        sub = Grid(grid.r_v, grid.z_v[a:b2 + 1])
+        sm = Masks(masks.cell_band, masks.rface_band, masks.zface_band, masks.zc_flags[a:b2], masks.zv_flags[a:b2])
+        kr, kz, ko = face_conductivities(case, sub, sm, T[a:b2])
+        k_r[a:b] = kr[:b - a]
+        k_out[a:b] = ko[:b - a]
+        k_z[a:b2 - 1] = kz
+        smc = Masks(masks.cell_band, masks.rface_band, masks.zface_band, masks.zc_flags[a:b], masks.zv_flags[a:b])
+        rho[a:b], cp[a:b] = rho_cp_cells(case, smc, T[a:b])
+    _par_rows(block, nz, min_rows=16)
+    return k_r, k_z, k_out, rho, cp
+
+
 # ---------------------------------------------------------------------------
 # assembly of one sweep (SURVEY 9.4)
 # ---------------------------------------------------------------------------
@@ -290,11 +350,27 @@ class System:
 
     def matvec(self, x):
         x = x.reshape(self.diag.shape)
-        y = self.diag * x
-        y[:, :-1] -= self.cR[:, :-1] * x[:, 1:]
-        y[:, 1:] -= self.cR[:, :-1] * x[:, :-1]
-        y[:-1, :] -= self.cZ[:-1, :] * x[1:, :]
-        y[1:, :] -= self.cZ[:-1, :] * x[:-1, :]
+        nz = x.shape[0]
+        if _POOL is None:
+            y = self.diag * x
+            y[:, :-1] -= self.cR[:, :-1] * x[:, 1:]
+            y[:, 1:] -= self.cR[:, :-1] * x[:, :-1]
+            y[:-1, :] -= self.cZ[:-1, :] * x[1:, :]
+            y[1:, :] -= self.cZ[:-1, :] * x[:-1, :]
+            return y
+        y = np.empty_like(x)
+        cR, cZ, dg = self.cR, self.cZ, self.diag
+
+        def block(a, b):
+            yb = dg[a:b] * x[a:b]
+            yb[:, :-1] -= cR[a:b, :-1] * x[a:b, 1:]
+            yb[:, 1:] -= cR[a:b, :-1] * x[a:b, :-1]
+            hi = min(b, nz - 1)
+            yb[:hi - a, :] -= cZ[a:hi, :] * x[a + 1:hi + 1, :]
+            lo = max(a, 1)
+            yb[lo - a:, :] -= cZ[lo - 1:b - 1, :] * x[lo - 1:b - 1, :]
+            y[a:b] = yb
+        _par_rows(block, nz)
         return y
 
     def to_csr(self):
@@ -346,7 +422,7 @@ class Oracle:
         g, c, m = self.grid, self.case, self.masks
         T = self.T
         T_old = self.T_old if self.has_old else T
-        k_r, k_z, k_out = face_conductivities(c, g, m, T)
+        k_r, k_z, k_out, rho, cp = _properties(c, g, m, T)
         if c.gamma == 'snapshot':
             G_r, G_z, k0_out = self._snap
         elif c.gamma == 'lazy':
@@ -360,7 +436,6 @@ class Oracle:
         cZ[:-1, :] = G_z * self.geo_z
         if c.axial_break is not None:
             cZ[:-1, :][np.asarray(c.axial_break, dtype=bool), :] = 0.0
-        rho, cp = rho_cp_cells(c, m, T)
         cap = cp * rho * self.vol / dt
         diag = cap.copy()
         diag[:, :-1] += cR[:, :-1]
@@ -445,8 +520,19 @@ class _MgLevel:
         self.fd, self.fe = rline_factor(self.S)
 
     def line(self, v):
-        y, _ = sla.lapack.dpttrs(self.fd, self.fe, v.ravel().copy())
-        return y.reshape(v.shape)
+        if _POOL is None:
+            y, _ = sla.lapack.dpttrs(self.fd, self.fe, v.ravel().copy())
+            return y.reshape(v.shape)
+        # the chain decouples at every row end (cR = 0 there): row blocks are independent tridiagonal solves
+        nz, nr = v.shape
+        out = np.empty_like(v)
+        fd, fe = self.fd, self.fe
+
+        def block(a, b):
+            y, _ = sla.lapack.dpttrs(fd[a * nr:b * nr], fe[a * nr:b * nr - 1], v[a:b].ravel().copy())
+            out[a:b] = y.reshape(b - a, nr)
+        _par_rows(block, nz)
+        return out
 
     def coarsen(self):
         cR, cZ, dg = self.S.cR, self.S.cZ, self.S.diag

@@ -478,3 +478,123 @@ def test_adaptive_dt_driver_matches_oracle_on_its_own_step_sequence(cfg, start):
             at5 = o.T[:, -1].copy()
     assert np.max(np.abs(r['T'] - o.T)) <= 3 * len(r['dt']) * PER_STEP_TOL_K
     assert np.max(np.abs(r['profiles'][0] - at5)) <= 3 * len(r['dt']) * PER_STEP_TOL_K
+
+
+# ----------------------------------------------------------------------------------------------
+# the configurations bench.py times: same solver options, compared with the oracle's field
+BENCH_OPTS = dict(precond='mgline', extrapolate=3, refactor_every=5)
+
+
+def _oracle_step(o, dt, sweeps, tol=1e-10):
+    o.update_old()
+    for _ in range(sweeps):
+        o.sweep(dt, solver='pcg_mgline', tol=tol, criterion='precond_inf')
+
+
+def test_bench_options_transient_1024x256(cfg):
+    """25 steps of `T.updateOld()` + 5 sweeps (main.py:267-271) at dt = 0.1 s on a 1024 x 256 composite mesh with exactly
+    the options of bench.py (mgline preconditioner, cubic extrapolated PCG start, pivots / coarse operators refreshed once
+    per step, second-sweep start from the previous re-sweep correction): the field after EVERY step against the oracle
+    (PCG to 1e-10 K), <= 1e-6 K per step and <= 1e-3 K at the end."""
+    s, o = make_pair(cfg, (1024, 32, 64, 160), has_old=True, solver_kw=BENCH_OPTS)
+    worst, iters = 0.0, []
+    with s:
+        for step in range(25):
+            it0 = s.total_iters
+            s.run(0.1, 1, sweeps=5, has_old=True)
+            T = s.value.reshape(o.T.shape)
+            iters.append(s.total_iters - it0)
+            stats = s.stats(5)
+            assert all(st['converged'] and not st['breakdown'] for st in stats), (step, stats)
+            _oracle_step(o, 0.1, 5)
+            err = float(np.max(np.abs(T - o.T)))
+            worst = max(worst, err)
+            assert err <= PER_STEP_TOL_K, (step, err)
+    assert worst <= END_TOL_K
+    # the history-based starts must actually engage (fewer iterations late than early in the run)
+    assert sum(iters[-5:]) < sum(iters[:5]), iters
+
+
+def test_bench_options_full_size_two_steps(cfg):
+    """BASELINE configs[2] itself (4096 x 1024, the bench workload and options): two time steps from the ambient field
+    against the oracle's FIELD (not a residual property)."""
+    s, o = make_pair(cfg, (4096, 128, 256, 640), has_old=True, solver_kw=BENCH_OPTS)
+    with s:
+        for step in range(2):
+            s.run(0.1, 1, sweeps=5, has_old=True)
+            T = s.value.reshape(o.T.shape)
+            assert all(st['converged'] for st in s.stats(5))
+            _oracle_step(o, 0.1, 5, tol=1e-9)
+            assert float(np.max(np.abs(T - o.T))) <= PER_STEP_TOL_K, step
+
+
+@pytest.mark.parametrize('tag', ['s128x256', 'native'])
+def test_mgline_refactor_every_and_hot_start(cfg, tag):
+    """refactor_every > 1 with the V-cycle (stale pivots / coarse operators only precondition): same field as the direct
+    solve from a hot state that crosses the melting smear."""
+    s, o = make_pair(cfg, SHAPES[tag], T0=lambda g: hot_field(g, amp=150.0), has_old=True,
+                     solver_kw=dict(precond='mgline', refactor_every=5, extrapolate=3))
+    with s:
+        s.run(0.1, 6, sweeps=5, has_old=True)
+        T = s.value.reshape(o.T.shape)
+        assert all(st['converged'] for st in s.stats(30))
+    for _ in range(6):
+        o.update_old()
+        for _ in range(5):
+            o.sweep(0.1, solver='banded' if o.grid.nr <= 160 else 'splu')
+    assert np.max(np.abs(T - o.T)) <= 30 * PER_STEP_TOL_K
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE configs[0] / configs[1] to their stated end times (VERDICT r1, "full-length transients")
+def _long_golden(name):
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return np.load(os.path.join(root, 'tests', 'golden', f'oracle_long_{name}.npz'))
+
+
+def _run_to_keeps(cfg, gold, **modes):
+    from heat_pipe_solver_b200 import ConductionSolver, generate_composite_mesh
+    mesh, _ = generate_composite_mesh(dict(cfg['mesh']), cfg['dimensions'])
+    dt, sweeps, has_old = float(gold['dt']), int(gold['sweeps']), bool(gold['has_old'])
+    errs, walls = {}, {}
+    wall_steps = set(int(v) for v in gold['wall_steps'])
+    stops = sorted(set(int(v) for v in gold['keep_steps']) | wall_steps)
+    with ConductionSolver(mesh, cfg['dimensions'], cfg['parameters'], cfg['constants'], **modes) as s:
+        done = 0
+        for stop in stops:
+            s.run(dt, stop - done, sweeps=sweeps, has_old=has_old)
+            done = stop
+            T = s.value.reshape(mesh.shape)
+            if f'T_{stop}' in gold:
+                errs[stop] = float(np.max(np.abs(T - gold[f'T_{stop}'])))
+            if stop in wall_steps:
+                walls[stop] = T[:, -1].copy()
+        assert not any(st['breakdown'] or st['hit_max_iter'] for st in s.stats(64))
+    return errs, walls
+
+
+def test_config0_simple_properties_to_3000s(cfg):
+    """configs[0]: constant properties, dt = 0.1 s, 30 000 steps of the reference's active loop (main.py:119-120 with
+    t_end = 3000, 200-202) against the oracle's committed fields along the run."""
+    gold = _long_golden('simple')
+    errs, walls = _run_to_keeps(cfg, gold, properties='simple')
+    assert max(errs) == 30000
+    assert all(e <= END_TOL_K for e in errs.values()), errs
+    for k, step in enumerate(gold['wall_steps']):
+        assert np.max(np.abs(walls[int(step)] - gold['wall'][k])) <= END_TOL_K
+
+
+def test_config1_temperature_dependent_to_12000s(cfg):
+    """configs[1]: T-dependent properties, `T.updateOld()` + 5 sweeps (main.py:267-271), dt = 1 s, to t = 12 000 s: fields
+    at 100 / 1000 / 3000 / 6000 / 12 000 s against the oracle's, and the outer-wall temperature at z ~ 0 every 1000 s against
+    the read-offs of the reference's committed plot plots/12000s/top_wall_axial_profiles.png (+-2 K)."""
+    gold = _long_golden('tdep')
+    errs, walls = _run_to_keeps(cfg, gold)
+    assert max(errs) == 12000
+    assert all(e <= END_TOL_K for e in errs.values()), errs
+    readoffs = {4000: 447, 5000: 470, 6000: 490, 7000: 508, 8000: 524, 9000: 539, 10000: 553, 11000: 566, 12000: 578}
+    for step, Tplot in readoffs.items():
+        assert abs(walls[step][0] - Tplot) <= 2.0, (step, walls[step][0], Tplot)
+    for step, Tplot in {1000: 350, 2000: 387, 3000: 419}.items():      # plot curves at 1038 / 1998 / 2958 s
+        assert abs(walls[step][0] - Tplot) <= 4.0, (step, walls[step][0], Tplot)

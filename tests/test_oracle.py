@@ -173,3 +173,28 @@ def test_oracle_reproduces_committed_snapshots(name):
     assert np.max(np.abs(T - gold[name + '_T'])) <= 1e-9
     big = gold[name + '_res'] > 1e-7          # residuals at round-off level are not reproducible across BLAS builds
     assert np.allclose(res[big], gold[name + '_res'][big], rtol=1e-6)
+
+
+def test_long_golden_matches_the_reference_plot_readoffs_and_the_oracle():
+    """tests/golden/oracle_long_tdep.npz (configs[1] to 12 000 s, written by make_oracle_long_golden.py): the outer-wall
+    temperature at z ~ 0 every 1000 s against the read-offs of the reference's committed plot
+    plots/12000s/top_wall_axial_profiles.png (+-2 K), and the first kept field against a fresh
+    oracle run (the fixture is what the oracle produces)."""
+    import importlib.util
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'oracle_long_tdep.npz'))
+    wall = {int(s): w for s, w in zip(gold['wall_steps'], gold['wall'])}
+    for step, Tplot in {4000: 447, 5000: 470, 6000: 490, 7000: 508, 8000: 524, 9000: 539, 10000: 553, 11000: 566, 12000: 578}.items():
+        assert abs(wall[step][0] - Tplot) <= 2.0, (step, wall[step][0])
+    for step, (T0_plot, peak_plot) in {1000: (350, 355), 2000: (387, 390), 3000: (419, 421)}.items():   # curves at 1038 / 1998 / 2958 s
+        assert abs(wall[step][0] - T0_plot) <= 4.0 and abs(wall[step].max() - peak_plot) <= 4.0
+    spec = importlib.util.spec_from_file_location('make_oracle_long_golden', os.path.join(ROOT, 'tests', 'golden', 'make_oracle_long_golden.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    short = dict(mod.CASES['tdep'], steps=100, keep=(100,), wall_every=100)
+    out = mod.run_case(short)
+    assert np.max(np.abs(out['T_100'] - gold['T_100'])) <= 1e-9
+    simple = np.load(os.path.join(ROOT, 'tests', 'golden', 'oracle_long_simple.npz'))
+    short = dict(mod.CASES['simple'], steps=1000, keep=(1000,), wall_every=1000)
+    assert np.max(np.abs(mod.run_case(short)['T_1000'] - simple['T_1000'])) <= 1e-9
+    # constant properties conserve energy exactly: monotone heating, bounded by the input
+    assert np.all(np.diff(simple['wall'][:, 0]) > 0)
