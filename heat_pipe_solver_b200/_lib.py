@@ -35,7 +35,8 @@ class HpSolveOpts(C.Structure):
     _fields_ = [('precond', C.c_int32), ('criterion', C.c_int32), ('tol', C.c_double), ('max_iter', C.c_int32),
                 ('loop_mode', C.c_int32), ('poll_chunk', C.c_int32), ('refactor_every', C.c_int32),
                 ('extrapolate', C.c_int32), ('mg_levels', C.c_int32), ('mg_coarse_sweeps', C.c_int32), ('reuse_converged', C.c_int32),
-                ('mg_omega', C.c_double)]
+                ('mg_omega', C.c_double), ('while_unroll', C.c_int32), ('peer_timeout_ms', C.c_int32),
+                ('mg_zscale', C.c_double)]
 
 
 class HpSweepStat(C.Structure):
@@ -60,6 +61,7 @@ SIGNATURES = {
     'hp_destroy': (C.c_int, [_H]),
     'hp_set_stream': (C.c_int, [_H, C.c_void_p]),
     'hp_set_opts': (C.c_int, [_H, C.POINTER(HpSolveOpts)]),
+    'hp_get_opts': (C.c_int, [_H, C.POINTER(HpSolveOpts)]),
     'hp_set_T_dev': (C.c_int, [_H, C.c_void_p]),
     'hp_get_T_dev': (C.c_int, [_H, C.c_void_p]),
     'hp_set_T_host': (C.c_int, [_H, C.c_void_p]),
@@ -84,6 +86,8 @@ SIGNATURES = {
     'hp_comm_init': (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
     'hp_peer_export': (C.c_int, [_H, C.POINTER(C.c_int32), C.c_void_p]),
     'hp_peer_import': (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_int32)]),
+    'hp_comm_fault': (C.c_int, [_H]),
+    'hp_comm_clear_fault': (C.c_int, [_H]),
 }
 
 _lib = None

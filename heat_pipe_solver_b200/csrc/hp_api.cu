@@ -66,6 +66,24 @@ static bool load_nccl() {
             return fail(std::string(#call) + " -> " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error")); \
     } while (0)
 
+// Coarse levels inside the level block: level l has ceil(nz_{l-1} / 2) rows, 8 fields each (cR, cZ, diag, dinv, rhs, x, x2,
+// tmp), ghost-row layout like the fine fields.
+enum { LV_CR = 0, LV_CZ, LV_DIAG, LV_DINV, LV_RHS, LV_X, LV_X2, LV_TMP, LV_FIELDS };
+struct LevelLayout { int n; int nz[HP_MAX_LEVELS]; size_t off[HP_MAX_LEVELS][LV_FIELDS]; size_t elems; };
+static LevelLayout level_layout(int nz, int nr) {
+    LevelLayout L{};
+    L.n = 1; L.nz[0] = nz;
+    size_t e = 0;
+    for (int l = 1; l < HP_MAX_LEVELS && L.nz[l - 1] > 1; ++l) {
+        const int rows = (L.nz[l - 1] + 1) / 2;
+        L.nz[l] = rows;
+        for (int k = 0; k < LV_FIELDS; ++k) { L.off[l][k] = e; e += (size_t)(rows + 2) * nr + 64; }
+        L.n = l + 1;
+    }
+    L.elems = e;
+    return L;
+}
+
 struct GraphEntry {
     double dt; int sweeps; int has_old; int update_old; hp_solve_opts opts;
     cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
@@ -93,34 +111,28 @@ struct hp_solver_s {
     // slabs
     int rank = 0, nranks = 1;
     ncclComm_t nccl = nullptr;
-    // 'mgline' hierarchy (level 0 aliases the fine fields)
+    // 'mgline' hierarchy (level 0 aliases the fine fields; the coarse levels live in ONE allocation whose layout is a
+    // function of (nz, nr) alone, so a rank can address the level arrays of its neighbouring slabs through peer memory)
     HpLevel lev[HP_MAX_LEVELS];
-    int nlev = 0, nlev_alloc = 0;
-    // replicated global coarse levels of mgline under peer-memory slabs (shape fixed at hp_peer_export time)
+    int nlev = 0;
+    double* lvblock = nullptr;
+    LevelLayout lay{}, lay_lo{}, lay_hi{};
+    double *lv_lo = nullptr, *lv_hi = nullptr;      // level blocks of the lower / upper neighbour (peer mappings)
     std::vector<int> nz_of_rank;
-    int g_switch = 0;                // local level whose rows are gathered into global level 0 (0 = rank-local cycle)
-    int g_rows_mine = 0, g_row0 = 0; // my rows / first row inside global level 0
-    int nglev = 0;
-    HpLevel glev[HP_MAX_LEVELS];
-    long long g_off[HP_MAX_LEVELS][8];   // element offsets of (cR, cZ, diag, dinv, rhs, x, x2, tmp) inside gblock
-    double* gblock = nullptr;
-    size_t gblock_elems = 0;
-    bool g_active = false;
+    int* h_fault = nullptr;          // pinned + mapped: raised by a kernel whose wait for a peer timed out
     // peer-memory exchange (hp_peer_export / hp_peer_import)
     HpComm* comm = nullptr;          // my mailbox
     double* qz_block = nullptr;      // base of the (q, z) allocation (IPC handle is per allocation)
     std::vector<void*> ipc_opened;
-    unsigned long long* gbar = nullptr;   // grid-barrier words of k_mg_subcycle
-    bool mg_fused = true;
-    bool mg_upfused = true;      // coarse up-leg stages as one kernel (k_mg_up) instead of residual + line solve
-    bool pdl = false;                 // programmatic dependent launch edges between the kernel nodes of the step graph
+    bool mg_upfused = true;      // fused V-cycle stages (k_mg_fused<1|2>) usable: one row team owns a whole row
     int hist = 0;                    // completed steps since the field was last set: Told (and d1, d2) hold that much history
     double hist_dt = 0.0;            // time step the history was taken with
-    bool c2_on = true;               // track the re-sweep correction (predicted start of the second sweep); HP_SWEEP2=0 disables
     bool c2_stashed = false;         // d.c2 holds the first-sweep solution of the step just finished
     bool ghost_dirty = true;         // ghost rows of T must be refreshed by an explicit exchange before the next sweep
     // L2 access-policy window over the contiguous (q, z) block
     bool l2_on = false;
+    bool l2_limit_changed = false;      // cudaLimitPersistingL2CacheSize is device-wide: put back at hp_destroy
+    size_t l2_limit_before = 0;
     void* l2_base = nullptr;
     size_t l2_bytes = 0;
     cudaAccessPolicyWindow l2_window{};
@@ -130,6 +142,19 @@ struct hp_solver_s {
     std::vector<int> prof_kind;
     size_t prof_used = 0;
 };
+
+static int check_fault(hp_solver_s* h) {
+    if (h->h_fault && *(volatile int*)h->h_fault)
+        return fail("a wait for a neighbouring slab timed out (hp_solve_opts.peer_timeout_ms): the simulation on this handle is "
+                    "stopped; synchronise all ranks and call hp_comm_clear_fault, or destroy the handle");
+    return 0;
+}
+
+static int fetch_state(hp_solver_s* h) {
+    CK(cudaMemcpyAsync(h->h_state, h->d.st, sizeof(HpState), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
 
 static int dev_alloc(hp_solver_s* h, void** p, size_t bytes) {
     CK(cudaMalloc(p, bytes ? bytes : 8));
@@ -147,23 +172,19 @@ static int upload(hp_solver_s* h, const T** dst, const std::vector<T>& v) {
 
 // L2 residency of the producer->consumer vectors of the PCG iteration (q: k_cg_A -> k_cg_B, z: k_cg_B -> k_cg_A).
 // The window is attached to every PCG kernel launch (stream attribute in stream mode, kernel-node attribute in
-// graphs).  HP_L2_PERSIST=0 disables it (A/B measurements).
+// graphs).
 static void setup_l2_window(hp_solver_s* h, const cudaDeviceProp& prop) {
     h->l2_on = false;
-    const char* env = getenv("HP_L2_PERSIST");
-    const int mode = env ? atoi(env) : 1;
-    if (mode == 0) return;
     if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
     // Only when the whole window fits the persisting carve-out: a partially persisting window (hitRatio < 1) over
     // vectors larger than L2 halves the streaming rate of both PCG kernels (measured on 16384x4096, profiles/).
     size_t win = h->l2_bytes;                                   // q and z
     const size_t cap = (size_t)prop.persistingL2CacheMaxSize < (size_t)prop.accessPolicyMaxWindowSize
                            ? (size_t)prop.persistingL2CacheMaxSize : (size_t)prop.accessPolicyMaxWindowSize;
-    if (win > cap) {
-        if (mode == 2 && win / 2 <= cap) win = win / 2;        // experiment: q alone
-        else return;
-    }
+    if (win > cap) return;
+    if (cudaDeviceGetLimit(&h->l2_limit_before, cudaLimitPersistingL2CacheSize) != cudaSuccess) { cudaGetLastError(); return; }
     if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, win) != cudaSuccess) { cudaGetLastError(); return; }
+    h->l2_limit_changed = true;
     memset(&h->l2_window, 0, sizeof(h->l2_window));
     h->l2_window.base_ptr = h->l2_base;
     h->l2_window.num_bytes = win;
@@ -182,59 +203,58 @@ static int apply_l2_to_stream(hp_solver_s* h) {
     return 0;
 }
 
-// ---- 'mgline' hierarchy: level l+1 has ceil(nz_l / 2) rows; stops at 16 rows or mg_levels -------------------
-static int local_level_count(int nz, int max_levels) {
+// ---- 'mgline' hierarchy: level l+1 has ceil(nz_l / 2) rows; a level is added while the one above has >= 32 rows ------
+static int local_level_count(long long nz, int max_levels) {
     int n = 1;
-    for (int nzl = nz; n < max_levels && nzl >= 32; nzl = (nzl + 1) / 2) ++n;
+    for (long long nzl = nz; n < max_levels && nzl >= 32; nzl = (nzl + 1) / 2) ++n;
     return n;
 }
-static int rows_at_level(int nz, int l) {
-    for (int k = 0; k < l; ++k) nz = (nz + 1) / 2;
-    return nz;
+
+// Number of levels.  One GPU, or slabs without peer memory (rank-local cycle): from the local row count.  Peer-memory
+// slabs: the hierarchy of the WHOLE mesh, distributed -- the same count on every rank, from the global row count, reduced
+// until the row pairs of every level line up with the slab cuts (every slab but the last a multiple of 2^(levels-1) rows).
+static int level_count_for(const hp_solver_s* h) {
+    const int nr_ = h->nranks;
+    if (!(nr_ > 1 && h->d.p2p && (int)h->nz_of_rank.size() == nr_)) return local_level_count(h->d.nz, h->opts.mg_levels);
+    long long total = 0;
+    for (int v : h->nz_of_rank) total += v;
+    int n = local_level_count(total, h->opts.mg_levels);
+    for (; n >= 2; --n) {
+        const int A = 1 << (n - 1);
+        bool ok = true;
+        for (int r = 0; r + 1 < nr_; ++r) ok = ok && (h->nz_of_rank[r] % A == 0);
+        if (ok) break;
+    }
+    return n < 1 ? 1 : n;
+}
+
+static int ensure_levels(hp_solver_s* h) {
+    if (h->lvblock) return 0;
+    HpDev& d = h->d;
+    h->lay = level_layout(d.nz, d.nr);
+    if (dev_alloc(h, (void**)&h->lvblock, (h->lay.elems + 64) * sizeof(double))) return -1;
+    CK(cudaMemsetAsync(h->lvblock, 0, (h->lay.elems + 64) * sizeof(double), h->stream));
+    HpLevel& L0 = h->lev[0];
+    L0.nz = d.nz; L0.cR = d.cR; L0.cZ = d.cZ; L0.diag = d.diag; L0.dinv = d.dinv;
+    L0.rhs = d.r; L0.x = d.z; L0.tmp = d.q;
+    if (dev_alloc(h, (void**)&L0.x2, h->field_elems * sizeof(double))) return -1;
+    CK(cudaMemsetAsync(L0.x2, 0, h->field_elems * sizeof(double), h->stream));
+    for (int l = 1; l < h->lay.n; ++l) {
+        HpLevel& L = h->lev[l];
+        L.nz = h->lay.nz[l];
+        double** f[LV_FIELDS] = {&L.cR, &L.cZ, &L.diag, &L.dinv, &L.rhs, &L.x, &L.x2, &L.tmp};
+        for (int k = 0; k < LV_FIELDS; ++k) *f[k] = h->lvblock + h->lay.off[l][k];
+    }
+    h->mg_upfused = hpk::mg_fused_supported(h->cfg) && h->cfg.ncolA == 1;
+    return 0;
 }
 
 static int setup_mg(hp_solver_s* h) {
-    HpDev& d = h->d;
-    int want = local_level_count(d.nz, h->opts.mg_levels);
-    // under peer-memory slabs every rank stops at the same level, and the rows of that level are gathered into the
-    // replicated global hierarchy whose shape was fixed at export time
-    h->g_active = false;
-    if (h->nranks > 1 && d.p2p && h->gblock && !h->nz_of_rank.empty()) {
-        int s_min = HP_MAX_LEVELS;
-        for (int r = 0; r < h->nranks; ++r) {
-            int c = local_level_count(h->nz_of_rank[r], h->opts.mg_levels) - 1;
-            if (c < s_min) s_min = c;
-        }
-        if (s_min >= 1 && s_min == h->g_switch) { want = s_min + 1; h->g_active = true; }
-    }
-    if (h->nlev_alloc == 0) {
-        HpLevel& L0 = h->lev[0];
-        L0.nz = d.nz; L0.cR = d.cR; L0.cZ = d.cZ; L0.diag = d.diag; L0.dinv = d.dinv;
-        L0.rhs = d.r; L0.x = d.z; L0.tmp = d.q;
-        if (dev_alloc(h, (void**)&L0.x2, h->field_elems * sizeof(double))) return -1;
-        CK(cudaMemsetAsync(L0.x2, 0, h->field_elems * sizeof(double), h->stream));
-        if (dev_alloc(h, (void**)&h->gbar, 2 * sizeof(unsigned long long))) return -1;
-        CK(cudaMemsetAsync(h->gbar, 0, 2 * sizeof(unsigned long long), h->stream));
-        const char* ef = getenv("HP_MG_FUSED");
-        // measured on B200: inside the step graph the fused cycle (132 us) is no faster than its 21 separate launches
-        // (~6 us each), both are bound by the chain of dependent row latencies -> off unless asked for
-        h->mg_fused = (ef && ef[0] == '1') && hpk::mg_subcycle_supported(h->cfg);
-        const char* eu = getenv("HP_MG_UPFUSE");
-        h->mg_upfused = !(eu && eu[0] == '0') && hpk::mg_subcycle_supported(h->cfg) && h->cfg.ncolA == 1;
-        h->nlev_alloc = 1;
-    }
-    for (int l = h->nlev_alloc; l < want; ++l) {
-        HpLevel& L = h->lev[l];
-        L.nz = (h->lev[l - 1].nz + 1) / 2;
-        const size_t elems = (size_t)(L.nz + 2) * d.nr + 64;
-        double** f[] = {&L.cR, &L.cZ, &L.diag, &L.dinv, &L.rhs, &L.x, &L.x2, &L.tmp};
-        for (double** p : f) {
-            if (dev_alloc(h, (void**)p, elems * sizeof(double))) return -1;
-            CK(cudaMemsetAsync(*p, 0, elems * sizeof(double), h->stream));
-        }
-        h->nlev_alloc = l + 1;
-    }
+    if (ensure_levels(h)) return -1;
+    int want = level_count_for(h);
+    if (want > h->lay.n) want = h->lay.n;
     h->nlev = want;
+    h->d.mg_local = (h->nranks > 1 && !h->d.p2p) ? 1 : 0;
     return 0;
 }
 
@@ -242,12 +262,11 @@ static HpKArgs make_args(const hp_solver_s* h, double dt, int has_old) {
     HpKArgs a{};
     a.dt = dt; a.tol = h->opts.tol; a.has_old = has_old; a.max_iter = h->opts.max_iter;
     a.criterion = h->opts.criterion; a.use_cond = 0; a.cond = 0; a.rhs_out = nullptr;
-    static const int pf = [] { const char* e = getenv("HP_PREFETCH"); return e ? atoi(e) : 0; }();
-    a.prefetch = pf;
-    a.mg = (h->opts.precond == 2) ? 1 : 0; a.init_phase = 0; a.omega = h->opts.mg_omega; a.shift = 0;   // measured slower on B200 (profiles/): off unless asked for
+    a.mg = (h->opts.precond == 2) ? 1 : 0; a.init_phase = 0; a.omega = h->opts.mg_omega; a.shift = 0;
     // repeated converged sweeps as bookkeeping only (HpState.noop_ok, opt-in); under slabs the reducing kernels must run
     // on every rank for the flag protocol, so single GPU only
     a.noop_enable = (h->opts.reuse_converged && h->nranks == 1) ? 1 : 0;
+    a.timeout_ns = (unsigned long long)h->opts.peer_timeout_ms * 1000000ull;
     return a;
 }
 
@@ -257,8 +276,7 @@ enum { KIND_OTHER = 0, KIND_COEF, KIND_DIAG, KIND_FACTOR, KIND_INIT, KIND_A, KIN
 static int launch(hp_solver_s* h, const HpKernelLaunch& k, void** params, int kind = KIND_OTHER) {
     const bool prof = h->prof_on && h->prof_used < h->prof_ev.size() / 2;
     if (prof) CK(cudaEventRecord(h->prof_ev[2 * h->prof_used], h->stream));
-    if (k.cooperative) CK(cudaLaunchCooperativeKernel(k.func, k.grid, k.block, params, k.smem, h->stream));
-    else CK(cudaLaunchKernel(k.func, k.grid, k.block, params, k.smem, h->stream));
+    CK(cudaLaunchKernel(k.func, k.grid, k.block, params, k.smem, h->stream));
     if (prof) {
         CK(cudaEventRecord(h->prof_ev[2 * h->prof_used + 1], h->stream));
         h->prof_kind.push_back(kind);
@@ -282,6 +300,7 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("hp_create: no CUDA device available -- libhpsolver has no CPU fallback");
     hp_solver_s* h = new hp_solver_s();
+    struct Guard { hp_solver_s* h; ~Guard() { if (h) hp_destroy(h); } } guard{h};    // every early return below frees the handle
     h->stream = (cudaStream_t)stream;
     h->phys = *phys;
     CK(cudaGetDevice(&h->device));
@@ -289,16 +308,17 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
     CK(cudaGetDeviceProperties(&prop, h->device));
     h->num_sms = prop.multiProcessorCount;
     const char* err = nullptr;
-    if (!hpk::pick_config(m->nr, m->nz, h->num_sms, &h->cfg, &err)) { delete h; return fail(std::string("hp_create: ") + err); }
+    if (!hpk::pick_config(m->nr, m->nz, h->num_sms, &h->cfg, &err)) return fail(std::string("hp_create: ") + err);
     const int nr = m->nr, nz = m->nz;
     for (int i = 0; i < nr; ++i)
-        if (!(m->r_v[i + 1] > m->r_v[i])) { delete h; return fail("hp_create: r_v must be strictly increasing"); }
+        if (!(m->r_v[i + 1] > m->r_v[i])) return fail("hp_create: r_v must be strictly increasing");
     for (int g = 0; g < nz + 2; ++g)
-        if (!(m->z_v[g + 1] > m->z_v[g])) { delete h; return fail("hp_create: z_v must be strictly increasing"); }
+        if (!(m->z_v[g + 1] > m->z_v[g])) return fail("hp_create: z_v must be strictly increasing");
 
     HpDev& d = h->d;
     d.nr = nr; d.nz = nz; d.ncolA = h->cfg.ncolA; d.p2p = 0; d.seq = nullptr; d.z_lo = d.z_hi = d.T_lo = d.T_hi = nullptr;
-    for (int r = 0; r < HP_MAX_RANKS; ++r) { d.comm_peer[r] = nullptr; d.gblock_peer[r] = nullptr; }
+    for (int r = 0; r < HP_MAX_RANKS; ++r) d.comm_peer[r] = nullptr;
+    d.mg_local = 0; d.fault_host = nullptr;
     d.nranks = 1; d.rank = 0; d.red_local = nullptr; d.red_all = nullptr;
     std::vector<double> r_v(m->r_v, m->r_v + nr + 1), r_c(nr), dr(nr), ar(nr, 0.0), dcr(nr, 1.0);
     for (int i = 0; i < nr; ++i) { r_c[i] = 0.5 * (r_v[i] + r_v[i + 1]); dr[i] = r_v[i + 1] - r_v[i]; }
@@ -310,7 +330,7 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
     if (!m->cartesian) { wc = r_c; wf = r_v; }
     d.A_out_r = wf[nr];
     d.d_out = r_v[nr] - r_c[nr - 1];
-#define UP(field, vec) if (upload(h, &d.field, vec)) { hp_destroy(h); return -1; }
+#define UP(field, vec) if (upload(h, &d.field, vec)) return -1;
     UP(r_v, r_v); UP(r_c, r_c); UP(dr, dr); UP(wc, wc); UP(wf, wf); UP(ar, ar); UP(dcr, dcr);
     UP(z_c, z_c); UP(dz, dz); UP(az, az); UP(dcz, dcz);
     UP(cell_band, std::vector<int8_t>(m->cell_band, m->cell_band + nr));
@@ -327,14 +347,14 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
     h->field_elems = (size_t)(nz + 2) * nr + 64;
     double** fields[] = {&d.T, &d.Told, &d.cR, &d.cZ, &d.diag, &d.dinv, &d.r, &d.p0, &d.p1};
     for (double** f : fields) {
-        if (dev_alloc(h, (void**)f, h->field_elems * sizeof(double))) { hp_destroy(h); return -1; }
+        if (dev_alloc(h, (void**)f, h->field_elems * sizeof(double))) return -1;
         CK(cudaMemsetAsync(*f, 0, h->field_elems * sizeof(double), h->stream));
     }
     // q and z are produced by one PCG kernel and consumed by the next one: one contiguous block so that a single
     // L2 access-policy window can keep both resident across kernel boundaries (setup_l2_window)
     {
         double* qz = nullptr;
-        if (dev_alloc(h, (void**)&qz, 2 * h->field_elems * sizeof(double))) { hp_destroy(h); return -1; }
+        if (dev_alloc(h, (void**)&qz, 2 * h->field_elems * sizeof(double))) return -1;
         CK(cudaMemsetAsync(qz, 0, 2 * h->field_elems * sizeof(double), h->stream));
         d.q = qz; d.z = qz + h->field_elems;
         h->qz_block = qz;
@@ -342,22 +362,22 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
     }
     setup_l2_window(h, prop);
     void* p = nullptr;
-    if (dev_alloc(h, &p, sizeof(double) * (nz + 2))) { hp_destroy(h); return -1; }
+    if (dev_alloc(h, &p, sizeof(double) * (nz + 2))) return -1;
     d.k0_out = (const double*)p;
-    if (dev_alloc(h, (void**)&d.st, sizeof(HpState))) { hp_destroy(h); return -1; }
+    if (dev_alloc(h, (void**)&d.st, sizeof(HpState))) return -1;
     CK(cudaMemsetAsync(d.st, 0, sizeof(HpState), h->stream));
-    if (dev_alloc(h, (void**)&d.stats, sizeof(hp_sweep_stat) * HP_STATS_CAP)) { hp_destroy(h); return -1; }
+    if (dev_alloc(h, (void**)&d.stats, sizeof(hp_sweep_stat) * HP_STATS_CAP)) return -1;
     CK(cudaMemsetAsync(d.stats, 0, sizeof(hp_sweep_stat) * HP_STATS_CAP, h->stream));
-    if (dev_alloc(h, (void**)&d.partials, sizeof(double) * HP_NRED * HP_MAX_PARTIALS)) { hp_destroy(h); return -1; }
+    if (dev_alloc(h, (void**)&d.partials, sizeof(double) * HP_NRED * HP_MAX_PARTIALS)) return -1;
     CK(cudaMallocHost((void**)&h->h_state, sizeof(HpState)));
+    CK(cudaHostAlloc((void**)&h->h_fault, sizeof(int), cudaHostAllocMapped));
+    *h->h_fault = 0;
+    CK(cudaHostGetDevicePointer((void**)&d.fault_host, h->h_fault, 0));
 
     h->opts.precond = 1; h->opts.criterion = 0; h->opts.tol = 1e-9; h->opts.max_iter = 5000;
-    // measured on B200: programmatic edges make the step SLOWER (mgline 8.97 -> 10.70 ms, rline 18.2 -> 19.4 ms; the
-    // early-scheduled dependents compete for SM slots with the draining grid) -> opt-in only (HP_PDL=1)
-    { const char* e = getenv("HP_PDL"); h->pdl = (e && e[0] == '1'); }
-    { const char* e = getenv("HP_SWEEP2"); h->c2_on = !(e && e[0] == '0'); }
     h->opts.loop_mode = 1; h->opts.poll_chunk = 8; h->opts.refactor_every = 1; h->opts.extrapolate = 3;
-    h->opts.mg_levels = 6; h->opts.mg_coarse_sweeps = 2; h->opts.mg_omega = 0.7; h->opts.reuse_converged = 0;
+    h->opts.mg_levels = 6; h->opts.mg_coarse_sweeps = 2; h->opts.mg_omega = 0.55; h->opts.reuse_converged = 0;
+    h->opts.while_unroll = 1; h->opts.peer_timeout_ms = 60000; h->opts.mg_zscale = 0.5;
 
     // initial field + snapshots (main.py:34,133,145,152)
     CK(hpk::launch_fill_rows(d, d.T, h->stream));
@@ -367,12 +387,13 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
         HpKernelLaunch k = hpk::desc_snapshot_kout(h->cfg, d);
         double* k0 = (double*)d.k0_out;
         void* params[] = {&d, &h->phys, &a, &k0};
-        if (launch(h, k, params)) { hp_destroy(h); return -1; }
+        if (launch(h, k, params)) return -1;
         HpKernelLaunch kc = hpk::desc_coef(h->cfg, d);
         void* params2[] = {&d, &h->phys, &a};
-        if (launch(h, kc, params2)) { hp_destroy(h); return -1; }
+        if (launch(h, kc, params2)) return -1;
     }
     CK(cudaStreamSynchronize(h->stream));
+    guard.h = nullptr;
     *out = h;
     return 0;
 }
@@ -394,6 +415,8 @@ int hp_destroy(hp_handle h) {
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_state) cudaFreeHost(h->h_state);
+    if (h->h_fault) cudaFreeHost(h->h_fault);
+    if (h->l2_limit_changed) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_limit_before);
     delete h;
     return 0;
 }
@@ -426,12 +449,26 @@ int hp_set_opts(hp_handle h, const hp_solve_opts* o) {
     if (h->opts.mg_levels < 2) h->opts.mg_levels = 6;
     if (h->opts.mg_levels > HP_MAX_LEVELS) h->opts.mg_levels = HP_MAX_LEVELS;
     if (h->opts.mg_coarse_sweeps < 0) h->opts.mg_coarse_sweeps = 2;
-    if (!(h->opts.mg_omega > 0.0 && h->opts.mg_omega <= 1.0)) h->opts.mg_omega = 0.7;
+    if (h->opts.mg_coarse_sweeps > 8) h->opts.mg_coarse_sweeps = 8;
+    if (!(h->opts.mg_omega > 0.0 && h->opts.mg_omega <= 1.0)) h->opts.mg_omega = 0.55;
+    if (!(h->opts.mg_zscale > 0.0 && h->opts.mg_zscale <= 1.0)) h->opts.mg_zscale = 0.5;
+    if (h->opts.while_unroll < 1) h->opts.while_unroll = 1;
+    if (h->opts.while_unroll > 8) h->opts.while_unroll = 8;
+    if (h->opts.peer_timeout_ms < 1) h->opts.peer_timeout_ms = 60000;
     if (h->opts.precond == 2) {
         if (setup_mg(h)) return -1;
-        if (h->nlev < 2) h->opts.precond = 1;          // mesh too short to coarsen: plain line preconditioner
+        // mesh too short to coarsen: plain line preconditioner.  Under peer-memory slabs the level count comes from the
+        // global mesh, so every rank takes the same decision; slabs without peer memory decide per rank -- the caller
+        // (distributed.make_solver_for_rank) resolves the preconditioner globally before it gets here
+        if (h->nlev < 2) h->opts.precond = 1;
     }
     return invalidate_noop(h);
+}
+
+int hp_get_opts(hp_handle h, hp_solve_opts* out) {
+    if (!h || !out) return fail("hp_get_opts: null argument");
+    *out = h->opts;
+    return 0;
 }
 
 static size_t owned_bytes(hp_handle h) { return (size_t)h->d.nz * h->d.nr * sizeof(double); }
@@ -446,6 +483,7 @@ int hp_set_T_dev(hp_handle h, const double* d_T) {
 }
 int hp_get_T_dev(hp_handle h, double* d_T) {
     if (!h || !d_T) return fail("hp_get_T_dev: null argument");
+    if (check_fault(h)) return -1;
     CK(cudaMemcpyAsync(d_T, h->d.T + h->d.nr, owned_bytes(h), cudaMemcpyDeviceToDevice, h->stream));
     return 0;
 }
@@ -460,7 +498,7 @@ int hp_get_T_host(hp_handle h, double* h_T) {
     if (!h || !h_T) return fail("hp_get_T_host: null argument");
     CK(cudaMemcpyAsync(h_T, h->d.T + h->d.nr, owned_bytes(h), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    return 0;
+    return check_fault(h);
 }
 const double* hp_T_ptr(hp_handle h) { return h ? h->d.T + h->d.nr : nullptr; }
 
@@ -488,37 +526,13 @@ static int exchange_rows(hp_solver_s* h, double* field) {
 }
 
 // ---- emission of the sweep either as plain stream launches or as CUDA-graph kernel nodes --------------------------------
-struct NodeChain {
-    cudaGraph_t g; cudaGraphNode_t last = nullptr; int count = 0;
-    bool last_is_kernel = false;      // a programmatic (PDL) edge may only connect two kernel nodes
-};
+struct NodeChain { cudaGraph_t g; cudaGraphNode_t last = nullptr; int count = 0; };
 static int chain_kernel(NodeChain& c, const HpKernelLaunch& k, void** params, const hp_solver_s* h = nullptr) {
     cudaGraphNode_t n;
-    const bool pdl = h && h->pdl && c.last && c.last_is_kernel && !k.cooperative;
-    if (pdl) {
-        // programmatic edge: the node may be scheduled while its predecessor drains; every kernel starts with
-        // griddepcontrol.wait (pdl_enter), which restores full completion + memory visibility
-        cudaGraphNodeParams gp{};
-        gp.type = cudaGraphNodeTypeKernel;
-        gp.kernel.func = (void*)k.func; gp.kernel.gridDim = k.grid; gp.kernel.blockDim = k.block;
-        gp.kernel.sharedMemBytes = (unsigned)k.smem; gp.kernel.kernelParams = params; gp.kernel.extra = nullptr;
-        cudaGraphEdgeData ed;
-        memset(&ed, 0, sizeof(ed));
-        ed.from_port = cudaGraphKernelNodePortProgrammatic;
-        ed.type = cudaGraphDependencyTypeProgrammatic;
-        CK(cudaGraphAddNode_v2(&n, c.g, &c.last, &ed, 1, &gp));
-    } else {
-        cudaKernelNodeParams np{};
-        np.func = (void*)k.func; np.gridDim = k.grid; np.blockDim = k.block; np.sharedMemBytes = (unsigned)k.smem;
-        np.kernelParams = params; np.extra = nullptr;
-        CK(cudaGraphAddKernelNode(&n, c.g, c.last ? &c.last : nullptr, c.last ? 1 : 0, &np));
-    }
-    if (k.cooperative) {
-        cudaKernelNodeAttrValue v;
-        memset(&v, 0, sizeof(v));
-        v.cooperative = 1;
-        CK(cudaGraphKernelNodeSetAttribute(n, cudaKernelNodeAttributeCooperative, &v));
-    }
+    cudaKernelNodeParams np{};
+    np.func = (void*)k.func; np.gridDim = k.grid; np.blockDim = k.block; np.sharedMemBytes = (unsigned)k.smem;
+    np.kernelParams = params; np.extra = nullptr;
+    CK(cudaGraphAddKernelNode(&n, c.g, c.last ? &c.last : nullptr, c.last ? 1 : 0, &np));
     if (h && h->l2_on) {
         cudaKernelNodeAttrValue v;
         memset(&v, 0, sizeof(v));
@@ -526,7 +540,6 @@ static int chain_kernel(NodeChain& c, const HpKernelLaunch& k, void** params, co
         CK(cudaGraphKernelNodeSetAttribute(n, cudaKernelNodeAttributeAccessPolicyWindow, &v));
     }
     c.last = n; c.count++;
-    c.last_is_kernel = !k.cooperative;
     return 0;
 }
 
@@ -551,9 +564,8 @@ static int emit_combine(Emitter& e, HpKArgs& a, int fin_kind) {
     return emit(e, hpk::desc_finalize(), p4);
 }
 
-// mgline: Galerkin operators and line pivots of the coarse levels (after the fine diagonal / pivots are current).
-// Under peer-memory slabs the rows of the last local level are gathered into the replicated global level 0 of every
-// rank (with the true interface couplings), which is then coarsened further on every rank redundantly.
+// mgline: coarse operators and line pivots of the coarse levels (after the fine diagonal / pivots are current).  Needs no
+// communication: with the slab cuts aligned to the row pairs every coarse coefficient is a function of this rank's rows.
 static int emit_mg_setup(Emitter& e, bool always) {
     hp_solver_s* h = e.h;
     HpDev& d = h->d;
@@ -565,30 +577,13 @@ static int emit_mg_setup(Emitter& e, bool always) {
     ls.n = 1;
     ls.lev[0] = h->lev[0];
     int rows = 0;
-    const int s = h->nlev - 1;
+    double zs = h->opts.mg_zscale;
+    int keep_ghost = d.mg_local ? 0 : 1;
     for (int l = 1; l < h->nlev; ++l) {
-        void* pc[] = {&h->lev[l - 1], &h->lev[l], &nr, &skip};
+        void* pc[] = {&h->lev[l - 1], &h->lev[l], &nr, &zs, &keep_ghost, &skip};
         if (emit(e, hpk::desc_mg_coarsen(h->cfg, h->lev[l].nz, nr), pc, KIND_MG_SETUP)) return -1;
-        if (!(h->g_active && l == s)) { ls.lev[ls.n++] = h->lev[l]; rows += h->lev[l].nz; }
-    }
-    if (h->g_active) {
-        HpGatherArgs g{};
-        g.src[0] = h->lev[s].cR; g.src[1] = h->lev[s].cZ; g.src[2] = h->lev[s].diag;
-        g.dst_off[0] = h->g_off[0][0]; g.dst_off[1] = h->g_off[0][1]; g.dst_off[2] = h->g_off[0][2];
-        g.top_override = d.cZ + (size_t)d.nz * nr;      // fine coupling of my last row to the next slab (0 at the top end)
-        g.override_idx = 1;
-        g.nsrc = 3; g.nrows = h->g_rows_mine; g.row0_dst = h->g_row0; g.kind = HP_COMM_GOP;
-        void* pg[] = {&d, &g, &skip};
-        if (emit(e, hpk::desc_gather_rows(h->cfg, 3LL * g.nrows * nr), pg, KIND_MG_SETUP)) return -1;
-        int kind = HP_COMM_GOP;
-        void* pw[] = {&d, &kind, &skip};
-        if (emit(e, hpk::desc_wait_flag(), pw, KIND_MG_SETUP)) return -1;
-        ls.lev[ls.n++] = h->glev[0]; rows += h->glev[0].nz;
-        for (int gl = 1; gl < h->nglev; ++gl) {
-            void* pc[] = {&h->glev[gl - 1], &h->glev[gl], &nr, &skip};
-            if (emit(e, hpk::desc_mg_coarsen(h->cfg, h->glev[gl].nz, nr), pc, KIND_MG_SETUP)) return -1;
-            ls.lev[ls.n++] = h->glev[gl]; rows += h->glev[gl].nz;
-        }
+        ls.lev[ls.n++] = h->lev[l];
+        rows += h->lev[l].nz;
     }
     if (rows == 0) return 0;
     void* pf[] = {&ls, &nr, &skip};
@@ -597,132 +592,108 @@ static int emit_mg_setup(Emitter& e, bool always) {
 
 // mgline V(1,1) cycle on r (level-0 rhs) starting from zline = M^-1 r in d.z (left there by k_cg_B); leaves the
 // preconditioned residual in d.z and finalises (r.z, beta) in the last kernel.
+//   down leg  l = 0..c-1 : residual of x_l (level 0: omega zline), restricted to rhs_{l+1}, x_{l+1} = omega M^-1 rhs_{l+1}
+//   coarsest  level c    : `mg_coarse_sweeps` further smoothing steps, ping-pong between x_c and x2_c
+//   up leg    l = c-1..1 : x2_l = xt + omega M^-1 (rhs_l - L xt),  xt = x_l + P e_{l+1}
+//   level 0              : z = xt + omega M^-1 (r - L xt), r.z
+// Fused stages (one row team per row, k_mg_fused<2|1>) when the launch shapes allow, else residual + line-solve launches.
+// Under peer-memory slabs every stage that produces a correction hands its boundary rows to the neighbours (HpXchg) and
+// the stage that reads them waits for the flag: the arrays a stage pushes into are never read by the stage running at the
+// same time on the neighbour (the up leg and the coarsest sweeps write x2 / ping-pong, the down leg writes x).
 static int emit_vcycle(Emitter& e, const HpKArgs& a_in, int init_phase) {
     hp_solver_s* h = e.h;
     HpDev& d = h->d;
     HpKArgs a = a_in;
     a.init_phase = init_phase;
-    const int nr = d.nr;
-    // profiling kind of a coarse stage: local levels 1..5+ separately, replicated global levels under "mg_coarse"
-    auto ckind = [&](const HpLevel& Lv) -> int {
-        const long long l = &Lv - h->lev;
-        if (l < 1 || l >= h->nlev) return KIND_MG_COARSE;
-        return KIND_MG_L1 + (int)(l > 5 ? 5 : l) - 1;
-    };
-    auto res = [&](HpLevel& Lv, bool fine, const double* xin, const double* ec, int nzc, double* xout, double* resout,
-                   double* crhs, double scale) -> int {
-        HpMgResArgs m{xin, ec, xout, resout, crhs, scale, nzc};
-        void* p[] = {&d, &a, &Lv, &m};
-        return emit(e, hpk::desc_mg_res(h->cfg, Lv.nz), p, fine ? KIND_MG_RES0 : ckind(Lv));
-    };
-    auto line = [&](HpLevel& Lv, bool fine, const double* rhs, const double* base, double* out, int fin) -> int {
-        HpMgLineArgs m{rhs, base, out, fin};
-        void* p[] = {&d, &a, &Lv, &m};
-        return emit(e, hpk::desc_mg_line(h->cfg, Lv.nz), p, fine ? KIND_MG_LINE0 : ckind(Lv));
-    };
-    // fused up-leg stage: out = xt + omega M^-1 (rhs - L xt), xt = xin + P ec   (one launch instead of res + line)
-    auto up = [&](HpLevel& Lv, const double* xin, const double* ec, int nzc, double* out) -> int {
-        HpMgResArgs m{xin, ec, out, nullptr, nullptr, 1.0, nzc};
-        void* p[] = {&d, &a, &Lv, &m};
-        return emit(e, hpk::desc_mg_up(h->cfg, Lv.nz), p, ckind(Lv));
-    };
-    const bool upf = h->mg_upfused;
-    // down-leg stage of level Lv: residual of xin (scaled), restricted into Ln.rhs; with `presmooth` the pre-smoothing of
-    // the next level, Ln.x = omega M^-1 Ln.rhs, rides in the same launch when the fused kernels are usable
-    auto down = [&](HpLevel& Lv, bool fine, const double* xin, double scale, double* xout, HpLevel& Ln, bool presmooth) -> int {
-        if (upf && presmooth) {
-            HpMgResArgs m{xin, nullptr, xout, nullptr, Ln.rhs, scale, Ln.nz, Ln.dinv, Ln.cR, Ln.x};
-            void* p[] = {&d, &a, &Lv, &m};
-            return emit(e, hpk::desc_mg_down(h->cfg, Lv.nz), p, fine ? KIND_MG_RES0 : ckind(Lv));
-        }
-        if (res(Lv, fine, xin, nullptr, Ln.nz, xout, nullptr, Ln.rhs, scale)) return -1;
-        return presmooth ? line(Ln, false, Ln.rhs, nullptr, Ln.x, 0) : 0;
-    };
-    // post-smoothing of level l with coarse correction ec; returns where the smoothed correction was left
-    auto up_leg = [&](HpLevel& Lv, const double* ec, int nzc) -> const double* {
-        if (upf) return up(Lv, Lv.x, ec, nzc, Lv.x2) ? nullptr : Lv.x2;
-        if (res(Lv, false, Lv.x, ec, nzc, Lv.x2, Lv.tmp, nullptr, 1.0)) return nullptr;
-        if (line(Lv, false, Lv.tmp, Lv.x2, Lv.x, 0)) return nullptr;
-        return Lv.x;
-    };
-    // complete V-cycle on levels lo..n-1 of Ls (rhs of level lo given, Ls[lo].x = omega M^-1 rhs too if `presmoothed`);
-    // *top = where the correction of level lo is left
-    auto subcycle = [&](HpLevel* Ls, int lo, int n, bool presmoothed, const double** top) -> int {
-        const int c = n - 1;
-        if (!presmoothed && line(Ls[lo], false, Ls[lo].rhs, nullptr, Ls[lo].x, 0)) return -1;
-        for (int l = lo; l < c; ++l)
-            if (down(Ls[l], false, Ls[l].x, 1.0, nullptr, Ls[l + 1], true)) return -1;
-        const double* cur = Ls[c].x;
-        for (int k = 0; k < h->opts.mg_coarse_sweeps; ++k) {
-            if (upf) {
-                double* other = (cur == Ls[c].x) ? Ls[c].x2 : Ls[c].x;
-                if (up(Ls[c], cur, nullptr, 1, other)) return -1;
-                cur = other;
-            } else {
-                if (res(Ls[c], false, Ls[c].x, nullptr, 1, nullptr, Ls[c].tmp, nullptr, 1.0)) return -1;
-                if (line(Ls[c], false, Ls[c].tmp, Ls[c].x, Ls[c].x, 0)) return -1;
-            }
-        }
-        for (int l = c - 1; l >= lo; --l) {
-            cur = up_leg(Ls[l], cur, Ls[l + 1].nz);
-            if (!cur) return -1;
-        }
-        *top = cur;
-        return 0;
-    };
-    // same cycle in ONE cooperative launch (grid barriers instead of kernel boundaries) when the row-team shapes allow
-    auto fused = [&](HpLevel* Ls, int lo, int n, int part, const double* ec_top) -> int {
-        HpLevelSet ls;
-        ls.n = n;
-        for (int l = 0; l < n; ++l) ls.lev[l] = Ls[l];
-        HpSubcycleArgs sc{lo, n, h->opts.mg_coarse_sweeps, part, ec_top, h->gbar};
-        void* p[] = {&d, &a, &ls, &sc};
-        return emit(e, hpk::desc_mg_subcycle(h->cfg), p, KIND_MG_COARSE);
-    };
+    const size_t nr = d.nr;
     HpLevel* L = h->lev;
-    const int nl = h->nlev;
-    // level 0 starts from omega * zline (its pre-smoothing is k_cg_B's line solve)
-    const int s = nl - 1;                  // g_active: rows of local level s are one slice of the replicated global level 0
-    // level 1 is pre-smoothed here unless the cooperative cycle does it or it is the level handed to the global hierarchy
-    const bool pre1 = !h->mg_fused && !(h->g_active && s == 1);
-    if (down(L[0], true, d.z, a.omega, L[0].x2, L[1], pre1)) return -1;
-    const double* ec0 = L[1].x;          // coarse correction seen by level 0
-    if (!h->g_active) {
-        if (h->mg_fused ? fused(L, 1, nl, 0, nullptr) : subcycle(L, 1, nl, true, &ec0)) return -1;
-    } else {
-        if (h->mg_fused && s > 1) {
-            if (fused(L, 1, nl, 1, nullptr)) return -1;
+    const int nl = h->nlev, c = nl - 1;
+    const bool dist = h->nranks > 1 && d.p2p;
+    const bool upf = h->mg_upfused;
+    if (c + h->opts.mg_coarse_sweeps + c > HP_MAX_STAGES) return fail("mgline: too many stages for the flag table");
+    int next_slot = 0;
+    auto ckind = [&](int l) -> int { return l < 1 ? KIND_MG_RES0 : KIND_MG_L1 + (l > 5 ? 5 : l) - 1; };
+    // exchange descriptor of a stage that writes `field` (LV_X / LV_X2) of level l and reads ghost rows delivered by `wait`
+    auto xout = [&](int l, int field, int wait) -> HpXchg {
+        HpXchg x{nullptr, nullptr, -1, dist ? wait : -1};
+        if (!dist) return x;
+        x.sig = HP_COMM_STAGE0 + next_slot++;
+        if (h->rank > 0) x.push_lo = h->lv_lo + h->lay_lo.off[l][field] + (size_t)(h->lay_lo.nz[l] + 1) * nr;
+        if (h->rank < h->nranks - 1) x.push_hi = h->lv_hi + h->lay_hi.off[l][field];
+        return x;
+    };
+    auto xwait = [&](int wait) -> HpXchg { return HpXchg{nullptr, nullptr, -1, dist ? wait : -1}; };
+    auto res = [&](int l, const double* xin, const double* ec, int nzc, double* xo, double* resout, double* crhs, double scale,
+                   int xo_ghost, HpXchg xc) -> int {
+        HpMgResArgs m{xin, ec, xo, resout, crhs, scale, nzc, nullptr, nullptr, nullptr, xo_ghost, xc};
+        void* p[] = {&d, &a, &L[l], &m};
+        return emit(e, hpk::desc_mg_res(h->cfg, L[l].nz), p, ckind(l));
+    };
+    auto line = [&](int l, const double* rhs, const double* base, double* out, int fin, HpXchg xc) -> int {
+        HpMgLineArgs m{rhs, base, out, fin, xc};
+        void* p[] = {&d, &a, &L[l], &m};
+        return emit(e, hpk::desc_mg_line(h->cfg, L[l].nz), p, l == 0 ? KIND_MG_LINE0 : ckind(l));
+    };
+    auto field_of = [&](int l, const double* p) -> int { return p == L[l].x ? LV_X : LV_X2; };
+    int sig = -1;                       // slot of the stage that delivered the ghost rows of the array read next
+    // ---- down leg
+    for (int l = 0; l < c; ++l) {
+        HpLevel& Ln = L[l + 1];
+        const double* xin = l == 0 ? d.z : L[l].x;
+        const double scale = l == 0 ? a.omega : 1.0;
+        double* xo = l == 0 ? L[0].x2 : nullptr;
+        const int wait = l == 0 ? -1 : sig;             // level 0: the z ghost rows came with k_cg_B and its k_wait
+        if (upf) {
+            HpXchg xc = xout(l + 1, LV_X, wait);
+            HpMgResArgs m{xin, nullptr, xo, nullptr, Ln.rhs, scale, Ln.nz, Ln.dinv, Ln.cR, Ln.x, l == 0 ? 1 : 0, xc};
+            void* p[] = {&d, &a, &L[l], &m};
+            if (emit(e, hpk::desc_mg_down(h->cfg, L[l].nz), p, ckind(l))) return -1;
+            sig = xc.sig;
         } else {
-            for (int l = 1; l < s; ++l)
-                if (down(L[l], false, L[l].x, 1.0, nullptr, L[l + 1], l + 1 < s)) return -1;
+            if (res(l, xin, nullptr, Ln.nz, xo, nullptr, Ln.rhs, scale, l == 0 ? 1 : 0, xwait(wait))) return -1;
+            HpXchg xc = xout(l + 1, LV_X, -1);
+            if (line(l + 1, Ln.rhs, nullptr, Ln.x, 0, xc)) return -1;
+            sig = xc.sig;
         }
-        const int* skip = &d.st->mg_skip;
-        HpGatherArgs g{};
-        g.src[0] = L[s].rhs; g.dst_off[0] = h->g_off[0][4];
-        g.top_override = nullptr; g.override_idx = -1;
-        g.nsrc = 1; g.nrows = h->g_rows_mine; g.row0_dst = h->g_row0; g.kind = HP_COMM_GRHS;
-        void* pg[] = {&d, &g, &skip};
-        if (emit(e, hpk::desc_gather_rows(h->cfg, (long long)g.nrows * nr), pg, KIND_MG_COARSE)) return -1;
-        int kind = HP_COMM_GRHS;
-        void* pw[] = {&d, &kind, &skip};
-        if (emit(e, hpk::desc_wait_flag(), pw, KIND_MG_COARSE)) return -1;
-        const double* gtop = h->glev[0].x;
-        if (h->mg_fused ? fused(h->glev, 0, h->nglev, 0, nullptr) : subcycle(h->glev, 0, h->nglev, false, &gtop)) return -1;
-        const double* mine = gtop + (size_t)h->g_row0 * nr;              // my slice (ghost-inclusive indexing kept)
-        if (h->mg_fused && s > 1) {
-            if (fused(L, 1, nl, 2, mine)) return -1;
-        } else {
-            const double* cur = mine;
-            for (int l = s - 1; l >= 1; --l) {
-                cur = up_leg(L[l], cur, L[l + 1].nz);
-                if (!cur) return -1;
-            }
-            if (s > 1) ec0 = cur;
-        }
-        if (s == 1) ec0 = mine;
     }
-    if (res(L[0], true, L[0].x2, ec0, L[1].nz, d.z, L[0].tmp, nullptr, 1.0)) return -1;
-    if (line(L[0], true, L[0].tmp, d.z, d.z, 1)) return -1;
+    // ---- coarsest level
+    const double* cur = L[c].x;
+    for (int k = 0; k < h->opts.mg_coarse_sweeps; ++k) {
+        double* other = (cur == L[c].x) ? L[c].x2 : L[c].x;
+        if (upf) {
+            HpXchg xc = xout(c, field_of(c, other), sig);
+            HpMgResArgs m{cur, nullptr, other, nullptr, nullptr, 1.0, 1, nullptr, nullptr, nullptr, 0, xc};
+            void* p[] = {&d, &a, &L[c], &m};
+            if (emit(e, hpk::desc_mg_up(h->cfg, L[c].nz), p, ckind(c))) return -1;
+            sig = xc.sig;
+        } else {
+            if (res(c, cur, nullptr, 1, nullptr, L[c].tmp, nullptr, 1.0, 0, xwait(sig))) return -1;
+            HpXchg xc = xout(c, field_of(c, other), -1);
+            if (line(c, L[c].tmp, cur, other, 0, xc)) return -1;
+            sig = xc.sig;
+        }
+        cur = other;
+    }
+    // ---- up leg
+    for (int l = c - 1; l >= 1; --l) {
+        if (upf) {
+            HpXchg xc = xout(l, LV_X2, sig);
+            HpMgResArgs m{L[l].x, cur, L[l].x2, nullptr, nullptr, 1.0, L[l + 1].nz, nullptr, nullptr, nullptr, 0, xc};
+            void* p[] = {&d, &a, &L[l], &m};
+            if (emit(e, hpk::desc_mg_up(h->cfg, L[l].nz), p, ckind(l))) return -1;
+            sig = xc.sig;
+        } else {
+            if (res(l, L[l].x, cur, L[l + 1].nz, L[l].x2, L[l].tmp, nullptr, 1.0, 0, xwait(sig))) return -1;
+            HpXchg xc = xout(l, LV_X2, -1);
+            if (line(l, L[l].tmp, L[l].x2, L[l].x2, 0, xc)) return -1;
+            sig = xc.sig;
+        }
+        cur = L[l].x2;
+    }
+    // ---- level 0: z = xt + omega M^-1 (r - L xt); its boundary rows travel with the r.z reduction
+    if (res(0, L[0].x2, cur, L[1].nz, d.z, L[0].tmp, nullptr, 1.0, 0, xwait(sig))) return -1;
+    HpXchg xf{dist ? d.z_lo : nullptr, dist ? d.z_hi : nullptr, -1, -1};
+    if (line(0, L[0].tmp, d.z, d.z, 1, xf)) return -1;
     HpKArgs af = a;
     return emit_combine(e, af, 4);
 }
@@ -827,7 +798,8 @@ static bool same_opts(const hp_solve_opts& a, const hp_solve_opts& b) {
     return a.precond == b.precond && a.criterion == b.criterion && a.tol == b.tol && a.max_iter == b.max_iter &&
            a.loop_mode == b.loop_mode && a.refactor_every == b.refactor_every && a.extrapolate == b.extrapolate &&
            a.mg_levels == b.mg_levels && a.mg_coarse_sweeps == b.mg_coarse_sweeps && a.mg_omega == b.mg_omega &&
-           a.reuse_converged == b.reuse_converged;
+           a.reuse_converged == b.reuse_converged && a.while_unroll == b.while_unroll && a.mg_zscale == b.mg_zscale &&
+           a.peer_timeout_ms == b.peer_timeout_ms;
 }
 
 static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int update_old, GraphEntry** out) {
@@ -840,6 +812,7 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
     GraphEntry ge;
     ge.dt = dt; ge.sweeps = sweeps; ge.has_old = has_old; ge.update_old = update_old; ge.opts = h->opts;
     CK(cudaGraphCreate(&ge.graph, 0));
+    struct GraphGuard { cudaGraph_t g; ~GraphGuard() { if (g) cudaGraphDestroy(g); } } gguard{ge.graph};   // node-building failures
     NodeChain c{ge.graph};
     Emitter e{h, &c};
     HpDev& d = h->d;
@@ -859,7 +832,7 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
         cudaGraphNode_t n;
         CK(cudaGraphAddMemcpyNode1D(&n, ge.graph, c.last ? &c.last : nullptr, c.last ? 1 : 0, d.Told, d.T,
                                     (size_t)(d.nz + 2) * d.nr * sizeof(double), cudaMemcpyDeviceToDevice));
-        c.last = n; c.last_is_kernel = false;
+        c.last = n;
         // T_old moved: the first sweep of this step is not a repeat of the last sweep of the previous one
         cudaMemsetParams mp{};
         mp.dst = &d.st->noop_ok; mp.value = 0; mp.elementSize = 4; mp.width = 1; mp.height = 1; mp.pitch = 4;
@@ -886,28 +859,21 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
         cp.conditional.size = 1;
         cudaGraphNode_t wn;
         CK(cudaGraphAddNode(&wn, ge.graph, c.last ? &c.last : nullptr, c.last ? 1 : 0, &cp));
-        c.last = wn; c.last_is_kernel = false;
+        c.last = wn;
         NodeChain body{cp.conditional.phGraph_out[0]};
         Emitter eb{h, &body};
-        // HP_UNROLL=U (experiment, default 1): U iterations per pass of the WHILE node -- the evaluation of the node costs
-        // ~18 us, the kernels of iterations past convergence return at once (the protocol of the host-polled chunks)
-        static const int unroll = [] { const char* e = getenv("HP_UNROLL"); int u = e ? atoi(e) : 1; return u < 1 ? 1 : (u > 8 ? 8 : u); }();
+        // while_unroll = U iterations per pass of the WHILE node: evaluating the node costs ~18 us, the kernels of iterations
+        // past convergence return at once (the protocol of the host-polled chunks)
+        const int unroll = h->opts.while_unroll;
         for (int u = 0; u < unroll; ++u)
             if (emit_iteration(eb, a)) return -1;
         ge.body_nodes = body.count / unroll;
     }
     ge.static_nodes = c.count;
     {
-        cudaError_t ie = cudaGraphInstantiate(&ge.exec, ge.graph, 0);
-        if (ie != cudaSuccess && (h->pdl || (h->mg_fused && h->opts.precond == 2))) {
-            // programmatic edges / cooperative nodes not accepted in this graph shape: rebuild without them
-            cudaGetLastError();
-            cudaGraphDestroy(ge.graph);
-            if (h->pdl) h->pdl = false; else h->mg_fused = false;
-            return get_graph(h, dt, sweeps, has_old, update_old, out);
-        }
-        CK(ie);
+        CK(cudaGraphInstantiate(&ge.exec, ge.graph, 0));
     }
+    gguard.g = nullptr;
     h->graphs.push_back(ge);
     *out = &h->graphs.back();
     return 0;
@@ -919,6 +885,7 @@ static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int upd
 static int run_steps(hp_solver_s* h, double dt, int n_steps, int sweeps, int has_old, int is_step) {
     if (!(dt > 0.0)) return fail("dt must be > 0");
     if (sweeps < 1) return fail("sweeps must be >= 1");
+    if (check_fault(h)) return -1;
     const int max_order = is_step ? (h->opts.extrapolate > 3 ? 3 : h->opts.extrapolate) : 0;
     const bool ext = max_order > 0;
     if (ext && h->hist_dt != dt) { if (h->hist > 1) h->hist = 1; h->hist_dt = dt; }     // increments scale with dt
@@ -938,7 +905,7 @@ static int run_steps(hp_solver_s* h, double dt, int n_steps, int sweeps, int has
         return o;
     };
     // re-sweep correction tracking (see k_delta / k_stash): needs a second sweep to stash the first-sweep solution at
-    const bool track = ext && sweeps >= 2 && h->c2_on;
+    const bool track = ext && sweeps >= 2;
     if (track && !h->d.c2) {
         const size_t bytes = h->field_elems * sizeof(double);
         if (dev_alloc(h, (void**)&h->d.c2, bytes)) return -1;
@@ -1016,15 +983,10 @@ int hp_run_host(hp_handle h, const double* h_T_in, double* h_T_out, double dt, i
     return hp_get_T_host(h, h_T_out);
 }
 
-static int fetch_state(hp_solver_s* h) {
-    CK(cudaMemcpyAsync(h->h_state, h->d.st, sizeof(HpState), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    return 0;
-}
-
 int hp_get_stats(hp_handle h, hp_sweep_stat* out, int max_n) {
     if (!h || !out || max_n < 1) { fail("hp_get_stats: bad argument"); return -1; }
     if (fetch_state(h)) return -1;
+    if (check_fault(h)) return -1;
     long long total = h->h_state->sweep_count;
     long long n = total < max_n ? total : max_n;
     if (n > HP_STATS_CAP) n = HP_STATS_CAP;
@@ -1109,45 +1071,15 @@ int hp_peer_export(hp_handle h, const int32_t* nz_of_rank, void* out256) {
         if (dev_alloc(h, (void**)&d.seq, sizeof(unsigned long long) * HP_COMM_KINDS)) return -1;
         CK(cudaMemset(d.seq, 0, sizeof(unsigned long long) * HP_COMM_KINDS));
     }
-    // shape of the replicated global coarse hierarchy (identical on every rank: it only depends on nz_of_rank, nr, opts)
     h->nz_of_rank.assign(nz_of_rank, nz_of_rank + h->nranks);
-    int s_min = HP_MAX_LEVELS;
-    for (int r = 0; r < h->nranks; ++r) {
-        int c = local_level_count(nz_of_rank[r], h->opts.mg_levels) - 1;
-        if (c < s_min) s_min = c;
-    }
-    h->g_switch = s_min;
-    int M = 0;
-    for (int r = 0; r < h->nranks; ++r) {
-        if (r == h->rank) h->g_row0 = M;
-        M += rows_at_level(nz_of_rank[r], s_min);
-    }
-    h->g_rows_mine = rows_at_level(nz_of_rank[h->rank], s_min);
-    h->nglev = 0;
-    size_t elems = 0;
-    for (int rows = M; h->nglev < HP_MAX_LEVELS; rows = (rows + 1) / 2) {
-        h->glev[h->nglev].nz = rows;
-        for (int k = 0; k < 8; ++k) { h->g_off[h->nglev][k] = (long long)elems; elems += (size_t)(rows + 2) * d.nr + 64; }
-        h->nglev++;
-        if (rows < 32) break;
-    }
-    if (!h->gblock) {
-        h->gblock_elems = elems;
-        if (dev_alloc(h, (void**)&h->gblock, elems * sizeof(double))) return -1;
-        CK(cudaMemset(h->gblock, 0, elems * sizeof(double)));
-    } else if (elems != h->gblock_elems) {
-        return fail("hp_peer_export: called twice with different shapes");
-    }
-    for (int g = 0; g < h->nglev; ++g) {
-        double** f[] = {&h->glev[g].cR, &h->glev[g].cZ, &h->glev[g].diag, &h->glev[g].dinv,
-                        &h->glev[g].rhs, &h->glev[g].x, &h->glev[g].x2, &h->glev[g].tmp};
-        for (int k = 0; k < 8; ++k) *f[k] = h->gblock + h->g_off[g][k];
-    }
+    if (nz_of_rank[h->rank] != d.nz) return fail("hp_peer_export: nz_of_rank[rank] differs from this handle's row count");
+    if (ensure_levels(h)) return -1;            // the coarse-level block the neighbours push their boundary rows into
+    CK(cudaStreamSynchronize(h->stream));
     cudaIpcMemHandle_t hd[4];
     CK(cudaIpcGetMemHandle(&hd[0], h->comm));
     CK(cudaIpcGetMemHandle(&hd[1], h->qz_block));
     CK(cudaIpcGetMemHandle(&hd[2], d.T));
-    CK(cudaIpcGetMemHandle(&hd[3], h->gblock));
+    CK(cudaIpcGetMemHandle(&hd[3], h->lvblock));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     memcpy(out256, hd, sizeof(hd));
     return 0;
@@ -1163,28 +1095,30 @@ int hp_peer_import(hp_handle h, const void* all_handles, const int32_t* nz_of_ra
     HpDev& d = h->d;
     const size_t nr = d.nr;
     for (int r = 0; r < h->nranks; ++r) {
-        if (r == h->rank) { d.comm_peer[r] = h->comm; d.gblock_peer[r] = h->gblock; continue; }
+        if (r == h->rank) { d.comm_peer[r] = h->comm; continue; }
         void* p = nullptr;
         CK(cudaIpcOpenMemHandle(&p, hd[4 * r + 0], cudaIpcMemLazyEnablePeerAccess));
         h->ipc_opened.push_back(p);
         d.comm_peer[r] = (HpComm*)p;
-        CK(cudaIpcOpenMemHandle(&p, hd[4 * r + 3], cudaIpcMemLazyEnablePeerAccess));
-        h->ipc_opened.push_back(p);
-        d.gblock_peer[r] = (double*)p;
     }
+    h->nz_of_rank.assign(nz_of_rank, nz_of_rank + h->nranks);
+    h->lv_lo = h->lv_hi = nullptr;
     d.z_lo = d.z_hi = d.T_lo = d.T_hi = nullptr;
-    auto open_nb = [&](int r, double** qz, double** T) -> int {
+    auto open_nb = [&](int r, double** qz, double** T, double** lv) -> int {
         void* p = nullptr;
         CK(cudaIpcOpenMemHandle(&p, hd[4 * r + 1], cudaIpcMemLazyEnablePeerAccess));
         h->ipc_opened.push_back(p); *qz = (double*)p;
         CK(cudaIpcOpenMemHandle(&p, hd[4 * r + 2], cudaIpcMemLazyEnablePeerAccess));
         h->ipc_opened.push_back(p); *T = (double*)p;
+        CK(cudaIpcOpenMemHandle(&p, hd[4 * r + 3], cudaIpcMemLazyEnablePeerAccess));
+        h->ipc_opened.push_back(p); *lv = (double*)p;
         return 0;
     };
     if (h->rank > 0) {                       // lower neighbour: its UPPER ghost row (nz_lo + 1) mirrors my row 1
         const int r = h->rank - 1;
         double *qz, *T;
-        if (open_nb(r, &qz, &T)) return -1;
+        if (open_nb(r, &qz, &T, &h->lv_lo)) return -1;
+        h->lay_lo = level_layout(nz_of_rank[r], d.nr);
         const size_t felems = (size_t)(nz_of_rank[r] + 2) * nr + 64;
         d.z_lo = qz + felems + (size_t)(nz_of_rank[r] + 1) * nr;
         d.T_lo = T + (size_t)(nz_of_rank[r] + 1) * nr;
@@ -1192,7 +1126,8 @@ int hp_peer_import(hp_handle h, const void* all_handles, const int32_t* nz_of_ra
     if (h->rank < h->nranks - 1) {           // upper neighbour: its LOWER ghost row (0) mirrors my row nz
         const int r = h->rank + 1;
         double *qz, *T;
-        if (open_nb(r, &qz, &T)) return -1;
+        if (open_nb(r, &qz, &T, &h->lv_hi)) return -1;
+        h->lay_hi = level_layout(nz_of_rank[r], d.nr);
         const size_t felems = (size_t)(nz_of_rank[r] + 2) * nr + 64;
         d.z_hi = qz + felems;
         d.T_hi = T;
@@ -1200,7 +1135,28 @@ int hp_peer_import(hp_handle h, const void* all_handles, const int32_t* nz_of_ra
     d.p2p = 1;
     h->ghost_dirty = true;
     destroy_graphs(h);
-    if (h->opts.precond == 2 && setup_mg(h)) return -1;      // switch the cycle to the replicated global coarse levels
+    if (h->opts.precond == 2) {                              // the cycle becomes the distributed whole-mesh hierarchy
+        if (setup_mg(h)) return -1;
+        if (h->nlev < 2) h->opts.precond = 1;
+    }
+    return 0;
+}
+
+int hp_comm_fault(hp_handle h) { return (h && h->h_fault && *(volatile int*)h->h_fault) ? 1 : 0; }
+
+int hp_comm_clear_fault(hp_handle h) {
+    if (!h) return fail("null handle");
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->comm) {
+        CK(cudaMemset(h->comm, 0, sizeof(HpComm)));
+        CK(cudaMemset(h->d.seq, 0, sizeof(unsigned long long) * HP_COMM_KINDS));
+    }
+    if (fetch_state(h)) return -1;
+    HpState st = *h->h_state;
+    st.flags &= ~8; st.cycle = 0; st.ticket = 0; st.done = 1; st.mg_skip = 1;
+    CK(cudaMemcpy(h->d.st, &st, sizeof(HpState), cudaMemcpyHostToDevice));
+    if (h->h_fault) *(volatile int*)h->h_fault = 0;
+    h->ghost_dirty = true;
     return 0;
 }
 

@@ -9,7 +9,8 @@
 #define HP_NRED 4                // reduced values per kernel
 
 #define HP_MAX_RANKS 16
-enum { HP_COMM_DIAG = 0, HP_COMM_A = 1, HP_COMM_B = 2, HP_COMM_MG = 3, HP_COMM_GOP = 4, HP_COMM_GRHS = 5, HP_COMM_KINDS = 6 };
+#define HP_MAX_STAGES 40         // stages of one V-cycle that hand boundary rows to the neighbouring slabs
+enum { HP_COMM_DIAG = 0, HP_COMM_A = 1, HP_COMM_B = 2, HP_COMM_MG = 3, HP_COMM_STAGE0 = 4, HP_COMM_KINDS = 4 + HP_MAX_STAGES };
 
 // Peer-memory mailbox of one rank (cudaMalloc'ed, IPC-mapped into every peer of the box over NVLink).
 // red[kind][src] / flag[kind][src] are WRITTEN BY rank `src` (remote stores from its reducing kernel) and read locally.
@@ -31,6 +32,7 @@ struct HpState {
     int32_t mg_init;     // 1 -> the next V-cycle is the first of its sweep (its last kernel starts the rz recurrence: no beta)
     unsigned int ticket; // last-CTA election
     unsigned int _pad2;
+    unsigned long long cycle;   // V-cycles started so far (sequence number of the stage flags between neighbouring slabs)
     long long sweep_count;
     long long total_iters;
     // A sweep that converged at its INIT decision (no iteration, no shifted start) left T, r, diag and the decision inputs
@@ -74,7 +76,8 @@ struct HpDev {
     int p2p;
     HpComm* comm_peer[HP_MAX_RANKS];   // every rank's mailbox (own one included) as seen from this GPU
     unsigned long long* seq;           // [HP_COMM_KINDS] how many times this rank has produced each kind
-    double* gblock_peer[HP_MAX_RANKS]; // every rank's block of replicated global coarse levels (mgline under slabs)
+    int mg_local;                      // 1: the V-cycle ignores the couplings to the ghost rows (slabs without peer memory)
+    int* fault_host;                   // pinned host word (mapped): set when a wait for a peer timed out
     double *z_lo, *z_hi;               // neighbour's z ghost row that mirrors my first / last owned row (or null)
     double *T_lo, *T_hi;               // same for the field T
     double* red_local;       // [HP_NRED]
@@ -92,14 +95,13 @@ struct HpLevel {
 
 struct HpLevelSet { int n; HpLevel lev[2 * HP_MAX_LEVELS]; };   // entry 0 is skipped by k_factor_levels
 
-// k_gather_rows: this rank's rows of up to 3 level arrays -> the same rows of EVERY rank's replicated global level
-struct HpGatherArgs {
-    const double* src[3];        // ghost-inclusive local arrays (row 1 = first owned row)
-    long long dst_off[3];        // element offset of the destination array inside a rank's gblock
-    const double* top_override;  // if set: replaces the LAST owned row of src[override_idx] (interface coupling)
-    int override_idx;
-    int nsrc, nrows, row0_dst;   // rows to copy, first destination row (owned index) in the global level
-    int kind;                    // HP_COMM_* flag signalled to every rank when all rows are stored
+// Hand-over of the two boundary rows a V-cycle stage produces to the neighbouring slabs (peer-memory stores fused into
+// the producing kernel) and the wait of the consuming stage, fused into its first / last row team.
+struct HpXchg {
+    double* push_lo;     // lower neighbour's ghost row that mirrors the first row of this stage's output (or null)
+    double* push_hi;     // upper neighbour's ghost row that mirrors the last row (or null)
+    int sig;             // >= 0: flag slot HP_COMM_STAGE0 + k raised at the neighbours once the rows are stored
+    int wait;            // >= 0: flag slot of the stage whose rows this kernel reads from its ghost rows
 };
 
 // arguments of k_mg_res / k_mg_line (hp_kernels.cu)
@@ -107,18 +109,12 @@ struct HpMgResArgs {
     const double* xin; const double* ec; double* xout; double* resout; double* crhs;
     double scale; int nzc;
     const double* c_dinv; const double* c_cR; double* c_x;     // k_mg_fused MODE 2: pivots / couplings / correction of level+1
+    int xout_ghost;      // also write the two ghost rows of xout (the scaled iterate of the level-0 down stage)
+    HpXchg xc;
 };
 struct HpMgLineArgs {
     const double* rhs; const double* base; double* out; int final_;
-};
-
-// k_mg_subcycle: the complete V-cycle on levels lo..n-1 of a level set in ONE cooperative launch (grid barriers between
-// the stages instead of kernel boundaries: the coarse levels are launch-latency bound)
-struct HpSubcycleArgs {
-    int lo, n, sweeps;
-    int part;                   // 0 whole cycle; 1 down leg only (levels lo..n-2: smooth, restrict); 2 up leg only
-    const double* ec_top;       // part 2: correction prolonged into level n-2 (a slice of the replicated global level 0)
-    unsigned long long* gbar;   // [0] arrival counter (monotonic), [1] its value at the start of the next launch
+    HpXchg xc;
 };
 
 // Per-launch scalar arguments shared by all kernels: signature (HpDev, hp_phys, HpKArgs [, extra]).
@@ -129,7 +125,7 @@ struct HpKArgs {
     int32_t max_iter;
     int32_t criterion;
     int32_t use_cond;
-    int32_t prefetch;          // bit0: k_cg_A, bit1: k_cg_B issue bulk L2 prefetches of the next row
+    int32_t _pad1;
     int32_t mg;                // 1: 'mgline' preconditioner: k_cg_B only decides convergence, the V-cycle's last kernel
                                //    produces z, r.z and advances the recurrences
     int32_t init_phase;        // (unused since the V-cycle opens the loop body: HpState.mg_init tells the first cycle of a sweep)
@@ -139,6 +135,7 @@ struct HpKArgs {
     int32_t noop_enable;       // k_diag / INIT kernel may take the bookkeeping-only path (single GPU, no debug outputs, no shift)
     int32_t shift;             // 1: this (A, B) pair moves the start of the solve to x0 + z (z = extrapolated increment):
                                //    alpha := 1, and k_cg_B finalises like the INIT kernel
+    unsigned long long timeout_ns;   // bound of every wait for a peer flag
     unsigned long long cond;   // cudaGraphConditionalHandle of the enclosing WHILE node (use_cond != 0)
     double* rhs_out;           // optional (debug): full rhs, ghost-inclusive layout
 };
@@ -159,7 +156,6 @@ struct HpKernelLaunch {
     const void* func;
     dim3 grid, block;
     size_t smem;
-    bool cooperative = false;   // all CTAs must be co-resident (grid barriers inside)
 };
 
 namespace hpk {
@@ -177,16 +173,13 @@ HpKernelLaunch desc_factor(const HpLaunchCfg&, const HpDev&);
 HpKernelLaunch desc_cg_init(const HpLaunchCfg&, const HpDev&, int precond, int criterion);
 HpKernelLaunch desc_cg_A(const HpLaunchCfg&, const HpDev&);
 // 'mgline' V-cycle pieces (argument lists next to the kernels in hp_kernels.cu)
-HpKernelLaunch desc_mg_coarsen(const HpLaunchCfg&, int nzc, int nr);
+HpKernelLaunch desc_mg_coarsen(const HpLaunchCfg&, int nzc, int nr);   // args: (HpLevel f, HpLevel c, int nr, double zscale, int keep_ghost, const int* skip)
 HpKernelLaunch desc_mg_res(const HpLaunchCfg&, int nz_level);
 HpKernelLaunch desc_mg_line(const HpLaunchCfg&, int nz_level);
 HpKernelLaunch desc_mg_down(const HpLaunchCfg&, int nz_level);   // same args: residual + restriction + pre-smoothing of level+1
 HpKernelLaunch desc_mg_up(const HpLaunchCfg&, int nz_level);     // args: (HpDev, HpKArgs, HpLevel, HpMgResArgs): fused prolong+residual+smooth
-HpKernelLaunch desc_mg_subcycle(const HpLaunchCfg&);            // args: (HpDev, HpKArgs, HpLevelSet, HpSubcycleArgs); cooperative
-bool mg_subcycle_supported(const HpLaunchCfg&);
+bool mg_fused_supported(const HpLaunchCfg&);
 HpKernelLaunch desc_factor_levels(int total_coarse_rows);   // args: (HpLevelSet, int nr, const int* skip)
-HpKernelLaunch desc_gather_rows(const HpLaunchCfg&, long long elems);  // args: (HpDev, HpGatherArgs, const int* skip)
-HpKernelLaunch desc_wait_flag();                                        // args: (HpDev, int kind, const int* skip)
 HpKernelLaunch desc_wait();       // args: (HpDev, hp_phys, HpKArgs, int kind): peer-memory variant of finalize
 HpKernelLaunch desc_finalize();   // args: (HpDev, hp_phys, HpKArgs, int kind) kind: 0 diag, 1 A, 2 B, 3 init
 HpKernelLaunch desc_cg_B(const HpLaunchCfg&, const HpDev&, int precond, int criterion);

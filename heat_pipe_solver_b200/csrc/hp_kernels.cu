@@ -26,26 +26,11 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
-// Programmatic dependent launch: inside the step graph consecutive kernel nodes are linked by programmatic edges, so a
-// kernel may be scheduled while its predecessor drains.  EVERY kernel starts with this: it blocks until the predecessor
-// grid has completed and its writes are visible, then lets its own successor be scheduled early.  Without the edge
-// (plain stream launches) both instructions are no-ops.
-__device__ __forceinline__ void pdl_enter() {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
-
 __device__ __forceinline__ void ld256(const double* p, double* v) {
     asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
 __device__ __forceinline__ void st256(double* p, const double* v) {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
-}
-
-// TMA-class bulk prefetch of one contiguous row into L2 (one instruction, no registers, no smem):
-// the next row of every streamed field is requested while the current row is being processed.
-__device__ __forceinline__ void prefetch_row_l2(const double* row, int nr) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"(nr * 8) : "memory");
 }
 
 template <int EPT, bool VEC>
@@ -229,6 +214,7 @@ __device__ __forceinline__ void finalize_B(const HpDev& d, const HpKArgs& a, boo
     else if (s->iter >= a.max_iter) { done = 1; flags |= 2; }
     s->done = done; s->flags = flags;
     s->mg_skip = done;
+    if (stage == 1 && !done) s->cycle += 1;      // a V-cycle follows: sequence number of its stage flags (same on every rank)
     // converged before any iteration, from the un-shifted start: nothing of the sweep's inputs or outputs moved
     if (init && !a.shift && flags == 1 && s->iter == 0) { s->noop_ok = 1; s->noop_dt = a.dt; s->noop_has_old = a.has_old; }
     else s->noop_ok = 0;
@@ -274,11 +260,28 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
+// a wait for a peer gave up: sticky bit3 of the sweep flags + the host-visible fault word (every later API call on the handle
+// fails until hp_comm_clear_fault)
+__device__ __forceinline__ void raise_fault(const HpDev& d) {
+    atomicOr(&d.st->flags, 8);
+    if (d.fault_host) { *(volatile int*)d.fault_host = 1; __threadfence_system(); }
+}
+// bounded wait until the flag `slot` written by rank `src` into this rank's mailbox reaches `want`
+__device__ __forceinline__ bool wait_peer_flag(const HpDev& d, const HpKArgs& a, int slot, int src, unsigned long long want) {
+    const unsigned long long* f = &d.comm_peer[d.rank]->flag[slot][src];
+    if (ld_acquire_sys(f) >= want) return true;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(f) < want) {
+        if (global_ns() - t0 > a.timeout_ns) return false;
+        __nanosleep(32);
+    }
+    return true;
+}
+
 // k_wait: one warp; lane r waits until rank r's flag of `kind` reaches this rank's own production count (all ranks run
 // the same kernel sequence), then lane 0 combines the sums in rank order and advances the scalar recurrences.
-// A bounded wait (2 s): on timeout the sweep is aborted with flags bit3 instead of hanging the GPU.
+// The wait is bounded (hp_solve_opts.peer_timeout_ms): on timeout the sweep is aborted and the handle's fault is raised.
 __global__ void k_wait(HpDev d, hp_phys ph, HpKArgs a, int fin_kind) {
-    pdl_enter();
     const int kind = (fin_kind == FIN_DIAG) ? HP_COMM_DIAG : (fin_kind == FIN_A ? HP_COMM_A : (fin_kind == FIN_MGFINAL ? HP_COMM_MG : HP_COMM_B));
     HpState* s = d.st;
     if ((fin_kind == FIN_A || fin_kind == FIN_B) && s->done) return;
@@ -287,15 +290,10 @@ __global__ void k_wait(HpDev d, hp_phys ph, HpKArgs a, int fin_kind) {
     const HpComm* mine = d.comm_peer[d.rank];
     const unsigned long long want = d.seq[kind];
     bool ok = true;
-    if (lane < d.nranks && !(s->flags & 8)) {
-        const unsigned long long t0 = global_ns();
-        while (ld_acquire_sys(&mine->flag[kind][lane]) < want) {
-            if (global_ns() - t0 > 2000000000ull) { ok = false; break; }
-            __nanosleep(64);
-        }
-    }
+    if (lane < d.nranks && !(s->flags & 8)) ok = wait_peer_flag(d, a, kind, lane, want);
     const unsigned bad = __ballot_sync(0xffffffffu, !ok);
     if (lane != 0) return;
+    (void)mine;
     double v[HP_NRED] = {0.0, 0.0, 0.0, 0.0};
     for (int r = 0; r < d.nranks; ++r) {
         const volatile double* p = mine->red[kind][r];
@@ -308,14 +306,14 @@ __global__ void k_wait(HpDev d, hp_phys ph, HpKArgs a, int fin_kind) {
     else if (fin_kind == FIN_MGFINAL) finalize_B(d, a, a.init_phase != 0, v[0], 0.0, 0.0, 2);
     else finalize_B(d, a, fin_kind == FIN_INIT || a.shift, v[0], v[1], v[2], a.mg ? 1 : 0);
     if (bad || (s->flags & 8)) {          // a peer never arrived: stop this sweep, make the failure sticky
-        s->flags |= 8; s->done = 1;
+        raise_fault(d);
+        s->done = 1; s->mg_skip = 1;
         d.stats[(s->sweep_count - 1) % HP_STATS_CAP].flags |= 8;
         set_cond(a, 0);
     }
 }
 
 __global__ void k_finalize(HpDev d, hp_phys ph, HpKArgs a, int kind) {
-    pdl_enter();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if ((kind == FIN_A || kind == FIN_B) && d.st->done) return;
     if (kind == FIN_MGFINAL && d.st->mg_skip) return;
@@ -373,7 +371,6 @@ __device__ __forceinline__ double k_outface(const HpDev& d, const hp_phys& ph, i
 // k_snapshot_kout : k0_out[g] = k(outer face, T_amb[g])                       grid: rows
 // ------------------------------------------------------------------------------------------------
 __global__ void k_snapshot_kout(HpDev d, hp_phys ph, HpKArgs a, double* k0_out) {
-    pdl_enter();
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < d.nz + 2) k0_out[g] = k_outface(d, ph, g, d.Tamb_line[g]);
 }
@@ -385,7 +382,6 @@ __global__ void k_snapshot_kout(HpDev d, hp_phys ph, HpKArgs a, double* k0_out) 
 //   wf = r_v, wc = r_c on CylindricalGrid2D (areas / volumes per radian); 1 on a Cartesian Grid2D
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_coef(HpDev d, hp_phys ph, HpKArgs a) {
-    pdl_enter();
     const long long n = (long long)(d.nz + 1) * d.nr;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -417,7 +413,6 @@ __global__ void __launch_bounds__(256) k_coef(HpDev d, hp_phys ph, HpKArgs a) {
 // ------------------------------------------------------------------------------------------------
 constexpr int DIAG_U = 4;      // cells per thread whose loads are issued before any of their (long, fp64) property chains
 __global__ void __launch_bounds__(256, 2) k_diag(HpDev d, hp_phys ph, HpKArgs a, int write_dinv_jacobi, int tpr_log2) {
-    pdl_enter();
     // rows over CTAs (and over row groups inside a CTA when a row is shorter than the CTA), columns over threads:
     // no integer division per cell, per-row quantities read once
     const int nr = d.nr;
@@ -541,7 +536,6 @@ __device__ __forceinline__ void factor_row(const double* __restrict__ dg, const 
 }
 
 __global__ void __launch_bounds__(32) k_factor_rline(HpDev d, hp_phys ph, HpKArgs a) {
-    pdl_enter();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= d.nz) return;
     const long long base = (long long)(j + 1) * d.nr;
@@ -576,7 +570,7 @@ __device__ __forceinline__ void team_barrier(int team_in_cta) {
     if constexpr (TPL > 32) {
         asm volatile("bar.sync %0, %1;" ::"r"(team_in_cta + 1), "r"(TPL) : "memory");
     } else {
-        __syncwarp();
+        __syncwarp(team_mask<TPL>());
     }
 }
 
@@ -662,7 +656,6 @@ __device__ __forceinline__ void line_solve(const double (&rv)[EPT], const double
 // last CTA: alpha = rz/pq, parity ^= 1, first = 0
 template <int TPL, int EPT, bool VEC, int MINB = TeamGeom<TPL>::minb_A(EPT)>
 __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, MINB) k_cg_A(HpDev d, hp_phys ph, HpKArgs a) {
-    pdl_enter();
     using G = TeamGeom<TPL>;
     const HpState s0 = *d.st;
     if (s0.done) return;
@@ -716,13 +709,6 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, MINB) k_cg_A(HpDev d, hp_p
         if (ja == 0) store_row<EPT, VEC>(pout, i0, nr, pm);                      // lower ghost row
         for (int g = ja + 1; g <= jb; ++g) {
             const long long rb = (long long)g * nr;
-            if (VEC && tl == 0 && g < jb && (a.prefetch & 1)) {
-                prefetch_row_l2(zf + rb + 2 * (long long)nr, nr);
-                if (!first) prefetch_row_l2(pin + rb + 2 * (long long)nr, nr);
-                prefetch_row_l2(d.cR + rb + nr, nr);
-                prefetch_row_l2(d.cZ + rb + nr, nr);
-                prefetch_row_l2(d.diag + rb + nr, nr);
-            }
             // ---- every load of this row is issued before the first use ----
             double zz[EPT], pp[EPT], cr[EPT], cz[EPT], dg[EPT];
             load_row<EPT, VEC>(zf + rb + nr, i0, nr, zz);
@@ -782,7 +768,6 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, MINB) k_cg_A(HpDev d, hp_p
 // last CTA: beta = rz_new/rz, iter++, convergence flag, sweep statistics, WHILE condition
 template <int TPL, int EPT, bool VEC, bool RLINE, bool INIT>
 __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT)) k_cg_B(HpDev d, hp_phys ph, HpKArgs a) {
-    pdl_enter();
     using G = TeamGeom<TPL>;
     const HpState s0 = *d.st;
     if (!INIT && s0.done) return;
@@ -806,16 +791,6 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT)
     double acc[3] = {0.0, 0.0, 0.0};   // rz, rr, crit(max)
     for (int g = ja + 1; g <= jb; ++g) {
         const long long rb = (long long)g * nr;
-        if (VEC && tl == 0 && g < jb && (a.prefetch & 2)) {             // next row of every streamed field -> L2
-            prefetch_row_l2(d.r + rb + nr, nr);
-            prefetch_row_l2(d.dinv + rb + nr, nr);
-            if constexpr (RLINE) prefetch_row_l2(d.cR + rb + nr, nr);
-            if constexpr (!INIT) {
-                prefetch_row_l2(d.T + rb + nr, nr);
-                prefetch_row_l2(pcur + rb + nr, nr);
-                prefetch_row_l2(d.q + rb + nr, nr);
-            }
-        }
         // ---- every load of this row is issued before the first store / use (the vector loads and stores are
         //      volatile asm and keep program order: a load placed after a store would wait for a full extra
         //      DRAM round trip) ----
@@ -855,7 +830,7 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT)
                                  s_bA[team_in_cta], s_bB[team_in_cta], zv);
         }
         store_row<EPT, VEC>(d.z + rb, i0, nr, zv);
-        if (d.p2p && !a.mg) {   // halo of the preconditioned residual, fused into its producer
+        if (d.p2p) {            // halo of the (line-)preconditioned residual, fused into its producer
             if (g == 1 && d.z_lo) store_row<EPT, VEC>(d.z_lo, i0, nr, zv);
             if (g == nz && d.z_hi) store_row<EPT, VEC>(d.z_hi, i0, nr, zv);
         }
@@ -884,7 +859,6 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT)
 // auxiliary kernels
 // ------------------------------------------------------------------------------------------------
 __global__ void k_eval_property(hp_phys ph, int id, const double* __restrict__ T, double* __restrict__ out, long long n) {
-    pdl_enter();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = hp::eval_property(ph, id, T[i]);
 }
@@ -892,7 +866,6 @@ __global__ void k_eval_property(hp_phys ph, int id, const double* __restrict__ T
 // rho, cp per owned cell; kavg = mean of k over the cell's 4 faces (main.py:243: k.value[cellFaceIDs] mean)
 __global__ void k_cell_fields(HpDev d, hp_phys ph, double* __restrict__ rho_o, double* __restrict__ cp_o,
                               double* __restrict__ kavg_o) {
-    pdl_enter();
     const long long n = (long long)d.nz * d.nr;
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(c / d.nr), i = (int)(c - (long long)j * d.nr), g = j + 1;
@@ -924,14 +897,12 @@ __global__ void k_cell_fields(HpDev d, hp_phys ph, double* __restrict__ rho_o, d
 
 // rhs (owned rows, compact nz*nr) from a ghost-inclusive scratch array
 __global__ void k_copy_owned(const double* __restrict__ src_ghost, double* __restrict__ dst, int nr, long long n) {
-    pdl_enter();
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x)
         dst[c] = src_ghost[c + nr];
 }
 
 // field[g,:] = Tamb_line[g] for all rows incl. ghosts  (main.py:34,152)
 __global__ void k_fill_rows(HpDev d, double* __restrict__ field) {
-    pdl_enter();
     const long long n = (long long)(d.nz + 2) * d.nr;
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x)
         field[c] = d.Tamb_line[(int)(c / d.nr)];
@@ -949,7 +920,6 @@ __global__ void k_fill_rows(HpDev d, double* __restrict__ field) {
 // here C_n is formed, the history is built from the first-sweep increments D_n = S1_n - F_{n-1} (so the prediction aims
 // at S1_{n+1}, what the first solve actually converges to), and c2 <- C_n is the predicted start of the second sweep.
 __global__ void __launch_bounds__(256) k_delta(HpDev d, hp_phys ph, HpKArgs a) {
-    pdl_enter();
     const long long n = (long long)(d.nz + 2) * d.nr;
     const int ord = a.ext_order;
     if (blockIdx.x == 0 && threadIdx.x == 0) d.st->noop_ok = 0;         // T_old moves
@@ -977,72 +947,10 @@ __global__ void __launch_bounds__(256) k_delta(HpDev d, hp_phys ph, HpKArgs a) {
 // head of the second sweep of a step (T = S1_n, every row incl. ghosts): z <- C_{n-1} as the predicted increment of this
 // sweep (applied by the shift pair), c2 <- S1_n for k_delta of the next step
 __global__ void __launch_bounds__(256) k_stash(HpDev d, hp_phys ph, HpKArgs a) {
-    pdl_enter();
     const long long n = (long long)(d.nz + 2) * d.nr;
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
         if (a.c2_valid) d.z[c] = d.c2[c];
         d.c2[c] = d.T[c];
-    }
-}
-
-// ---- replicated global coarse levels under slabs ---------------------------------------------------------------------
-// signal `kind` to every rank (sequence flag, release at system scope); called by ONE thread after the data stores of the
-// whole grid are ordered before it (system fence + ticket in every CTA)
-__device__ __forceinline__ void signal_all(const HpDev& d, int kind) {
-    const unsigned long long sq = d.seq[kind] + 1ull;
-    d.seq[kind] = sq;
-    __threadfence_system();
-    for (int r = 0; r < d.nranks; ++r) {
-        unsigned long long* f = &d.comm_peer[r]->flag[kind][d.rank];
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(sq) : "memory");
-    }
-}
-
-__global__ void __launch_bounds__(256) k_gather_rows(HpDev d, HpGatherArgs g, const int* skip) {
-    pdl_enter();
-    if (*skip) return;
-    const long long per = (long long)g.nrows * d.nr, n = per * g.nsrc;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(t / per);
-        const long long e = t - (long long)k * per;
-        const int row = (int)(e / d.nr), i = (int)(e - (long long)row * d.nr);
-        double v = g.src[k][(long long)(row + 1) * d.nr + i];
-        if (g.top_override && k == g.override_idx && row == g.nrows - 1) v = g.top_override[i];
-        const long long off = g.dst_off[k] + (long long)(g.row0_dst + row + 1) * d.nr + i;
-        for (int r = 0; r < d.nranks; ++r) d.gblock_peer[r][off] = v;
-    }
-    __shared__ int s_last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        s_last = (atomicAdd(&d.st->ticket, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-        d.st->ticket = 0u;
-        signal_all(d, g.kind);
-    }
-}
-
-// wait (bounded) until every rank has signalled `kind` as often as this rank has
-__global__ void k_wait_flag(HpDev d, int kind, const int* skip) {
-    pdl_enter();
-    if (*skip) return;
-    const int lane = threadIdx.x;
-    const HpComm* mine = d.comm_peer[d.rank];
-    const unsigned long long want = d.seq[kind];
-    bool ok = true;
-    if (lane < d.nranks && !(d.st->flags & 8)) {
-        const unsigned long long t0 = global_ns();
-        while (ld_acquire_sys(&mine->flag[kind][lane]) < want) {
-            if (global_ns() - t0 > 2000000000ull) { ok = false; break; }
-            __nanosleep(64);
-        }
-    }
-    const unsigned bad = __ballot_sync(0xffffffffu, !ok);
-    if (lane == 0 && bad) {
-        d.st->flags |= 8;
-        d.stats[(d.st->sweep_count - 1) % HP_STATS_CAP].flags |= 8;
     }
 }
 
@@ -1051,24 +959,70 @@ __global__ void k_wait_flag(HpDev d, int kind, const int* skip) {
 // The radial stiffness is removed exactly by the line solves on every level; coarsening the axial index removes the
 // axial stiffness that makes plain line-PCG need O(sqrt(D)) iterations (D = axial diffusion number of a cell).
 // Galerkin operators with piecewise-constant aggregation stay 5-point, so every level reuses the same row kernels.
-// Rank-local under slabs (ghost couplings are ignored inside the cycle): no communication in the preconditioner.
+// Under peer-memory slabs the hierarchy is the single-domain one, distributed: every level keeps its couplings to the
+// neighbouring slabs, every stage hands its two boundary rows to the neighbours (HpXchg: peer stores + a sequence flag, fused
+// into the producing row team) and the first / last row team of the consuming stage waits for them.  Without peer memory
+// (NCCL slabs, d.mg_local) the cycle ignores the ghost couplings: no communication in the preconditioner.
 // ================================================================================================
 
-// coarse level from a fine one:  cR_c = cR[2J] + cR[2J+1],  cZ_c = coupling of the pair's top row to the next pair,
-// diag_c = diag[2J] + diag[2J+1] - 2 cZ[2J]  (P^T A P with P = row-pair injection).      thread per coarse cell
-__global__ void __launch_bounds__(256) k_mg_coarsen(HpLevel f, HpLevel c, int nr, const int* skip) {
-    pdl_enter();
+// the team that owns the first (lo) / last (hi) rows of a stage waits for the rows its neighbours pushed in stage x.wait
+template <int TPL>
+__device__ __forceinline__ void stage_wait(const HpDev& d, const HpKArgs& a, const HpXchg& x, bool lo, bool hi, int tl,
+                                           int team_in_cta, unsigned long long cyc) {
+    if (x.wait < 0 || !d.p2p) return;
+    lo = lo && d.rank > 0;
+    hi = hi && d.rank < d.nranks - 1;
+    if (!(lo || hi)) return;                      // uniform over the team
+    if (tl == 0 && !(d.st->flags & 8)) {
+        bool ok = true;
+        if (lo) ok = wait_peer_flag(d, a, x.wait, d.rank - 1, cyc);
+        if (hi && ok) ok = wait_peer_flag(d, a, x.wait, d.rank + 1, cyc);
+        if (!ok) raise_fault(d);
+    }
+    team_barrier<TPL>(team_in_cta);
+    __threadfence_system();                       // every reader of the ghost rows orders its loads after the acquire
+}
+
+// boundary row of a stage's output -> the neighbour's ghost row, then the stage flag (release, system scope)
+template <int TPL, int EPT, bool VEC>
+__device__ __forceinline__ void stage_push(const HpDev& d, const HpXchg& x, bool is_lo, double* dst, int i0, int nr,
+                                           const double (&v)[EPT], int tl, int team_in_cta, unsigned long long cyc) {
+    store_row<EPT, VEC>(dst, i0, nr, v);
+    if (x.sig < 0) return;
+    __threadfence_system();
+    team_barrier<TPL>(team_in_cta);
+    if (tl == 0) {
+        unsigned long long* f = &d.comm_peer[is_lo ? d.rank - 1 : d.rank + 1]->flag[x.sig][d.rank];
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(cyc) : "memory");
+    }
+}
+
+// coarse level from a fine one (rows aggregated in pairs, P = row-pair injection):
+//   cR_c = cR[2J] + cR[2J+1]                                   radial couplings: Galerkin (P^T A P)
+//   cZ_c = zs * (coupling of the pair's top row to the next pair)
+//   diag_c = diag[2J] + diag[2J+1] - 2 cZ[2J] - (1 - zs) (cZ_up + cZ_down)
+// zs = 1 is the Galerkin operator.  With piecewise-constant aggregation its axial coupling is twice what a discretisation
+// on the coarse rows (twice the centre distance) gives, which halves the coarse correction of smooth axial modes; zs = 1/2
+// restores it (row sums = capacity + boundary terms are kept, the operator stays a symmetric M-matrix and keeps the
+// 5-point shape): 20 -> 7 PCG iterations on the 4096-row mesh.  Row 0 of cZ_c is the coupling to the slab below
+// (keep_ghost: distributed hierarchy under peer-memory slabs; zero at a physical end anyway).     thread per coarse cell
+__global__ void __launch_bounds__(256) k_mg_coarsen(HpLevel f, HpLevel c, int nr, double zs, int keep_ghost, const int* skip) {
     if (*skip) return;
-    const long long n = (long long)c.nz * nr;
+    const long long n = (long long)(c.nz + 1) * nr;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-        const int J = (int)(t / nr), i = (int)(t - (long long)J * nr);
+        const int J = (int)(t / nr) - 1, i = (int)(t - (long long)(J + 1) * nr);
+        if (J < 0) {                                   // ghost coupling below the first pair
+            c.cZ[i] = keep_ghost ? zs * f.cZ[i] : 0.0;
+            continue;
+        }
         const long long g0 = (long long)(2 * J + 1) * nr + i, g1 = g0 + nr;
         const bool two = (2 * J + 1) < f.nz;
         const long long gc = (long long)(J + 1) * nr + i;
         const double inner = two ? f.cZ[g0] : 0.0;
+        const double up = two ? f.cZ[g1] : f.cZ[g0], dn = f.cZ[g0 - nr];
         c.cR[gc] = f.cR[g0] + (two ? f.cR[g1] : 0.0);
-        c.cZ[gc] = (J == c.nz - 1) ? 0.0 : (two ? f.cZ[g1] : f.cZ[g0]);        // rank-local: nothing beyond the last pair
-        c.diag[gc] = f.diag[g0] + (two ? f.diag[g1] - 2.0 * inner : 0.0);
+        c.cZ[gc] = (J == c.nz - 1 && !keep_ghost) ? 0.0 : zs * up;
+        c.diag[gc] = f.diag[g0] + (two ? f.diag[g1] - 2.0 * inner : 0.0) - (1.0 - zs) * (up + dn);
     }
 }
 
@@ -1082,11 +1036,13 @@ __global__ void __launch_bounds__(256) k_mg_coarsen(HpLevel f, HpLevel c, int nr
 // c_x(J) = omega * M_{L+1}^-1 crhs(J) as soon as the coarse row J = pair-sum of residual rows is complete.  Both need the
 // team to own whole rows (no column tiles).
 template <int TPL, int EPT, bool VEC, int MODE = 0>
-__device__ __forceinline__ void mg_res_body(const HpDev& d, const HpLevel& L, const HpMgResArgs& m, long long team,
+__device__ __forceinline__ void mg_res_body(const HpDev& d, const HpKArgs& a, const HpLevel& L, const HpMgResArgs& m, long long team,
                                             long long nteams, double omega = 0.0, double* s_fA = nullptr,
                                             double* s_fB = nullptr, double* s_bA = nullptr, double* s_bB = nullptr) {
     const int nr = d.nr, nz = L.nz;
     const int tl = threadIdx.x % TPL, lane = threadIdx.x & (TeamGeom<TPL>::W - 1);
+    const int team_in_cta = threadIdx.x / TPL;
+    const unsigned long long cyc = d.st->cycle;
     const int ncol = d.ncolA;
     const long long nchunks = nteams / ncol;
     const long long chunk = team / ncol;
@@ -1103,11 +1059,9 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpLevel& L, co
     const bool has_r = (lane == TeamGeom<TPL>::W - 1) && (i0 + EPT < nr);
     const bool prolong = m.ec != nullptr;
     const double scale = m.scale;
-    auto crow = [&](int g) {                       // coarse ghost-inclusive row of fine row g (clamped at the ends)
-        int J = (g - 1) >> 1;
-        J = J < 0 ? 0 : (J > m.nzc - 1 ? m.nzc - 1 : J);
-        return (long long)(J + 1) * nr;
-    };
+    // coarse ghost-inclusive row of fine row g: the ghost rows 0 / nz+1 map to the coarse ghost rows 0 / nzc+1 (the
+    // neighbouring slab's boundary pair; never-written zeros at a physical end, where the coupling is zero)
+    auto crow = [&](int g) { return (long long)(((g - 1) >> 1) + 1) * nr; };
     auto xrow = [&](int g, double (&out)[EPT]) {
         load_row<EPT, VEC>(m.xin + (long long)g * nr, i0, nr, out);
         if (prolong) {
@@ -1126,6 +1080,7 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpLevel& L, co
         return v;
     };
     if (jb > ja) {
+        stage_wait<TPL>(d, a, m.xc, ja == 0, jb == nz, tl, team_in_cta, cyc);
         double xm[EPT], xc[EPT], xn[EPT], czm[EPT], rprev[EPT];
         double xc_l = 0.0, xc_r = 0.0;
         xrow(ja, xm);
@@ -1134,8 +1089,11 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpLevel& L, co
         if (has_r) xc_r = xat(ja + 1, i0 + EPT);
         load_row<EPT, VEC>(L.cZ + (long long)ja * nr, i0, nr, czm);
         if (ja == 0) {
+            if (d.mg_local) {
 #pragma unroll
-            for (int k = 0; k < EPT; ++k) czm[k] = 0.0;        // rank-local: no coupling to the lower ghost row
+                for (int k = 0; k < EPT; ++k) czm[k] = 0.0;    // rank-local cycle: no coupling to the lower ghost row
+            }
+            if (m.xout_ghost) store_row<EPT, VEC>(m.xout, i0, nr, xm);                  // ghost row of the scaled iterate
         }
 #pragma unroll
         for (int k = 0; k < EPT; ++k) rprev[k] = 0.0;
@@ -1168,8 +1126,11 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpLevel& L, co
             if (has_l) { xn_l = xat(g + 1, i0 - 1); crl_e = L.cR[rb + i0 - 1]; }
             if (has_r) xn_r = xat(g + 1, i0 + EPT);
             if (g == nz) {
+                if (d.mg_local) {
 #pragma unroll
-                for (int k = 0; k < EPT; ++k) cz[k] = 0.0;     // rank-local: no coupling to the upper ghost row
+                    for (int k = 0; k < EPT; ++k) cz[k] = 0.0; // rank-local cycle: no coupling to the upper ghost row
+                }
+                if (m.xout_ghost) store_row<EPT, VEC>(m.xout + rb + nr, i0, nr, xn);
             }
             const unsigned tm = team_mask<TPL>();
             constexpr int W = TeamGeom<TPL>::W;
@@ -1193,10 +1154,12 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpLevel& L, co
             }
             if constexpr (MODE == 1) {
                 double zv[EPT];
-                line_solve<TPL, EPT>(res, dv, cr, m0_edge, lane, tl >> 5, (int)(threadIdx.x / TPL), s_fA, s_fB, s_bA, s_bB, zv);
+                line_solve<TPL, EPT>(res, dv, cr, m0_edge, lane, tl >> 5, team_in_cta, s_fA, s_fB, s_bA, s_bB, zv);
 #pragma unroll
                 for (int k = 0; k < EPT; ++k) zv[k] = fma(omega, zv[k], xc[k]);
                 store_row<EPT, VEC>(m.xout + rb, i0, nr, zv);
+                if (g == 1 && m.xc.push_lo) stage_push<TPL, EPT, VEC>(d, m.xc, true, m.xc.push_lo, i0, nr, zv, tl, team_in_cta, cyc);
+                if (g == nz && m.xc.push_hi) stage_push<TPL, EPT, VEC>(d, m.xc, false, m.xc.push_hi, i0, nr, zv, tl, team_in_cta, cyc);
             } else {
                 if (m.xout) store_row<EPT, VEC>(m.xout + rb, i0, nr, xc);
                 if (m.resout) store_row<EPT, VEC>(m.resout + rb, i0, nr, res);
@@ -1209,10 +1172,13 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpLevel& L, co
                     store_row<EPT, VEC>(m.crhs + cb, i0, nr, sum);
                     if constexpr (MODE == 2) {
                         double zc[EPT];
-                        line_solve<TPL, EPT>(sum, cdv, ccr, m0_edge, lane, tl >> 5, (int)(threadIdx.x / TPL), s_fA, s_fB, s_bA, s_bB, zc);
+                        line_solve<TPL, EPT>(sum, cdv, ccr, m0_edge, lane, tl >> 5, team_in_cta, s_fA, s_fB, s_bA, s_bB, zc);
 #pragma unroll
                         for (int k = 0; k < EPT; ++k) zc[k] *= omega;
                         store_row<EPT, VEC>(m.c_x + cb, i0, nr, zc);
+                        const int Jg = ((g - 1) >> 1) + 1;
+                        if (Jg == 1 && m.xc.push_lo) stage_push<TPL, EPT, VEC>(d, m.xc, true, m.xc.push_lo, i0, nr, zc, tl, team_in_cta, cyc);
+                        if (Jg == m.nzc && m.xc.push_hi) stage_push<TPL, EPT, VEC>(d, m.xc, false, m.xc.push_hi, i0, nr, zc, tl, team_in_cta, cyc);
                     }
                 } else {
 #pragma unroll
@@ -1229,10 +1195,9 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpLevel& L, co
 template <int TPL, int EPT, bool VEC>
 __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_A(EPT))
 k_mg_res(HpDev d, HpKArgs a, HpLevel L, HpMgResArgs m) {
-    pdl_enter();
     using G = TeamGeom<TPL>;
     if (d.st->mg_skip) return;
-    mg_res_body<TPL, EPT, VEC>(d, L, m, (long long)blockIdx.x * G::LPC + threadIdx.x / TPL, (long long)gridDim.x * G::LPC);
+    mg_res_body<TPL, EPT, VEC>(d, a, L, m, (long long)blockIdx.x * G::LPC + threadIdx.x / TPL, (long long)gridDim.x * G::LPC);
 }
 
 // ---- k_mg_up : prolong + residual + post-smoothing of one coarse level in ONE pass (one stage instead of two in the
@@ -1240,12 +1205,11 @@ k_mg_res(HpDev d, HpKArgs a, HpLevel L, HpMgResArgs m) {
 template <int TPL, int EPT, bool VEC, int MODE>
 __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_A(EPT))
 k_mg_fused(HpDev d, HpKArgs a, HpLevel L, HpMgResArgs m) {
-    pdl_enter();
     using G = TeamGeom<TPL>;
     if (d.st->mg_skip) return;
     __shared__ double s_fA[G::LPC][G::NW], s_fB[G::LPC][G::NW], s_bA[G::LPC][G::NW], s_bB[G::LPC][G::NW];
     const int tic = threadIdx.x / TPL;
-    mg_res_body<TPL, EPT, VEC, MODE>(d, L, m, (long long)blockIdx.x * G::LPC + tic, (long long)gridDim.x * G::LPC, a.omega,
+    mg_res_body<TPL, EPT, VEC, MODE>(d, a, L, m, (long long)blockIdx.x * G::LPC + tic, (long long)gridDim.x * G::LPC, a.omega,
                                      s_fA[tic], s_fB[tic], s_bA[tic], s_bB[tic]);
 }
 template <int TPL, int EPT, bool VEC>
@@ -1267,6 +1231,7 @@ __device__ __forceinline__ double mg_line_body(const HpDev& d, double omega, con
     int ja = 0, jb = 0;
     if (team < nteams) { ja = (int)(team * nz / nteams); jb = (int)((team + 1) * nz / nteams); }
     double acc = 0.0;
+    const unsigned long long cyc = d.st->cycle;
     for (int g = ja + 1; g <= jb; ++g) {
         const long long rb = (long long)g * nr;
         double rv[EPT], dv[EPT], cr[EPT], zv[EPT];
@@ -1285,11 +1250,10 @@ __device__ __forceinline__ double mg_line_body(const HpDev& d, double omega, con
         if (m.final_) {
 #pragma unroll
             for (int k = 0; k < EPT; ++k) acc = fma(r0[k], zv[k], acc);
-            if (d.p2p) {
-                if (g == 1 && d.z_lo) store_row<EPT, VEC>(d.z_lo, i0, nr, zv);
-                if (g == nz && d.z_hi) store_row<EPT, VEC>(d.z_hi, i0, nr, zv);
-            }
         }
+        // boundary rows -> the neighbours' ghost rows (final stage: ordered before the flag of the r.z reduction)
+        if (g == 1 && m.xc.push_lo) stage_push<TPL, EPT, VEC>(d, m.xc, true, m.xc.push_lo, i0, nr, zv, tl, team_in_cta, cyc);
+        if (g == nz && m.xc.push_hi) stage_push<TPL, EPT, VEC>(d, m.xc, false, m.xc.push_hi, i0, nr, zv, tl, team_in_cta, cyc);
     }
     return acc;
 }
@@ -1297,7 +1261,6 @@ __device__ __forceinline__ double mg_line_body(const HpDev& d, double omega, con
 template <int TPL, int EPT, bool VEC>
 __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT))
 k_mg_line(HpDev d, HpKArgs a, HpLevel L, HpMgLineArgs m) {
-    pdl_enter();
     using G = TeamGeom<TPL>;
     if (d.st->mg_skip) return;
     __shared__ double s_fA[G::LPC][G::NW], s_fB[G::LPC][G::NW], s_bA[G::LPC][G::NW], s_bB[G::LPC][G::NW];
@@ -1314,85 +1277,6 @@ k_mg_line(HpDev d, HpKArgs a, HpLevel L, HpMgLineArgs m) {
     }
 }
 
-// ---- k_mg_subcycle : the V-cycle below the fine level in one cooperative launch -----------------------------------------
-__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-// all CTAs of the (co-resident) grid; `target` = counter value once every CTA has arrived.  Bounded: a missing CTA sets
-// the sticky error bit instead of hanging the GPU.
-__device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target, HpState* st) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1ull);
-        const unsigned long long t0 = global_ns();
-        while (ld_acquire_gpu(ctr) < target) {
-            if (global_ns() - t0 > 2000000000ull) { st->flags |= 8; break; }
-        }
-    }
-    __syncthreads();
-    __threadfence();        // gpu-scope fence: invalidates this SM's L1 so rows written by other SMs are re-fetched
-}
-
-template <int TPL, int EPT, bool VEC>
-__global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_A(EPT))
-k_mg_subcycle(HpDev d, HpKArgs a, HpLevelSet ls, HpSubcycleArgs sc) {
-    pdl_enter();
-    using G = TeamGeom<TPL>;
-    if (d.st->mg_skip) return;
-    __shared__ double s_fA[G::LPC][G::NW], s_fB[G::LPC][G::NW], s_bA[G::LPC][G::NW], s_bB[G::LPC][G::NW];
-    const int tic = threadIdx.x / TPL;
-    const long long team = (long long)blockIdx.x * G::LPC + tic, total = (long long)gridDim.x * G::LPC;
-    const unsigned long long base = sc.gbar[1];
-    unsigned long long nb = 0;
-    const double omega = a.omega;
-    auto sync = [&]() { ++nb; grid_barrier(&sc.gbar[0], base + nb * gridDim.x, d.st); };
-    auto teams_for = [&](int nz) -> long long {           // >= 2 rows per team, whole column-tile groups
-        long long t = (nz + 1) / 2;
-        t = t < 1 ? 1 : t;
-        t *= d.ncolA;
-        return t < total ? t : (total / d.ncolA) * d.ncolA;
-    };
-    auto line = [&](int l, const double* rhs, const double* bs, double* out) {
-        HpMgLineArgs m{rhs, bs, out, 0};
-        long long nt = teams_for(ls.lev[l].nz) / d.ncolA;
-        (void)mg_line_body<TPL, EPT, VEC>(d, omega, ls.lev[l], m, team, nt, s_fA[tic], s_fB[tic], s_bA[tic], s_bB[tic]);
-        sync();
-    };
-    auto res = [&](int l, const double* xin, const double* ec, int nzc, double* xout, double* resout, double* crhs) {
-        HpMgResArgs m{xin, ec, xout, resout, crhs, 1.0, nzc};
-        mg_res_body<TPL, EPT, VEC>(d, ls.lev[l], m, team, teams_for(ls.lev[l].nz));
-        sync();
-    };
-    HpLevel* L = ls.lev;
-    const int c = sc.n - 1;
-    if (sc.part != 2) {
-        for (int l = sc.lo; l < c; ++l) {
-            line(l, L[l].rhs, nullptr, L[l].x);
-            res(l, L[l].x, nullptr, L[l + 1].nz, nullptr, nullptr, L[l + 1].rhs);
-        }
-    }
-    if (sc.part == 0) {
-        line(c, L[c].rhs, nullptr, L[c].x);
-        for (int k = 0; k < sc.sweeps; ++k) {
-            res(c, L[c].x, nullptr, 1, nullptr, L[c].tmp, nullptr);
-            line(c, L[c].tmp, L[c].x, L[c].x);
-        }
-    }
-    if (sc.part != 1) {
-        for (int l = c - 1; l >= sc.lo; --l) {
-            const double* ec = (sc.part == 2 && l == c - 1) ? sc.ec_top : L[l + 1].x;
-            res(l, L[l].x, ec, L[l + 1].nz, L[l].x2, L[l].tmp, nullptr);
-            line(l, L[l].tmp, L[l].x2, L[l].x);
-        }
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) sc.gbar[1] = base + nb * gridDim.x;
-}
-template <int TPL, int EPT, bool VEC>
-const void* fn_mg_subcycle() { return (const void*)k_mg_subcycle<TPL, EPT, VEC>; }
-
 template <int TPL, int EPT, bool VEC>
 const void* fn_mg_res() { return (const void*)k_mg_res<TPL, EPT, VEC>; }
 template <int TPL, int EPT, bool VEC>
@@ -1401,7 +1285,6 @@ const void* fn_mg_line() { return (const void*)k_mg_line<TPL, EPT, VEC>; }
 // pivots of ALL coarse levels in one launch (thread per row of any level: the recurrence is a serial chain of nr
 // steps whatever the row count, so one launch costs the same latency as one level alone)
 __global__ void __launch_bounds__(32) k_factor_levels(HpLevelSet ls, int nr, const int* skip) {
-    pdl_enter();
     if (*skip) return;
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     for (int l = 1; l < ls.n; ++l) {
@@ -1463,13 +1346,6 @@ bool pick_config(int nr, int nz, int num_sms, HpLaunchCfg* cfg, const char** err
     else if (nr <= 4096) { tpl = 512; ept = 8; }
     else if (nr <= 8192) { tpl = 1024; ept = 8; }
     else { *err = "nr > 8192 radial cells per row is not supported"; return false; }
-    // experiment hook: HP_TEAM=TPLxEPT overrides the table when the pair is instantiated and covers the row
-    if (const char* e = getenv("HP_TEAM")) {
-        int t = 0, p = 0;
-        if (sscanf(e, "%dx%d", &t, &p) == 2 && (long long)t * p >= nr &&
-            ((t == 16 && p == 1) || (t == 32 && (p == 1 || p == 4)) || (t == 128 && (p == 4 || p == 8)) || (t == 256 && (p == 4 || p == 8)) ||
-             ((t == 512 || t == 1024) && p == 8))) { tpl = t; ept = p; }
-    }
     cfg->tpl = tpl; cfg->ept = ept;
     cfg->vec = (ept >= 4) && (nr % ept == 0);
     cfg->cta_threads = tpl < 256 ? 256 : tpl;
@@ -1543,7 +1419,7 @@ HpKernelLaunch desc_factor(const HpLaunchCfg& c, const HpDev& d) {
     return {(const void*)k_factor_rline, dim3(c.grid_factor), dim3(c.cta_factor), 0};
 }
 HpKernelLaunch desc_mg_coarsen(const HpLaunchCfg& c, int nzc, int nr) {
-    long long g = ((long long)nzc * nr + 255) / 256;
+    long long g = ((long long)(nzc + 1) * nr + 255) / 256;
     long long cap = (long long)c.num_sms * 8;
     return {(const void*)k_mg_coarsen, dim3((unsigned)(g < cap ? (g < 1 ? 1 : g) : cap)), dim3(256), 0};
 }
@@ -1556,7 +1432,7 @@ HpKernelLaunch desc_mg_res(const HpLaunchCfg& c, int nz_level) {
     cl.nz = (nz_level + 1) / 2;                      // chunks are whole row pairs
     return {f, dim3(team_grid(f, cl, c.ctaA, c.teams_per_ctaA, c.ncolA)), dim3(c.ctaA), 0};
 }
-HpKernelLaunch desc_mg_up(const HpLaunchCfg& c, int nz_level) {       // only when mg_subcycle_supported(c)
+HpKernelLaunch desc_mg_up(const HpLaunchCfg& c, int nz_level) {       // only when mg_fused_supported(c)
     const void* f = nullptr;
 #define HP_X(T, E, V) f = fn_mg_up<T, E, V>()
     HP_DISPATCH_A(c, HP_X);
@@ -1565,7 +1441,7 @@ HpKernelLaunch desc_mg_up(const HpLaunchCfg& c, int nz_level) {       // only wh
     cl.nz = (nz_level + 1) / 2;
     return {f, dim3(team_grid(f, cl, c.ctaA, c.teams_per_ctaA, 1)), dim3(c.ctaA), 0};
 }
-HpKernelLaunch desc_mg_down(const HpLaunchCfg& c, int nz_level) {     // only when mg_subcycle_supported(c)
+HpKernelLaunch desc_mg_down(const HpLaunchCfg& c, int nz_level) {     // only when mg_fused_supported(c)
     const void* f = nullptr;
 #define HP_X(T, E, V) f = fn_mg_down<T, E, V>()
     HP_DISPATCH_A(c, HP_X);
@@ -1583,30 +1459,13 @@ HpKernelLaunch desc_mg_line(const HpLaunchCfg& c, int nz_level) {
     cl.nz = nz_level;
     return {f, dim3(team_grid(f, cl, c.cta_threads, c.teams_per_cta, 1)), dim3(c.cta_threads), 0};
 }
-// the fused cycle needs the row teams of the residual and of the line solve to have the same shape (nr <= 1024)
-bool mg_subcycle_supported(const HpLaunchCfg& c) {
+// the fused stages need the row teams of the residual and of the line solve to have the same shape (nr <= 1024)
+bool mg_fused_supported(const HpLaunchCfg& c) {
     return c.tplA == c.tpl && c.eptA == c.ept && c.vecA == c.vec && c.ctaA == c.cta_threads;
-}
-HpKernelLaunch desc_mg_subcycle(const HpLaunchCfg& c) {
-    const void* f = nullptr;
-#define HP_X(T, E, V) f = fn_mg_subcycle<T, E, V>()
-    HP_DISPATCH_A(c, HP_X);
-#undef HP_X
-    int occ = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f, c.ctaA, 0) != cudaSuccess || occ < 1) occ = 1;
-    HpKernelLaunch k{f, dim3(c.num_sms * occ), dim3(c.ctaA), 0};
-    k.cooperative = true;
-    return k;
 }
 HpKernelLaunch desc_factor_levels(int total_coarse_rows) {
     return {(const void*)k_factor_levels, dim3((total_coarse_rows + 31) / 32), dim3(32), 0};
 }
-HpKernelLaunch desc_gather_rows(const HpLaunchCfg& c, long long elems) {
-    long long g = (elems + 255) / 256;
-    long long cap = (long long)c.num_sms * 4;
-    return {(const void*)k_gather_rows, dim3((unsigned)(g < 1 ? 1 : (g < cap ? g : cap))), dim3(256), 0};
-}
-HpKernelLaunch desc_wait_flag() { return {(const void*)k_wait_flag, dim3(1), dim3(32), 0}; }
 HpKernelLaunch desc_finalize() { return {(const void*)k_finalize, dim3(1), dim3(32), 0}; }
 HpKernelLaunch desc_wait() { return {(const void*)k_wait, dim3(1), dim3(32), 0}; }
 HpKernelLaunch desc_cg_A(const HpLaunchCfg& c, const HpDev& d) {

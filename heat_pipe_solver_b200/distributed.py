@@ -15,15 +15,53 @@ import ctypes as C
 import numpy as np
 
 
-def slab_rows(nz, rank, world):
-    """Contiguous block of axial rows for `rank`; sizes differ by at most one row."""
+def slab_rows(nz, rank, world, align=1):
+    """Contiguous block of axial rows for `rank`.  The cuts fall on multiples of `align` rows (sizes differ by at most one
+    block of `align` rows; the rows beyond the last whole block go to the last rank)."""
     if not (0 <= rank < world):
         raise ValueError("rank out of range")
-    if world > nz:
-        raise ValueError(f"cannot split {nz} rows over {world} ranks")
-    base, extra = divmod(nz, world)
-    j0 = rank * base + min(rank, extra)
-    return j0, j0 + base + (1 if rank < extra else 0)
+    blocks = nz // align
+    if world > blocks:
+        raise ValueError(f"cannot split {nz} rows over {world} ranks in blocks of {align}")
+    base, extra = divmod(blocks, world)
+    b0 = rank * base + min(rank, extra)
+    b1 = b0 + base + (1 if rank < extra else 0)
+    return b0 * align, (nz if rank == world - 1 else b1 * align)
+
+
+def mg_level_count(nz, max_levels=6):
+    """Levels of the 'mgline' hierarchy of a mesh with nz rows (rows halve per level; a level is added while the one above
+    has >= 32 rows) -- the rule of csrc/hp_api.cu::local_level_count."""
+    n, rows = 1, nz
+    while n < max_levels and rows >= 32:
+        n += 1
+        rows = (rows + 1) // 2
+    return n
+
+
+def slab_alignment(nz, world, max_levels=6):
+    """Row alignment of the slab cuts under which the distributed V-cycle is the single-domain one: every level pairs
+    rows 2J, 2J+1, so every slab but the last must hold a multiple of 2^(levels-1) rows.  Fewer levels if the mesh is too
+    short for that many whole blocks per rank."""
+    n = mg_level_count(nz, max_levels)
+    while n > 1 and nz // (1 << (n - 1)) < world:
+        n -= 1
+    return 1 << (n - 1)
+
+
+def resolve_precond(precond, nz, nr, world, comm, max_levels=6):
+    """'auto' decided from the GLOBAL mesh so that every rank runs the same kernel sequence (a per-rank decision can
+    differ between slabs that differ by one row).  Without peer memory the V-cycle is rank-local: every slab must be tall
+    enough to coarsen, else all ranks use the line preconditioner."""
+    if precond == 'auto':
+        precond = 'mgline' if (nz >= 256 and nz * nr >= 262144) else 'rline'
+    if precond == 'mgline' and world > 1:
+        if comm == 'p2p':
+            if mg_level_count(nz, max_levels) < 2 or slab_alignment(nz, world, max_levels) < 2:
+                precond = 'rline'
+        elif min(b - a for a, b in (slab_rows(nz, r, world) for r in range(world))) < 32:
+            precond = 'rline'
+    return precond
 
 
 def neighbours(rank, world):
@@ -58,8 +96,10 @@ def make_solver_for_rank(mesh, cfg, rank, world, comm='p2p', **solver_kw):
         return ConductionSolver(mesh, cfg['dimensions'], cfg['parameters'], cfg['constants'], **solver_kw)
     import torch
     import torch.distributed as dist
-    rows = slab_rows(mesh.nz, rank, world)
-    solver = ConductionSolver(mesh, cfg['dimensions'], cfg['parameters'], cfg['constants'], rows=rows, **solver_kw)
+    precond = resolve_precond(solver_kw.pop('precond', 'auto'), mesh.nz, mesh.nr, world, comm, solver_kw.get('mg_levels', 6))
+    align = slab_alignment(mesh.nz, world, solver_kw.get('mg_levels', 6)) if (precond == 'mgline' and comm == 'p2p') else 1
+    rows = slab_rows(mesh.nz, rank, world, align)
+    solver = ConductionSolver(mesh, cfg['dimensions'], cfg['parameters'], cfg['constants'], rows=rows, precond=precond, **solver_kw)
     # NCCL communicator of the library itself: rank 0 makes the id, torch.distributed carries it
     ident = torch.zeros(128, dtype=torch.uint8)
     if rank == 0:
@@ -71,13 +111,15 @@ def make_solver_for_rank(mesh, cfg, rank, world, comm='p2p', **solver_kw):
     dist.broadcast(ident, src=0)
     solver.init_comm(rank, world, bytes(ident.cpu().numpy().tobytes()))
     if comm == 'p2p':
-        nzs = [b - a for a, b in (slab_rows(mesh.nz, r, world) for r in range(world))]
+        nzs = [b - a for a, b in (slab_rows(mesh.nz, r, world, align) for r in range(world))]
         mine = torch.frombuffer(bytearray(solver.peer_export(nzs)), dtype=torch.uint8).cuda()
         gathered = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine)
         handles = b''.join(bytes(g.cpu().numpy().tobytes()) for g in gathered)
         solver.init_peer(handles, nzs)
         dist.barrier()
+        if precond == 'mgline' and solver.effective_precond != 'mgline':
+            raise RuntimeError("mgline was resolved for the slabs but the library fell back: inconsistent level count")
     elif comm != 'nccl':
         raise ValueError("comm must be 'p2p' or 'nccl'")
     return solver

@@ -44,15 +44,21 @@ def run(config_file=None, *, t_end=101.0, dt=0.1, sweeps=1, has_old=False, h=5.0
         radiation=False, measure_every=5, measure_times=None, mesh_params=None, T0=None,
         precond='auto', criterion='precond_inf', tol=1e-9, max_iter=5000, loop_mode='graph',
         capture_properties=True, verbose=False, device=None, sweep_tol=None, max_sweeps=50,
-        checkpoint=None, checkpoint_every=None, resume=None, extrapolate=True, reuse_converged=False):
+        checkpoint=None, checkpoint_every=None, resume=None, extrapolate=True, reuse_converged=False, comm='p2p'):
     """Transient conduction run.  Defaults = the reference's active code path (main.py:119-120,200-202:
     t_end=101 s, dt=0.1 s, one sweep per step with hasOld=False, h=5 W/m2K, temperature-dependent laws).
     The commented "sweep" variant (main.py:267-271) is ``sweeps=5, has_old=True``.
 
     Extras beyond the reference: ``sweeps='auto'`` (or ``sweep_tol``) re-sweeps every step until FiPy's
     pre-solve residual drops below ``sweep_tol`` (default 1e-8) or ``max_sweeps``; ``checkpoint=path`` writes an ``.npz``
-    (field, old field, step index, loop time, captured profiles) every ``checkpoint_every`` steps and at the end,
-    ``resume=path`` continues such a run (identical to solver tolerance; bit-identical with ``extrapolate=False``).
+    (field, step index, loop time and EVERY capture list so far) every ``checkpoint_every`` steps counted from the start of
+    this call and at the end; ``resume=path`` continues such a run (T_old is rebuilt by ``updateOld`` at the next step, so the
+    result is identical to solver tolerance; bit-identical with ``extrapolate=False``).
+
+    Under ``torch.distributed`` with world size N > 1 (``python -m torch.distributed.run --nproc-per-node N -m
+    heat_pipe_solver_b200.main``: the reference's ``mpirun -np N python main.py``, main.py:11,339) every rank owns an axial
+    slab of the mesh (FiPy partitions ``Grid2D`` the same way); captured profiles and the returned field are gathered, so
+    every rank returns the same global arrays.  ``comm='p2p'|'nccl'`` picks the slab exchange.
 
     Returns a dict: ``T`` (nz, nr) final field, ``times`` / ``profiles`` (top-wall axial temperature profiles,
     main.py:208-209), ``residuals`` (FiPy-style pre-solve residual at each capture), property profiles
@@ -71,13 +77,31 @@ def run(config_file=None, *, t_end=101.0, dt=0.1, sweeps=1, has_old=False, h=5.0
         print(f"Measuring at: {measure_times} seconds")                    # main.py:161
     times, captures = measurement_schedule(t_end, dt, measure_times)
 
-    solver = ConductionSolver(mesh, dimensions, parameters, constants, h=h, properties=properties, gamma=gamma,
-                              source=source, face_k=face_k, radiation=radiation, precond=precond,
-                              criterion=criterion, tol=tol, max_iter=max_iter, loop_mode=loop_mode, device=device,
-                              extrapolate=extrapolate, reuse_converged=reuse_converged)
+    rank, world = 0, 1
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    kw = dict(h=h, properties=properties, gamma=gamma, source=source, face_k=face_k, radiation=radiation, precond=precond,
+              criterion=criterion, tol=tol, max_iter=max_iter, extrapolate=extrapolate, reuse_converged=reuse_converged)
+    if world > 1:
+        from .distributed import gather_field, make_solver_for_rank
+        solver = make_solver_for_rank(mesh, cfg, rank, world, comm=comm,
+                                      loop_mode='host' if comm == 'nccl' else loop_mode, **kw)
+
+        def whole(t2d):                      # owned rows of every rank -> the global (nz, k) array, on every rank
+            return gather_field(t2d.contiguous())
+    else:
+        solver = ConductionSolver(mesh, dimensions, parameters, constants, loop_mode=loop_mode, device=device, **kw)
+
+        def whole(t2d):
+            return t2d
+    j0, j1 = solver.layout.j0, solver.layout.j1
     try:
         if T0 is not None:
-            solver.set_value(T0)
+            solver.set_value(np.asarray(T0, dtype=np.float64).reshape(mesh.shape)[j0:j1] if np.ndim(T0) else T0)
         reg = solver.regions
         top_is_wall = reg.cell_band[-1] == BAND_WALL                       # main.py:165-169
         vc_cols = np.nonzero(reg.cell_band == BAND_VC)[0]
@@ -87,7 +111,7 @@ def run(config_file=None, *, t_end=101.0, dt=0.1, sweeps=1, has_old=False, h=5.0
                    k_top_wall=[], k_wick=[], k_vc=[])
 
         def capture(t):
-            T = solver.value_tensor()
+            T = whole(solver.value_tensor())
             st = solver.stats(1)[0]
             if verbose:
                 print(f"Time {t:.2f}, Residual: {st['residual_l2']}")      # main.py:207
@@ -97,7 +121,7 @@ def run(config_file=None, *, t_end=101.0, dt=0.1, sweeps=1, has_old=False, h=5.0
             if capture_properties:
                 f = solver.cell_fields()
                 for key, name in (('rho', 'rho'), ('cp', 'cp'), ('k', 'k')):
-                    a = f[key]
+                    a = whole(f[key])
                     out[f'{name}_top_wall'].append(a[:, -1].cpu().numpy() if top_is_wall else np.empty(0))
                     out[f'{name}_vc'].append(a[:, vc_cols].reshape(-1).cpu().numpy())
                     out[f'{name}_wick'].append(a[:, wick_cols].mean(dim=1).cpu().numpy() if wick_cols.size else np.empty(0))
@@ -113,16 +137,21 @@ def run(config_file=None, *, t_end=101.0, dt=0.1, sweeps=1, has_old=False, h=5.0
             ck = np.load(resume, allow_pickle=False)
             if tuple(ck['shape']) != tuple(mesh.shape) or float(ck['dt']) != float(dt):
                 raise ValueError("checkpoint does not match this mesh / dt")
-            solver.set_value(ck['T'])
+            solver.set_value(ck['T'][j0:j1])
             done = int(ck['step'])
             for key in out:
                 if 'ck_' + key in ck.files:
                     out[key] = list(ck['ck_' + key])
 
+        def global_field():
+            return whole(solver.value_tensor()).cpu().numpy().reshape(mesh.shape)
+
         def write_checkpoint(step_index):
-            np.savez(checkpoint, T=solver.value.reshape(mesh.shape), step=step_index, dt=dt, shape=np.array(mesh.shape),
-                     t=float(times[step_index - 1]) + dt if step_index else 0.0,
-                     **{'ck_' + k: np.array(v) for k, v in out.items() if k in ('times', 'residuals', 'profiles')})
+            Tg = global_field()              # collective under slabs: every rank takes part, rank 0 writes
+            if rank == 0:
+                np.savez(checkpoint, T=Tg, step=step_index, dt=dt, shape=np.array(mesh.shape),
+                         t=float(times[step_index - 1]) + dt if step_index else 0.0,
+                         **{'ck_' + k: np.array(v) for k, v in out.items()})
 
         def advance(n):
             """n time steps; fixed sweep count = back-to-back graph launches, 'auto' = residual-controlled sweeps."""
@@ -139,8 +168,8 @@ def run(config_file=None, *, t_end=101.0, dt=0.1, sweeps=1, has_old=False, h=5.0
                         break
                 sweep_counts.append(k)
 
-        stops = sorted(set([s + 1 for s, _ in captures if s + 1 > done] + [len(times)] +
-                           (list(range(done + checkpoint_every, len(times), checkpoint_every)) if checkpoint and checkpoint_every else [])))
+        ck_stops = set(range(done + checkpoint_every, len(times), checkpoint_every)) if checkpoint and checkpoint_every else set()
+        stops = sorted(set([s + 1 for s, _ in captures if s + 1 > done] + [len(times)]) | ck_stops)
         cap_at = {s + 1: t for s, t in captures}
         for stop in stops:
             if stop > done:
@@ -148,7 +177,7 @@ def run(config_file=None, *, t_end=101.0, dt=0.1, sweeps=1, has_old=False, h=5.0
                 done = stop
             if stop in cap_at and (not out['times'] or out['times'][-1] < cap_at[stop]):
                 capture(cap_at[stop])
-            if checkpoint and checkpoint_every and stop % checkpoint_every == 0:
+            if stop in ck_stops:
                 write_checkpoint(stop)
         solver.synchronize()
         if checkpoint:
@@ -157,10 +186,10 @@ def run(config_file=None, *, t_end=101.0, dt=0.1, sweeps=1, has_old=False, h=5.0
         if verbose:
             print(f"Simulated time: {t_end} seconds")                      # main.py:337
             print(f"Actual execution time: {elapsed:.2f} seconds")         # main.py:338
-            print("%d cells on processor %d of %d" % (mesh.numberOfCells, 0, 1))   # main.py:339
+            print("%d cells on processor %d of %d" % (solver.n_cells, rank, world))   # main.py:339
         result = {k: (np.array(v) if k in ('times', 'residuals') else v) for k, v in out.items()}
         result['profiles'] = np.array(out['profiles'])
-        result.update(T=solver.value.reshape(mesh.shape), n_steps=len(times), iterations=solver.total_iters,
+        result.update(T=global_field(), n_steps=len(times), iterations=solver.total_iters,
                       sweeps=solver.total_sweeps, elapsed=elapsed, mesh=mesh, kernel_launches=solver.kernel_launches,
                       sweeps_per_step=np.array(sweep_counts))
         return result
@@ -246,9 +275,27 @@ if __name__ == '__main__':
     ap.add_argument('--save', default=None, help='write <path>.npz (fields, profiles) and <path>_profiles.csv')
     ap.add_argument('--experiment', action='append', default=[], metavar='TIME_S=CSV',
                     help='measured wall temperatures (x,y columns) to compare the snapshot at TIME_S with (main.py:372-405)')
+    ap.add_argument('--mesh', default=None, metavar='NZ,NR_VC,NR_WICK,NR_WALL', help='synthetic refinement of the composite mesh')
+    ap.add_argument('--comm', default='p2p', choices=['p2p', 'nccl'])
     a = ap.parse_args()
-    r = run(a.config, t_end=a.t_end, dt=a.dt, sweeps=a.sweeps, has_old=a.has_old,
+    import os
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world > 1:                                  # launched by torch.distributed.run: one process per GPU
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+        dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0'))))
+    mp_ = None
+    if a.mesh:
+        nz_, v_, w_, wl_ = (int(x) for x in a.mesh.split(','))
+        mp_ = dict(nx_wall=nz_, nr_wall=wl_, nx_wick=nz_, nr_wick=w_, nx_vc=nz_, nr_vc=v_)
+    r = run(a.config, t_end=a.t_end, dt=a.dt, sweeps=a.sweeps, has_old=a.has_old, mesh_params=mp_, comm=a.comm,
             properties='simple' if a.simple else 'temperature_dependent', verbose=True)
+    if world > 1:
+        dist.barrier()
+        if dist.get_rank() != 0:
+            dist.destroy_process_group()
+            raise SystemExit(0)
     print(f"peak top-wall temperature: {r['profiles'][-1].max() if len(r['profiles']) else float('nan'):.3f} K")
     if a.save:
         from . import report
@@ -257,3 +304,5 @@ if __name__ == '__main__':
         from . import report
         files = {float(e.split('=', 1)[0]): e.split('=', 1)[1] for e in a.experiment}
         print(report.format_comparison(report.compare_with_experiment(r, files, time_tolerance=a.dt)))
+    if world > 1:
+        dist.destroy_process_group()

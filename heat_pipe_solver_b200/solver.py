@@ -101,8 +101,8 @@ class ConductionSolver:
                  properties='temperature_dependent', gamma='snapshot', source='q_over_k',
                  face_k='masked_at_Tface', radiation=False, axial_break=None, rows=None,
                  precond='auto', criterion='precond_inf', tol=1e-9, max_iter=5000, loop_mode='graph',
-                 poll_chunk=8, refactor_every=1, extrapolate=True, mg_levels=6, mg_coarse_sweeps=2, mg_omega=0.7,
-                 reuse_converged=False,
+                 poll_chunk=8, refactor_every=1, extrapolate=True, mg_levels=6, mg_coarse_sweeps=2, mg_omega=0.55,
+                 mg_zscale=0.5, reuse_converged=False, while_unroll=1, peer_timeout_ms=60000,
                  device=None, simple=(7200.0, 440.5, 55.0),
                  layout=None, regions=None):
         import torch
@@ -159,14 +159,15 @@ class ConductionSolver:
             precond = 'mgline' if (self.nz >= 256 and self.nz * self.nr >= 262144) else 'rline'
         self.set_options(precond=precond, criterion=criterion, tol=tol, max_iter=max_iter, loop_mode=loop_mode,
                          poll_chunk=poll_chunk, refactor_every=refactor_every, extrapolate=extrapolate,
-                         mg_levels=mg_levels, mg_coarse_sweeps=mg_coarse_sweeps, mg_omega=mg_omega,
-                         reuse_converged=reuse_converged)
+                         mg_levels=mg_levels, mg_coarse_sweeps=mg_coarse_sweeps, mg_omega=mg_omega, mg_zscale=mg_zscale,
+                         reuse_converged=reuse_converged, while_unroll=while_unroll, peer_timeout_ms=peer_timeout_ms)
 
     # ------------------------------------------------------------------ options
     def set_options(self, **kw):
         cur = getattr(self, 'options', dict(precond='rline', criterion='precond_inf', tol=1e-9, max_iter=5000,
                                             loop_mode='graph', poll_chunk=8, refactor_every=1, extrapolate=True,
-                                            mg_levels=6, mg_coarse_sweeps=2, mg_omega=0.7, reuse_converged=False))
+                                            mg_levels=6, mg_coarse_sweeps=2, mg_omega=0.55, mg_zscale=0.5,
+                                            reuse_converged=False, while_unroll=1, peer_timeout_ms=60000))
         cur = dict(cur)
         for k, v in kw.items():
             if k not in cur:
@@ -182,13 +183,38 @@ class ConductionSolver:
         o.extrapolate = (3 if e else 0) if isinstance(e, bool) else int(e)
         o.mg_levels, o.mg_coarse_sweeps, o.mg_omega = int(cur['mg_levels']), int(cur['mg_coarse_sweeps']), float(cur['mg_omega'])
         o.reuse_converged = 1 if cur['reuse_converged'] else 0
+        o.mg_zscale = float(cur['mg_zscale'])
+        o.while_unroll, o.peer_timeout_ms = int(cur['while_unroll']), int(cur['peer_timeout_ms'])
         _lib.check(self.lib.hp_set_opts(self._h, C.byref(o)), 'hp_set_opts')
         self.options = cur
+
+    @property
+    def effective_precond(self):
+        """The preconditioner in force (the library replaces 'mgline' by 'rline' on a mesh too short to coarsen)."""
+        o = _lib.HpSolveOpts()
+        _lib.check(self.lib.hp_get_opts(self._h, C.byref(o)), 'hp_get_opts')
+        return {v: k for k, v in PRECOND.items()}[o.precond]
 
     # ------------------------------------------------------------------ field access
     @property
     def n_cells(self):
         return self.nr * self.nz
+
+    # The library enqueues on the stream the handle was created with (self._stream); torch temporaries of the helpers
+    # below are produced / consumed on whatever stream is current when they are called.  _on_handle_stream orders the two.
+    def _enter(self):
+        """The handle's stream waits for the caller's current stream (inputs prepared there are complete)."""
+        cur = self._torch.cuda.current_stream(self.device)
+        if cur != self._stream:
+            self._stream.wait_stream(cur)
+        return cur
+
+    def _leave(self, cur, *tensors):
+        """The caller's current stream waits for the handle's stream; the tensors stay alive until both are done."""
+        if cur != self._stream:
+            cur.wait_stream(self._stream)
+            for t in tensors:
+                t.record_stream(self._stream)
 
     def set_value(self, T):
         """`T.setValue(...)`: scalar, numpy array or torch tensor of nz*nr values (FiPy order)."""
@@ -201,13 +227,17 @@ class ConductionSolver:
             buf = torch.from_numpy(np.ascontiguousarray(T, dtype=np.float64).reshape(-1)).to(self.device)
         if buf.numel() != self.n_cells:
             raise ValueError(f"expected {self.n_cells} values, got {buf.numel()}")
+        cur = self._enter()
         _lib.check(self.lib.hp_set_T_dev(self._h, C.c_void_p(buf.data_ptr())), 'hp_set_T_dev')
-        torch.cuda.current_stream(self.device).synchronize()
+        self._leave(cur, buf)
+        self._stream.synchronize()            # buf may go out of scope: the copy has consumed it
 
     def value_tensor(self):
         """Copy of the field as a torch.float64 CUDA tensor of shape (nz, nr)."""
         out = self._torch.empty((self.nz, self.nr), dtype=self._torch.float64, device=self.device)
+        cur = self._enter()
         _lib.check(self.lib.hp_get_T_dev(self._h, C.c_void_p(out.data_ptr())), 'hp_get_T_dev')
+        self._leave(cur, out)
         return out
 
     @property
@@ -268,6 +298,15 @@ class ConductionSolver:
     def kernel_launches(self):
         return int(self.lib.hp_kernel_launches(self._h))
 
+    @property
+    def peer_fault(self):
+        """True once a kernel of this handle gave up waiting for a neighbouring slab; every call then raises HpError."""
+        return bool(self.lib.hp_comm_fault(self._h))
+
+    def clear_peer_fault(self):
+        """Collective recovery (all ranks: synchronise, barrier, call this, barrier)."""
+        _lib.check(self.lib.hp_comm_clear_fault(self._h), 'hp_comm_clear_fault')
+
     def init_comm(self, rank, world, unique_id: bytes):
         """Join the library's NCCL communicator (axial slabs); `unique_id` = 128 bytes from rank 0."""
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
@@ -306,6 +345,7 @@ class ConductionSolver:
         """The assembled 5-point system at the current iterate, as (nz, nr) CUDA tensors."""
         torch = self._torch
         out = {k: torch.empty((self.nz, self.nr), dtype=torch.float64, device=self.device) for k in ('cR', 'cZ', 'diag', 'rhs')}
+        self._enter()                        # hp_assemble_debug synchronises the handle's stream itself
         _lib.check(self.lib.hp_assemble_debug(self._h, float(dt), int(has_old), C.c_void_p(out['cR'].data_ptr()),
                                               C.c_void_p(out['cZ'].data_ptr()), C.c_void_p(out['diag'].data_ptr()),
                                               C.c_void_p(out['rhs'].data_ptr())), 'hp_assemble_debug')
@@ -315,8 +355,10 @@ class ConductionSolver:
         """rho, cp and face-averaged k per cell at the current iterate (main.py:212-254)."""
         torch = self._torch
         out = {k: torch.empty((self.nz, self.nr), dtype=torch.float64, device=self.device) for k in ('rho', 'cp', 'k')}
+        cur = self._enter()
         _lib.check(self.lib.hp_eval_cell_fields(self._h, C.c_void_p(out['rho'].data_ptr()), C.c_void_p(out['cp'].data_ptr()),
                                                 C.c_void_p(out['k'].data_ptr())), 'hp_eval_cell_fields')
+        self._leave(cur, *out.values())
         return out
 
     def eval_property(self, name, T):
@@ -324,8 +366,10 @@ class ConductionSolver:
         torch = self._torch
         Tc = T.to(device=self.device, dtype=torch.float64).contiguous()
         out = torch.empty_like(Tc)
+        cur = self._enter()
         _lib.check(self.lib.hp_eval_property(self._h, _choice(PROP_IDS, name, 'property'), C.c_void_p(Tc.data_ptr()),
                                              C.c_void_p(out.data_ptr()), Tc.numel()), 'hp_eval_property')
+        self._leave(cur, Tc, out)
         return out
 
     # ------------------------------------------------------------------ life cycle

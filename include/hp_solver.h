@@ -82,7 +82,13 @@ typedef struct hp_solve_opts {
     int32_t reuse_converged;  /* 1: a sweep that exactly repeats a sweep which converged before its first iteration (T, T_old, dt
                                  untouched since) only redoes the bookkeeping -- same residual / statistics, no assembly.
                                  Single GPU only.  0 (default): every sweep assembles, like the reference */
-    double mg_omega;        /* mgline: damping of the line smoother */
+    double mg_omega;        /* mgline: damping of the line smoother (default 0.55) */
+    int32_t while_unroll;   /* loop_mode 1: PCG iterations per pass of the device-side WHILE node (1..8, default 1) */
+    int32_t peer_timeout_ms;/* peer-memory slabs: how long a kernel waits for a neighbour's flag before it gives up and raises
+                               the handle's fault (default 60000).  A fault is sticky: every later call on the handle returns an
+                               error until hp_comm_clear_fault */
+    double mg_zscale;       /* mgline: axial coupling of a coarse operator relative to the Galerkin (row-pair aggregation) value;
+                               1 = Galerkin, 0.5 (default) = what a discretisation on the coarse rows gives */
 } hp_solve_opts;
 
 typedef struct hp_sweep_stat {
@@ -102,6 +108,9 @@ int hp_create(hp_handle* out, const hp_mesh_desc* mesh, const hp_phys* phys, voi
 int hp_destroy(hp_handle h);
 int hp_set_stream(hp_handle h, void* stream);
 int hp_set_opts(hp_handle h, const hp_solve_opts* opts);
+/* the options in force (after the library's own adjustments: clamped values, 'mgline' replaced by the line preconditioner
+ * on a mesh too short to coarsen) */
+int hp_get_opts(hp_handle h, hp_solve_opts* out);
 
 /* field access (`T.setValue`, `T.value`, main.py:152,208).  *_dev: device pointers, *_host: host pointers
  * (pinned for true asynchrony).  nz*nr doubles. */
@@ -172,6 +181,12 @@ int hp_comm_init(hp_handle h, int rank, int nranks, const void* id128);
  * the sums in rank order.  The whole time step is then one CUDA graph per rank (loop_mode 1). */
 int hp_peer_export(hp_handle h, const int32_t* nz_of_rank, void* out256);
 int hp_peer_import(hp_handle h, const void* all_handles, const int32_t* nz_of_rank);
+/* 1 if a kernel of this handle gave up waiting for a peer (flags bit3 of hp_sweep_stat).  While the fault is up hp_sweep /
+ * hp_step / hp_run / hp_run_host / hp_get_T_* / hp_get_stats return an error instead of results of a frozen simulation. */
+int hp_comm_fault(hp_handle h);
+/* collective recovery: after EVERY rank has synchronised its stream and passed a host-side barrier, every rank calls this
+ * (and passes another barrier before the next sweep); clears the fault, the mailbox flags and the sequence counters. */
+int hp_comm_clear_fault(hp_handle h);
 
 #ifdef __cplusplus
 }

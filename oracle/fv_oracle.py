@@ -511,8 +511,9 @@ def rline_factor(S: System):
 
 
 # ---------------------------------------------------------------------------
-# 'mgline' preconditioner twin: V(1,1), axial semi-coarsening by row pairs (Galerkin, piecewise constant), damped
-# radial-line Jacobi smoother -- the same cycle as csrc/hp_kernels.cu (k_mg_coarsen / k_mg_res / k_mg_line)
+# 'mgline' preconditioner twin: V(1,1), axial semi-coarsening by row pairs (piecewise-constant aggregation; radial couplings
+# Galerkin, axial coupling scaled by `zscale`: 1 = Galerkin, 1/2 = a discretisation on the coarse rows), damped radial-line
+# Jacobi smoother -- the same cycle as csrc/hp_kernels.cu (k_mg_coarsen / k_mg_res / k_mg_line)
 # ---------------------------------------------------------------------------
 class _MgLevel:
     def __init__(self, cR, cZ, diag):
@@ -534,7 +535,7 @@ class _MgLevel:
         _par_rows(block, nz)
         return out
 
-    def coarsen(self):
+    def coarsen(self, zscale=1.0):
         cR, cZ, dg = self.S.cR, self.S.cZ, self.S.diag
         nz = dg.shape[0]
         nzc = (nz + 1) // 2
@@ -546,16 +547,21 @@ class _MgLevel:
         top = np.where(np.arange(nzc) < nb, 2 * np.arange(nzc) + 1, 2 * np.arange(nzc))   # top fine row of every pair
         cZc[:] = cZ[top]
         cZc[-1, :] = 0.0
+        if zscale != 1.0:
+            # weaker axial coupling, row sums (capacity + boundary terms) kept: diag_c -= (1 - zs) (c_up + c_down)
+            dgc[:-1] -= (1.0 - zscale) * cZc[:-1]
+            dgc[1:] -= (1.0 - zscale) * cZc[:-1]
+            cZc *= zscale
         return _MgLevel(cRc, cZc, dgc)
 
 
-def mg_hierarchy(S: System, max_levels=6):
+def mg_hierarchy(S: System, max_levels=6, zscale=0.5):
     cZ = S.cZ.copy()
     cZ[-1, :] = 0.0
     levels = [_MgLevel(S.cR, cZ, S.diag)]
     nzl = S.diag.shape[0]
     while len(levels) < max_levels and nzl >= 32:
-        levels.append(levels[-1].coarsen())
+        levels.append(levels[-1].coarsen(zscale))
         nzl = (nzl + 1) // 2
     return levels
 
@@ -571,7 +577,7 @@ def _prolong(e, nz):
     return np.repeat(e, 2, axis=0)[:nz]
 
 
-def mg_vcycle(levels, r, zline, omega=0.7, coarse_sweeps=2):
+def mg_vcycle(levels, r, zline, omega=0.55, coarse_sweeps=2):
     """z = V(r); `zline` = M_line^-1 r of the fine level (what k_cg_B leaves in z)."""
     c = len(levels) - 1
     xs, rs = [omega * zline], [r]
@@ -652,11 +658,11 @@ def pcg(S: System, x0=None, precond='rline', tol=1e-9, criterion='precond_inf', 
     return x
 
 
-def _pcg_mgline(S, x, r, tol, criterion, max_iter, info, max_levels=6, omega=0.7, coarse_sweeps=2):
+def _pcg_mgline(S, x, r, tol, criterion, max_iter, info, max_levels=6, omega=0.55, coarse_sweeps=2, zscale=0.5):
     """PCG with the V-cycle as preconditioner; the stopping measure stays max|M_line^-1 r| (same rule as 'rline')."""
     if criterion != 'precond_inf':
         raise ValueError("mgline twin implements the precond_inf criterion")
-    levels = mg_hierarchy(S, max_levels)
+    levels = mg_hierarchy(S, max_levels, zscale)
     if len(levels) < 2:
         raise ValueError("mesh too short to coarsen")
     it = 0

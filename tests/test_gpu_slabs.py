@@ -45,3 +45,68 @@ def test_slabs_match_single_domain_oracle(cfg, tmp_path, world, shape, comm, loo
         for _ in range(sweeps):
             o.sweep(0.1, solver='banded' if grid.nr <= 160 else 'splu')
     assert np.max(np.abs(T - o.T)) <= 1e-6 * n_steps * sweeps
+
+
+def _run_workers(world, shape, n_steps, sweeps, out, comm, loop_mode, precond):
+    port = _free_port()
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, 'tests', 'slab_worker.py'), str(r), str(world), str(port),
+                               ','.join(map(str, shape)), str(n_steps), str(sweeps), out, comm, loop_mode, precond]) for r in range(world)]
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+
+
+@pytest.mark.parametrize('world,shape', [(2, (256, 8, 16, 40)),          # 5 levels, fused stages (nr = 64)
+                                         (2, (64, 512, 1024, 2560)),     # nr = 4096: the row shape of BASELINE configs[3]
+                                         (4, (512, 32, 64, 160)),        # 6 levels over 4 slabs of 128 rows
+                                         (2, (100, 12, 24, 64))])        # odd coarse row counts in the last slab
+def test_distributed_vcycle_is_the_single_domain_one(cfg, tmp_path, world, shape):
+    """Peer-memory slabs with 'mgline': the hierarchy is the whole-mesh one, distributed (boundary rows of every V-cycle
+    stage handed to the neighbours) -- the field equals the single-domain oracle's AND the PCG takes the same number of
+    iterations as the same mesh on one GPU (the r1 rank-local cycle needed 26 -> 36 per step at 8 slabs)."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from oracle import fv_oracle as fo
+    from heat_pipe_solver_b200 import ConductionSolver, generate_composite_mesh
+    out = str(tmp_path / 'slab.npy')
+    n_steps, sweeps = 2, 3
+    _run_workers(world, shape, n_steps, sweeps, out, 'p2p', 'graph', 'mgline')
+    T = np.load(out)
+    it_slabs = np.load(out + '.iters.npy')
+    grid = fo.build_grid(fo.synthetic_mesh_params(*shape), cfg['dimensions'])
+    z = grid.z_c[:, None] / grid.z_v[-1]
+    T0 = 290.0 + 250.0 * np.exp(-((z - 0.45) / 0.3) ** 2) * np.ones((1, grid.nr))
+    o = fo.Oracle(grid, fo.case_from_config(), T0=T0, has_old=True)
+    for _ in range(n_steps):
+        o.update_old()
+        for _ in range(sweeps):
+            o.sweep(0.1, solver='banded' if grid.nr <= 160 else 'splu')
+    assert np.max(np.abs(T - o.T)) <= 1e-6 * n_steps * sweeps
+    mesh, _ = generate_composite_mesh(fo.synthetic_mesh_params(*shape), cfg['dimensions'])
+    with ConductionSolver(mesh, cfg['dimensions'], cfg['parameters'], cfg['constants'], precond='mgline', poll_chunk=4) as s:
+        s.set_value(T0)
+        s.run(0.1, n_steps, sweeps=sweeps, has_old=True)
+        it_one = np.array([st['iters'] for st in s.stats(sweeps * n_steps)])
+        assert s.effective_precond == 'mgline'
+    assert np.all(np.abs(it_slabs - it_one) <= 1), (it_slabs, it_one)
+
+
+def test_main_run_under_slabs_matches_single_gpu(cfg, tmp_path):
+    """`python -m torch.distributed.run --nproc-per-node 2 -m heat_pipe_solver_b200.main` (the reference's
+    `mpirun -np 2 python main.py`, main.py:11,339): same captured profiles as the one-GPU run, and the reference's
+    per-rank console line."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    save = str(tmp_path / 'run2')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', str(_free_port()), '-m', 'heat_pipe_solver_b200.main', '--t-end', '6', '--dt', '0.1',
+           '--mesh', '128,8,16,40', '--save', save]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-3000:]
+    assert '4096 cells on processor 0 of 2' in p.stdout and '4096 cells on processor 1 of 2' in p.stdout
+    from heat_pipe_solver_b200.main import run
+    one = run(t_end=6.0, dt=0.1, mesh_params=dict(nx_wall=128, nr_wall=40, nx_wick=128, nr_wick=16, nx_vc=128, nr_vc=8))
+    two = np.load(save + '.npz')
+    assert np.max(np.abs(two['T'] - one['T'])) <= 1e-6
+    assert np.max(np.abs(two['profiles'] - one['profiles'])) <= 1e-6

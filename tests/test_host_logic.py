@@ -125,3 +125,30 @@ def test_slab_partition_under_gloo_world_size_2():
         p.join(120)
         assert p.exitcode == 0
     assert dict(out) == {0: True, 1: True}
+
+
+def test_aligned_slab_cuts_and_global_precond_resolution():
+    """Peer-memory slabs with 'mgline' cut the mesh on multiples of 2^(levels-1) rows (the distributed V-cycle is then the
+    single-domain one), and 'auto' / the mgline->rline fallback are decided from the GLOBAL mesh: every rank gets the same
+    answer even when the slabs differ by a row (nz=1023, nr=512, world=2 gave mgline on one rank, rline on the other)."""
+    from heat_pipe_solver_b200.distributed import mg_level_count, resolve_precond, slab_alignment, slab_rows
+    assert [mg_level_count(n) for n in (16, 31, 32, 64, 500, 4096, 16384)] == [1, 1, 2, 3, 6, 6, 6]
+    for nz, world in ((16384, 8), (16384, 4), (4096, 2), (1000, 3), (100, 2), (64, 2), (70, 4)):
+        a = slab_alignment(nz, world)
+        cuts = [slab_rows(nz, r, world, a) for r in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == nz
+        assert all(c0[1] == c1[0] for c0, c1 in zip(cuts, cuts[1:]))
+        assert all((b - a_) % a == 0 for a_, b in cuts[:-1]) and all(b > a_ for a_, b in cuts)
+        sizes = [b - a_ for a_, b in cuts[:-1]]
+        assert max(sizes) - min(sizes) <= a
+    assert slab_alignment(16384, 8) == 32 and slab_rows(16384, 3, 8, 32) == (6144, 8192)
+    assert slab_alignment(64, 2) == 4 and slab_alignment(70, 4) == 4
+    # the same decision on every rank, whatever its own slab looks like
+    assert resolve_precond('auto', 1023, 512, 2, 'p2p') == 'mgline'
+    assert resolve_precond('auto', 1023, 512, 2, 'nccl') == 'mgline'
+    assert resolve_precond('auto', 63, 64, 2, 'p2p') == 'rline'
+    assert resolve_precond('mgline', 63, 64, 2, 'nccl') == 'rline'          # 31-row slab cannot coarsen: all ranks use rline
+    assert resolve_precond('mgline', 40, 64, 2, 'p2p') == 'mgline' and resolve_precond('mgline', 20, 64, 2, 'p2p') == 'rline'
+    assert resolve_precond('jacobi', 4096, 1024, 8, 'p2p') == 'jacobi'
+    with pytest.raises(ValueError):
+        slab_rows(64, 0, 9, 8)

@@ -133,7 +133,7 @@ def test_pcg_iteration_counts_are_modest_with_line_preconditioner(cfg):
 def test_mgline_twin_matches_direct_solve_and_needs_few_iterations(cfg):
     """The oracle's twin of the GPU 'mgline' preconditioner (V-cycle, axial semi-coarsening by row pairs, damped
     radial-line Jacobi): same answer as the direct solve, mesh-independent iteration counts, odd row counts handled."""
-    for shape, max_it in (((64, 4, 8, 20), 8), ((250, 8, 16, 40), 14), ((512, 16, 32, 80), 20)):
+    for shape, max_it in (((64, 4, 8, 20), 10), ((250, 8, 16, 40), 14), ((512, 16, 32, 80), 20)):
         grid = fo.build_grid(fo.synthetic_mesh_params(*shape), cfg['dimensions'])
         z = grid.z_c[:, None] / grid.z_v[-1]
         T0 = 290.0 + 300.0 * np.exp(-((z - 0.1) / 0.35) ** 2) * np.ones((1, grid.nr))
@@ -149,8 +149,8 @@ def test_mgline_twin_matches_direct_solve_and_needs_few_iterations(cfg):
     # the hierarchy: 250 -> 125 -> 63 -> 32 -> 16 rows
     S = fo.Oracle(fo.build_grid(fo.synthetic_mesh_params(250, 8, 16, 40), cfg['dimensions']), fo.case_from_config()).assemble(0.1)
     assert [lv.S.diag.shape[0] for lv in fo.mg_hierarchy(S)] == [250, 125, 63, 32, 16]
-    # Galerkin coarse operator = P^T A P for P = row-pair injection
-    lv = fo.mg_hierarchy(S, max_levels=2)
+    # zscale = 1: Galerkin coarse operator = P^T A P for P = row-pair injection
+    lv = fo.mg_hierarchy(S, max_levels=2, zscale=1.0)
     nz, nr = S.diag.shape
     x = np.random.default_rng(1).standard_normal((lv[1].S.diag.shape[0], nr))
     Px = np.repeat(x, 2, axis=0)[:nz]
@@ -158,6 +158,19 @@ def test_mgline_twin_matches_direct_solve_and_needs_few_iterations(cfg):
     PtAPx = A_Px[0::2].copy()
     PtAPx[:nz // 2] += A_Px[1::2]
     assert np.allclose(PtAPx, lv[1].S.matvec(x), rtol=1e-12, atol=1e-12 * np.abs(S.diag).max())
+    # default zscale = 1/2: half the axial coupling, same row sums (capacity + boundary terms), same radial part
+    half = fo.mg_hierarchy(S, max_levels=2)[1].S
+    one = np.ones_like(half.diag)
+    assert np.allclose(half.matvec(one), lv[1].S.matvec(one), rtol=1e-10, atol=1e-12 * np.abs(S.diag).max())
+    assert np.allclose(half.cZ, 0.5 * lv[1].S.cZ) and np.array_equal(half.cR, lv[1].S.cR)
+    # on an axially refined mesh the rescaled operator needs a fraction of the Galerkin iterations
+    grid = fo.build_grid(fo.synthetic_mesh_params(2048, 4, 8, 20), cfg['dimensions'])
+    its = {}
+    for zs, om in ((1.0, 0.7), (0.5, 0.55)):
+        o = fo.Oracle(grid, fo.case_from_config())
+        o.sweep(0.1, solver='pcg_mgline', tol=1e-9, mg=dict(zscale=zs, omega=om))
+        its[zs] = o.last_solver_info['iterations']
+    assert its[0.5] <= 0.7 * its[1.0], its
 
 
 @pytest.mark.parametrize('name', ['simple_1sweep', 'tdep_5sweeps', 'intended_physics'])
