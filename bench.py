@@ -510,7 +510,7 @@ def main():
                          'they only precondition, the answer is unchanged)')
     ap.add_argument('--mg-levels', type=int, default=6)
     ap.add_argument('--mg-sweeps', type=int, default=2)
-    ap.add_argument('--mg-omega', type=float, default=0.7)
+    ap.add_argument('--mg-omega', type=float, default=0.6)
     ap.add_argument('--reuse-converged', action='store_true',
                     help='sweeps that exactly repeat a converged sweep only redo the bookkeeping (off: every sweep assembles, like the reference)')
     ap.add_argument('--comm', default='p2p', choices=['p2p', 'nccl'], help='slab exchange: NVLink peer stores fused into the kernels, or NCCL calls')

@@ -96,6 +96,8 @@ struct hp_solver_s {
     cudaStream_t stream = nullptr;
     hp_phys phys{};
     hp_solve_opts opts{};
+    int req_precond = 1;             // what the caller asked for (opts.precond falls back to 1 on a mesh too short to coarsen;
+                                     // re-resolved when the slab topology changes)
     HpDev d{};
     HpLaunchCfg cfg{};
     std::vector<void*> allocs;
@@ -245,7 +247,7 @@ static int ensure_levels(hp_solver_s* h) {
         double** f[LV_FIELDS] = {&L.cR, &L.cZ, &L.diag, &L.dinv, &L.rhs, &L.x, &L.x2, &L.tmp};
         for (int k = 0; k < LV_FIELDS; ++k) *f[k] = h->lvblock + h->lay.off[l][k];
     }
-    h->mg_upfused = hpk::mg_fused_supported(h->cfg) && h->cfg.ncolA == 1;
+    h->mg_upfused = hpk::mg_fused_supported(h->cfg);
     return 0;
 }
 
@@ -255,6 +257,18 @@ static int setup_mg(hp_solver_s* h) {
     if (want > h->lay.n) want = h->lay.n;
     h->nlev = want;
     h->d.mg_local = (h->nranks > 1 && !h->d.p2p) ? 1 : 0;
+    return 0;
+}
+
+// 'mgline' asked for: build the hierarchy for the current topology; a mesh too short to coarsen gets the plain line
+// preconditioner.  Under peer-memory slabs the level count comes from the global mesh, so every rank takes the same
+// decision; slabs without peer memory decide per rank -- the caller (distributed.make_solver_for_rank) resolves the
+// preconditioner globally before it gets here.
+static int resolve_mg(hp_solver_s* h) {
+    if (h->req_precond != 2) return 0;
+    h->opts.precond = 2;
+    if (setup_mg(h)) return -1;
+    if (h->nlev < 2) h->opts.precond = 1;
     return 0;
 }
 
@@ -376,7 +390,7 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
 
     h->opts.precond = 1; h->opts.criterion = 0; h->opts.tol = 1e-9; h->opts.max_iter = 5000;
     h->opts.loop_mode = 1; h->opts.poll_chunk = 8; h->opts.refactor_every = 1; h->opts.extrapolate = 3;
-    h->opts.mg_levels = 6; h->opts.mg_coarse_sweeps = 2; h->opts.mg_omega = 0.55; h->opts.reuse_converged = 0;
+    h->opts.mg_levels = 6; h->opts.mg_coarse_sweeps = 2; h->opts.mg_omega = 0.6; h->opts.reuse_converged = 0;
     h->opts.while_unroll = 1; h->opts.peer_timeout_ms = 60000; h->opts.mg_zscale = 0.5;
 
     // initial field + snapshots (main.py:34,133,145,152)
@@ -444,24 +458,19 @@ int hp_set_opts(hp_handle h, const hp_solve_opts* o) {
     if (o->max_iter < 1) return fail("hp_set_opts: max_iter must be >= 1");
     if (o->loop_mode < 0 || o->loop_mode > 1) return fail("hp_set_opts: loop_mode must be 0 or 1");
     h->opts = *o;
+    h->req_precond = o->precond;
     if (h->opts.poll_chunk < 1) h->opts.poll_chunk = 8;
     if (h->opts.refactor_every < 1) h->opts.refactor_every = 1;
     if (h->opts.mg_levels < 2) h->opts.mg_levels = 6;
     if (h->opts.mg_levels > HP_MAX_LEVELS) h->opts.mg_levels = HP_MAX_LEVELS;
     if (h->opts.mg_coarse_sweeps < 0) h->opts.mg_coarse_sweeps = 2;
     if (h->opts.mg_coarse_sweeps > 8) h->opts.mg_coarse_sweeps = 8;
-    if (!(h->opts.mg_omega > 0.0 && h->opts.mg_omega <= 1.0)) h->opts.mg_omega = 0.55;
+    if (!(h->opts.mg_omega > 0.0 && h->opts.mg_omega <= 1.0)) h->opts.mg_omega = 0.6;
     if (!(h->opts.mg_zscale > 0.0 && h->opts.mg_zscale <= 1.0)) h->opts.mg_zscale = 0.5;
     if (h->opts.while_unroll < 1) h->opts.while_unroll = 1;
     if (h->opts.while_unroll > 8) h->opts.while_unroll = 8;
     if (h->opts.peer_timeout_ms < 1) h->opts.peer_timeout_ms = 60000;
-    if (h->opts.precond == 2) {
-        if (setup_mg(h)) return -1;
-        // mesh too short to coarsen: plain line preconditioner.  Under peer-memory slabs the level count comes from the
-        // global mesh, so every rank takes the same decision; slabs without peer memory decide per rank -- the caller
-        // (distributed.make_solver_for_rank) resolves the preconditioner globally before it gets here
-        if (h->nlev < 2) h->opts.precond = 1;
-    }
+    if (resolve_mg(h)) return -1;
     return invalidate_noop(h);
 }
 
@@ -1135,11 +1144,7 @@ int hp_peer_import(hp_handle h, const void* all_handles, const int32_t* nz_of_ra
     d.p2p = 1;
     h->ghost_dirty = true;
     destroy_graphs(h);
-    if (h->opts.precond == 2) {                              // the cycle becomes the distributed whole-mesh hierarchy
-        if (setup_mg(h)) return -1;
-        if (h->nlev < 2) h->opts.precond = 1;
-    }
-    return 0;
+    return resolve_mg(h);                                    // the cycle becomes the distributed whole-mesh hierarchy
 }
 
 int hp_comm_fault(hp_handle h) { return (h && h->h_fault && *(volatile int*)h->h_fault) ? 1 : 0; }
@@ -1217,6 +1222,7 @@ int hp_comm_init(hp_handle h, int rank, int nranks, const void* id128) {
     CK(cudaMemsetAsync(h->d.red_local, 0, sizeof(double) * HP_NRED, h->stream));
     h->d.nranks = nranks; h->d.rank = rank;
     destroy_graphs(h);
+    if (resolve_mg(h)) return -1;          // slabs without peer memory: the V-cycle turns rank-local
     // the snapshot couplings across slab interfaces were assembled from the T_amb-filled ghost rows at create
     // time (both neighbours compute the same value); nothing to exchange here.
     return 0;

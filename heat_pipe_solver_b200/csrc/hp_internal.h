@@ -146,6 +146,7 @@ struct HpLaunchCfg {
     int cta_threads, teams_per_cta;              // marching kernels; their grid = one resident wave (team_grid)
     // k_cg_A (no row-wide dependency: rows wider than tplA*eptA are cut into ncolA column tiles)
     int tplA, eptA, vecA, ctaA, teams_per_ctaA, ncolA;
+    int clF;                 // fused V-cycle stages: CTAs per row (thread-block cluster), 1 = one CTA team, 0 = unsupported
     int num_sms, nz;
     int grid_cell, cta_cell;                     // grid for thread-per-cell kernels
     int grid_factor, cta_factor;

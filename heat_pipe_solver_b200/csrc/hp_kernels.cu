@@ -17,6 +17,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include "hp_internal.h"
 #include "hp_props.cuh"
 
@@ -565,9 +566,28 @@ __device__ __forceinline__ unsigned team_mask() {
     else return ((1u << TPL) - 1u) << ((threadIdx.x & 31) & ~(TPL - 1));
 }
 
-template <int TPL>
+// ---- thread-block clusters: a row wider than one CTA's team (nr > 1024) is owned by CL CTAs of 256 threads; the scan
+// carries of the line solve travel through distributed shared memory, one cluster barrier per direction.
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store v into the same shared-memory slot of CTA `cta` of this cluster
+__device__ __forceinline__ void st_cluster_f64(double* local_slot, unsigned cta, double v) {
+    unsigned la = (unsigned)__cvta_generic_to_shared(local_slot), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(cta));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
+
+template <int TPL, int CL = 1>
 __device__ __forceinline__ void team_barrier(int team_in_cta) {
-    if constexpr (TPL > 32) {
+    if constexpr (CL > 1) {
+        cluster_barrier();
+    } else if constexpr (TPL > 32) {
         asm volatile("bar.sync %0, %1;" ::"r"(team_in_cta + 1), "r"(TPL) : "memory");
     } else {
         __syncwarp(team_mask<TPL>());
@@ -580,11 +600,11 @@ __device__ __forceinline__ void team_barrier(int team_in_cta) {
 // Thread-local composition, warp shuffle scan, <= 32 warp totals through shared memory (one team barrier per
 // direction).  m0_edge = cR_{i0-1} dinv_{i0-1} for lane 0 of every warp but the first (fetched with the row loads).
 // ------------------------------------------------------------------------------------------------
-template <int TPL, int EPT>
+template <int TPL, int EPT, int CL = 1>
 __device__ __forceinline__ void line_solve(const double (&rv)[EPT], const double (&dv)[EPT], const double (&cr)[EPT],
                                            double m0_edge, int lane, int wt, int team_in_cta, double* s_fA, double* s_fB,
                                            double* s_bA, double* s_bB, double (&zv)[EPT]) {
-    constexpr int NW = TeamGeom<TPL>::NW, W = TeamGeom<TPL>::W;
+    constexpr int NW = TeamGeom<TPL>::NW * CL, W = TeamGeom<TPL>::W;       // wt = warp index inside the whole team
     const unsigned tm = team_mask<TPL>();
     double nb[EPT];     // cR_i * dinv_i : backward multiplier of cell i, forward multiplier of cell i+1
 #pragma unroll
@@ -613,8 +633,15 @@ __device__ __forceinline__ void line_solve(const double (&rv)[EPT], const double
     if (lane == 0) { Ax = 1.0; Bx = 0.0; }
     double carry = 0.0;
     if constexpr (NW > 1) {
-        if (lane == W - 1) { s_fA[wt] = A; s_fB[wt] = B; }
-        team_barrier<TPL>(team_in_cta);
+        if constexpr (CL > 1) {
+            if (lane == W - 1) {
+#pragma unroll
+                for (unsigned c = 0; c < (unsigned)CL; ++c) { st_cluster_f64(&s_fA[wt], c, A); st_cluster_f64(&s_fB[wt], c, B); }
+            }
+        } else {
+            if (lane == W - 1) { s_fA[wt] = A; s_fB[wt] = B; }
+        }
+        team_barrier<TPL, CL>(team_in_cta);
         for (int w = 0; w < wt; ++w) carry = fma(s_fA[w], carry, s_fB[w]);
     }
     const double ybefore = fma(Ax, carry, Bx);
@@ -640,8 +667,15 @@ __device__ __forceinline__ void line_solve(const double (&rv)[EPT], const double
     if (lane == W - 1) { Ax = 1.0; Bx = 0.0; }
     carry = 0.0;
     if constexpr (NW > 1) {
-        if (lane == 0) { s_bA[wt] = A; s_bB[wt] = B; }
-        team_barrier<TPL>(team_in_cta);
+        if constexpr (CL > 1) {
+            if (lane == 0) {
+#pragma unroll
+                for (unsigned c = 0; c < (unsigned)CL; ++c) { st_cluster_f64(&s_bA[wt], c, A); st_cluster_f64(&s_bB[wt], c, B); }
+            }
+        } else {
+            if (lane == 0) { s_bA[wt] = A; s_bB[wt] = B; }
+        }
+        team_barrier<TPL, CL>(team_in_cta);
         for (int w = NW - 1; w > wt; --w) carry = fma(s_bA[w], carry, s_bB[w]);
     }
     const double zafter = fma(Ax, carry, Bx);
@@ -966,7 +1000,7 @@ __global__ void __launch_bounds__(256) k_stash(HpDev d, hp_phys ph, HpKArgs a) {
 // ================================================================================================
 
 // the team that owns the first (lo) / last (hi) rows of a stage waits for the rows its neighbours pushed in stage x.wait
-template <int TPL>
+template <int TPL, int CL = 1>
 __device__ __forceinline__ void stage_wait(const HpDev& d, const HpKArgs& a, const HpXchg& x, bool lo, bool hi, int tl,
                                            int team_in_cta, unsigned long long cyc) {
     if (x.wait < 0 || !d.p2p) return;
@@ -979,18 +1013,18 @@ __device__ __forceinline__ void stage_wait(const HpDev& d, const HpKArgs& a, con
         if (hi && ok) ok = wait_peer_flag(d, a, x.wait, d.rank + 1, cyc);
         if (!ok) raise_fault(d);
     }
-    team_barrier<TPL>(team_in_cta);
+    team_barrier<TPL, CL>(team_in_cta);
     __threadfence_system();                       // every reader of the ghost rows orders its loads after the acquire
 }
 
 // boundary row of a stage's output -> the neighbour's ghost row, then the stage flag (release, system scope)
-template <int TPL, int EPT, bool VEC>
+template <int TPL, int EPT, bool VEC, int CL = 1>
 __device__ __forceinline__ void stage_push(const HpDev& d, const HpXchg& x, bool is_lo, double* dst, int i0, int nr,
                                            const double (&v)[EPT], int tl, int team_in_cta, unsigned long long cyc) {
     store_row<EPT, VEC>(dst, i0, nr, v);
     if (x.sig < 0) return;
     __threadfence_system();
-    team_barrier<TPL>(team_in_cta);
+    team_barrier<TPL, CL>(team_in_cta);
     if (tl == 0) {
         unsigned long long* f = &d.comm_peer[is_lo ? d.rank - 1 : d.rank + 1]->flag[x.sig][d.rank];
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(cyc) : "memory");
@@ -1035,18 +1069,19 @@ __global__ void __launch_bounds__(256) k_mg_coarsen(HpLevel f, HpLevel c, int nr
 // row g only needs the residual of row g).  MODE 2 fuses the pre-smoothing of the NEXT level into the restriction:
 // c_x(J) = omega * M_{L+1}^-1 crhs(J) as soon as the coarse row J = pair-sum of residual rows is complete.  Both need the
 // team to own whole rows (no column tiles).
-template <int TPL, int EPT, bool VEC, int MODE = 0>
+template <int TPL, int EPT, bool VEC, int MODE = 0, int CL = 1>
 __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpKArgs& a, const HpLevel& L, const HpMgResArgs& m, long long team,
                                             long long nteams, double omega = 0.0, double* s_fA = nullptr,
                                             double* s_fB = nullptr, double* s_bA = nullptr, double* s_bB = nullptr) {
     const int nr = d.nr, nz = L.nz;
-    const int tl = threadIdx.x % TPL, lane = threadIdx.x & (TeamGeom<TPL>::W - 1);
+    // CL > 1: the team is a cluster of CL CTAs (TPL threads each); tl runs over the whole team
+    const int tl = (CL > 1 ? (int)cluster_ctarank() * TPL : 0) + threadIdx.x % TPL, lane = threadIdx.x & (TeamGeom<TPL>::W - 1);
     const int team_in_cta = threadIdx.x / TPL;
     const unsigned long long cyc = d.st->cycle;
-    const int ncol = d.ncolA;
+    const int ncol = (MODE == 0) ? d.ncolA : 1;            // the fused stages own whole rows
     const long long nchunks = nteams / ncol;
     const long long chunk = team / ncol;
-    const int i0 = ((int)(team % ncol) * TPL + tl) * EPT;
+    const int i0 = ((int)(team % ncol) * TPL * CL + tl) * EPT;
     // chunks are made of whole row pairs so that a restricted row is produced by one team
     const long long npairs = (nz + 1) / 2;
     int ja = 0, jb = 0;
@@ -1080,7 +1115,7 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpKArgs& a, co
         return v;
     };
     if (jb > ja) {
-        stage_wait<TPL>(d, a, m.xc, ja == 0, jb == nz, tl, team_in_cta, cyc);
+        stage_wait<TPL, CL>(d, a, m.xc, ja == 0, jb == nz, tl, team_in_cta, cyc);
         double xm[EPT], xc[EPT], xn[EPT], czm[EPT], rprev[EPT];
         double xc_l = 0.0, xc_r = 0.0;
         xrow(ja, xm);
@@ -1154,12 +1189,12 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpKArgs& a, co
             }
             if constexpr (MODE == 1) {
                 double zv[EPT];
-                line_solve<TPL, EPT>(res, dv, cr, m0_edge, lane, tl >> 5, team_in_cta, s_fA, s_fB, s_bA, s_bB, zv);
+                line_solve<TPL, EPT, CL>(res, dv, cr, m0_edge, lane, tl >> 5, team_in_cta, s_fA, s_fB, s_bA, s_bB, zv);
 #pragma unroll
                 for (int k = 0; k < EPT; ++k) zv[k] = fma(omega, zv[k], xc[k]);
                 store_row<EPT, VEC>(m.xout + rb, i0, nr, zv);
-                if (g == 1 && m.xc.push_lo) stage_push<TPL, EPT, VEC>(d, m.xc, true, m.xc.push_lo, i0, nr, zv, tl, team_in_cta, cyc);
-                if (g == nz && m.xc.push_hi) stage_push<TPL, EPT, VEC>(d, m.xc, false, m.xc.push_hi, i0, nr, zv, tl, team_in_cta, cyc);
+                if (g == 1 && m.xc.push_lo) stage_push<TPL, EPT, VEC, CL>(d, m.xc, true, m.xc.push_lo, i0, nr, zv, tl, team_in_cta, cyc);
+                if (g == nz && m.xc.push_hi) stage_push<TPL, EPT, VEC, CL>(d, m.xc, false, m.xc.push_hi, i0, nr, zv, tl, team_in_cta, cyc);
             } else {
                 if (m.xout) store_row<EPT, VEC>(m.xout + rb, i0, nr, xc);
                 if (m.resout) store_row<EPT, VEC>(m.resout + rb, i0, nr, res);
@@ -1172,13 +1207,13 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpKArgs& a, co
                     store_row<EPT, VEC>(m.crhs + cb, i0, nr, sum);
                     if constexpr (MODE == 2) {
                         double zc[EPT];
-                        line_solve<TPL, EPT>(sum, cdv, ccr, m0_edge, lane, tl >> 5, team_in_cta, s_fA, s_fB, s_bA, s_bB, zc);
+                        line_solve<TPL, EPT, CL>(sum, cdv, ccr, m0_edge, lane, tl >> 5, team_in_cta, s_fA, s_fB, s_bA, s_bB, zc);
 #pragma unroll
                         for (int k = 0; k < EPT; ++k) zc[k] *= omega;
                         store_row<EPT, VEC>(m.c_x + cb, i0, nr, zc);
                         const int Jg = ((g - 1) >> 1) + 1;
-                        if (Jg == 1 && m.xc.push_lo) stage_push<TPL, EPT, VEC>(d, m.xc, true, m.xc.push_lo, i0, nr, zc, tl, team_in_cta, cyc);
-                        if (Jg == m.nzc && m.xc.push_hi) stage_push<TPL, EPT, VEC>(d, m.xc, false, m.xc.push_hi, i0, nr, zc, tl, team_in_cta, cyc);
+                        if (Jg == 1 && m.xc.push_lo) stage_push<TPL, EPT, VEC, CL>(d, m.xc, true, m.xc.push_lo, i0, nr, zc, tl, team_in_cta, cyc);
+                        if (Jg == m.nzc && m.xc.push_hi) stage_push<TPL, EPT, VEC, CL>(d, m.xc, false, m.xc.push_hi, i0, nr, zc, tl, team_in_cta, cyc);
                     }
                 } else {
 #pragma unroll
@@ -1212,6 +1247,29 @@ k_mg_fused(HpDev d, HpKArgs a, HpLevel L, HpMgResArgs m) {
     mg_res_body<TPL, EPT, VEC, MODE>(d, a, L, m, (long long)blockIdx.x * G::LPC + tic, (long long)gridDim.x * G::LPC, a.omega,
                                      s_fA[tic], s_fB[tic], s_bA[tic], s_bB[tic]);
 }
+// the same stages for rows of 1024 < nr <= 4096 cells: a cluster of CL CTAs (256 threads x 4 cells each) owns a row.  The
+// cluster shape is a compile-time attribute, so plain launches and graph kernel nodes need no launch attribute.
+#define HP_CLUSTER_FUSED(CLN)                                                                                          \
+    template <bool VEC, int MODE>                                                                                      \
+    __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(256, 2)                                               \
+    k_mg_fused_cl##CLN(HpDev d, HpKArgs a, HpLevel L, HpMgResArgs m) {                                                 \
+        if (d.st->mg_skip) return;                                                                                     \
+        __shared__ double s_fA[8 * CLN], s_fB[8 * CLN], s_bA[8 * CLN], s_bB[8 * CLN];                                  \
+        mg_res_body<256, 4, VEC, MODE, CLN>(d, a, L, m, (long long)(blockIdx.x / CLN), (long long)(gridDim.x / CLN),   \
+                                            a.omega, s_fA, s_fB, s_bA, s_bB);                                          \
+    }
+HP_CLUSTER_FUSED(2)
+HP_CLUSTER_FUSED(4)
+#undef HP_CLUSTER_FUSED
+static const void* fn_mg_fused_cluster(int cl, bool vec, int mode) {
+    if (cl == 2) {
+        if (mode == 1) return vec ? (const void*)k_mg_fused_cl2<true, 1> : (const void*)k_mg_fused_cl2<false, 1>;
+        return vec ? (const void*)k_mg_fused_cl2<true, 2> : (const void*)k_mg_fused_cl2<false, 2>;
+    }
+    if (mode == 1) return vec ? (const void*)k_mg_fused_cl4<true, 1> : (const void*)k_mg_fused_cl4<false, 1>;
+    return vec ? (const void*)k_mg_fused_cl4<true, 2> : (const void*)k_mg_fused_cl4<false, 2>;
+}
+
 template <int TPL, int EPT, bool VEC>
 const void* fn_mg_up() { return (const void*)k_mg_fused<TPL, EPT, VEC, 1>; }
 template <int TPL, int EPT, bool VEC>
@@ -1360,6 +1418,7 @@ bool pick_config(int nr, int nz, int num_sms, HpLaunchCfg* cfg, const char** err
     cfg->ctaA = 256;
     cfg->teams_per_ctaA = 256 / cfg->tplA;
     cfg->ncolA = (nr + cfg->tplA * cfg->eptA - 1) / (cfg->tplA * cfg->eptA);
+    cfg->clF = nr <= 1024 ? 1 : (nr <= 2048 ? 2 : (nr <= 4096 ? 4 : 0));     // CTAs per row of the fused V-cycle stages
     cfg->num_sms = num_sms; cfg->nz = nz;
     cfg->cta_cell = 256;
     long long ncell = (long long)(nz + 1) * nr;
@@ -1432,7 +1491,26 @@ HpKernelLaunch desc_mg_res(const HpLaunchCfg& c, int nz_level) {
     cl.nz = (nz_level + 1) / 2;                      // chunks are whole row pairs
     return {f, dim3(team_grid(f, cl, c.ctaA, c.teams_per_ctaA, c.ncolA)), dim3(c.ctaA), 0};
 }
+// fused stage on cluster teams: one resident wave of clusters, >= one row pair per cluster
+static HpKernelLaunch desc_fused_cluster(const HpLaunchCfg& c, int nz_level, int mode) {
+    const void* f = fn_mg_fused_cluster(c.clF, c.vecA, mode);
+    int nclus = 0;
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3(c.clF * c.num_sms); lc.blockDim = dim3(256);
+    if (cudaOccupancyMaxActiveClusters(&nclus, f, &lc) != cudaSuccess || nclus < 1) {
+        cudaGetLastError();
+        nclus = (c.num_sms * 2 / c.clF) * 7 / 8;
+    }
+    long long pairs = (nz_level + 1) / 2;
+    long long chunks = nclus < pairs ? nclus : pairs;
+    if (chunks < 1) chunks = 1;
+    long long grid = chunks * c.clF;
+    if (grid > HP_MAX_PARTIALS) grid = (HP_MAX_PARTIALS / c.clF) * c.clF;
+    return {f, dim3((unsigned)grid), dim3(256), 0};
+}
 HpKernelLaunch desc_mg_up(const HpLaunchCfg& c, int nz_level) {       // only when mg_fused_supported(c)
+    if (c.clF > 1) return desc_fused_cluster(c, nz_level, 1);
     const void* f = nullptr;
 #define HP_X(T, E, V) f = fn_mg_up<T, E, V>()
     HP_DISPATCH_A(c, HP_X);
@@ -1442,6 +1520,7 @@ HpKernelLaunch desc_mg_up(const HpLaunchCfg& c, int nz_level) {       // only wh
     return {f, dim3(team_grid(f, cl, c.ctaA, c.teams_per_ctaA, 1)), dim3(c.ctaA), 0};
 }
 HpKernelLaunch desc_mg_down(const HpLaunchCfg& c, int nz_level) {     // only when mg_fused_supported(c)
+    if (c.clF > 1) return desc_fused_cluster(c, nz_level, 2);
     const void* f = nullptr;
 #define HP_X(T, E, V) f = fn_mg_down<T, E, V>()
     HP_DISPATCH_A(c, HP_X);
@@ -1461,7 +1540,8 @@ HpKernelLaunch desc_mg_line(const HpLaunchCfg& c, int nz_level) {
 }
 // the fused stages need the row teams of the residual and of the line solve to have the same shape (nr <= 1024)
 bool mg_fused_supported(const HpLaunchCfg& c) {
-    return c.tplA == c.tpl && c.eptA == c.ept && c.vecA == c.vec && c.ctaA == c.cta_threads;
+    if (c.clF > 1) return true;                       // cluster teams (1024 < nr <= 4096)
+    return c.clF == 1 && c.ncolA == 1 && c.tplA == c.tpl && c.eptA == c.ept && c.vecA == c.vec && c.ctaA == c.cta_threads;
 }
 HpKernelLaunch desc_factor_levels(int total_coarse_rows) {
     return {(const void*)k_factor_levels, dim3((total_coarse_rows + 31) / 32), dim3(32), 0};

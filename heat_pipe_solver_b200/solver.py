@@ -101,7 +101,7 @@ class ConductionSolver:
                  properties='temperature_dependent', gamma='snapshot', source='q_over_k',
                  face_k='masked_at_Tface', radiation=False, axial_break=None, rows=None,
                  precond='auto', criterion='precond_inf', tol=1e-9, max_iter=5000, loop_mode='graph',
-                 poll_chunk=8, refactor_every=1, extrapolate=True, mg_levels=6, mg_coarse_sweeps=2, mg_omega=0.55,
+                 poll_chunk=8, refactor_every=1, extrapolate=True, mg_levels=6, mg_coarse_sweeps=2, mg_omega=0.6,
                  mg_zscale=0.5, reuse_converged=False, while_unroll=1, peer_timeout_ms=60000,
                  device=None, simple=(7200.0, 440.5, 55.0),
                  layout=None, regions=None):
@@ -166,7 +166,7 @@ class ConductionSolver:
     def set_options(self, **kw):
         cur = getattr(self, 'options', dict(precond='rline', criterion='precond_inf', tol=1e-9, max_iter=5000,
                                             loop_mode='graph', poll_chunk=8, refactor_every=1, extrapolate=True,
-                                            mg_levels=6, mg_coarse_sweeps=2, mg_omega=0.55, mg_zscale=0.5,
+                                            mg_levels=6, mg_coarse_sweeps=2, mg_omega=0.6, mg_zscale=0.5,
                                             reuse_converged=False, while_unroll=1, peer_timeout_ms=60000))
         cur = dict(cur)
         for k, v in kw.items():

@@ -82,7 +82,7 @@ typedef struct hp_solve_opts {
     int32_t reuse_converged;  /* 1: a sweep that exactly repeats a sweep which converged before its first iteration (T, T_old, dt
                                  untouched since) only redoes the bookkeeping -- same residual / statistics, no assembly.
                                  Single GPU only.  0 (default): every sweep assembles, like the reference */
-    double mg_omega;        /* mgline: damping of the line smoother (default 0.55) */
+    double mg_omega;        /* mgline: damping of the line smoother (default 0.6) */
     int32_t while_unroll;   /* loop_mode 1: PCG iterations per pass of the device-side WHILE node (1..8, default 1) */
     int32_t peer_timeout_ms;/* peer-memory slabs: how long a kernel waits for a neighbour's flag before it gives up and raises
                                the handle's fault (default 60000).  A fault is sticky: every later call on the handle returns an

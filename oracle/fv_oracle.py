@@ -577,7 +577,7 @@ def _prolong(e, nz):
     return np.repeat(e, 2, axis=0)[:nz]
 
 
-def mg_vcycle(levels, r, zline, omega=0.55, coarse_sweeps=2):
+def mg_vcycle(levels, r, zline, omega=0.6, coarse_sweeps=2):
     """z = V(r); `zline` = M_line^-1 r of the fine level (what k_cg_B leaves in z)."""
     c = len(levels) - 1
     xs, rs = [omega * zline], [r]
@@ -658,7 +658,7 @@ def pcg(S: System, x0=None, precond='rline', tol=1e-9, criterion='precond_inf', 
     return x
 
 
-def _pcg_mgline(S, x, r, tol, criterion, max_iter, info, max_levels=6, omega=0.55, coarse_sweeps=2, zscale=0.5):
+def _pcg_mgline(S, x, r, tol, criterion, max_iter, info, max_levels=6, omega=0.6, coarse_sweeps=2, zscale=0.5):
     """PCG with the V-cycle as preconditioner; the stopping measure stays max|M_line^-1 r| (same rule as 'rline')."""
     if criterion != 'precond_inf':
         raise ValueError("mgline twin implements the precond_inf criterion")
