@@ -296,9 +296,9 @@ def run_gpu(args, rank, world, local_rank):
         loop_mode = 'host' if (world > 1 and args.comm == 'nccl' and not ensemble) else args.loop_mode
         if not ensemble:
             solver = make_solver_for_rank(mesh, cfg, rank, world, comm=args.comm, tol=args.tol, loop_mode=loop_mode,
-                                          extrapolate=int(os.environ.get('HP_EXTRAP', '3')), precond=args.precond,
+                                          extrapolate=args.extrapolate, precond=args.precond,
                                           mg_levels=args.mg_levels, mg_coarse_sweeps=args.mg_sweeps, mg_omega=args.mg_omega,
-                                          refactor_every=args.refactor_every, reuse_converged=args.reuse_converged)
+                                          refactor_every=args.refactor_every, reuse_converged=args.reuse_converged, while_unroll=args.while_unroll)
 
         def barrier():
             stream.synchronize()
@@ -358,7 +358,9 @@ def run_gpu(args, rank, world, local_rank):
 
         # ---- per-kernel CUDA-event times (stream-launch mode, same workload continuing) ----------------------
         roof = None
-        if world == 1:
+        if world == 1 or (args.profile_slabs and not ensemble and args.comm == 'p2p'):
+            # (slabs: every rank runs the same stream-mode pass -- the flag protocol needs all of them; rank 0's table is
+            #  printed, its per-kernel times include the waits for the neighbours)
             solver.profile_begin(16384)
             solver.run(DT, max(1, min(3, args.steps)), sweeps=SWEEPS, has_old=HAS_OLD)
             kt = solver.profile_end()
@@ -368,7 +370,8 @@ def run_gpu(args, rank, world, local_rank):
             # per-launch duration over the launches that did the kernel's work ("full": >= half the longest launch of the
             # kind) -- launches that return at once in an already converged sweep do not move the algorithmic bytes
             cnt, tms, fcnt, fms = kt[dom]
-            bytes_per_launch = BYTES_PER_CELL.get(dom, 0) * n_cells
+            n_loc = solver.n_cells                 # cells this rank's kernels stream (the whole mesh on one GPU)
+            bytes_per_launch = BYTES_PER_CELL.get(dom, 0) * n_loc
             achieved = bytes_per_launch / (fms / fcnt * 1e-3) / 1e9 if fcnt else 0.0
             traffic = None
             tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
@@ -385,7 +388,7 @@ def run_gpu(args, rank, world, local_rank):
                     'launches_timed': fcnt, 'launches_returning_at_once': cnt - fcnt,
                     'share_of_step': tms / tot_ms if tot_ms else None,
                     'all_kernels': {k: {'launches': c, 'total_ms': m, 'full_launches': fc, 'avg_ms': (fm / fc if fc else None),
-                                        'GBps': (BYTES_PER_CELL.get(k, 0) * n_cells / (fm / fc * 1e-3) / 1e9 if fc else None)}
+                                        'GBps': (BYTES_PER_CELL.get(k, 0) * n_loc / (fm / fc * 1e-3) / 1e9 if fc else None)}
                                     for k, (c, m, fc, fm) in kt.items() if c}}
         slab_field = None
         if world > 1 and not ensemble and not args.no_single_gpu_ref:
@@ -399,9 +402,9 @@ def run_gpu(args, rank, world, local_rank):
         # the SAME time steps (the cost of a step falls along the transient, so the step indices must match)
         def single_gpu_run(big_mesh):
             one = make_solver_for_rank(big_mesh, cfg, 0, 1, tol=args.tol, loop_mode=args.loop_mode, precond=args.precond,
-                                       extrapolate=int(os.environ.get('HP_EXTRAP', '3')), refactor_every=args.refactor_every,
+                                       extrapolate=args.extrapolate, refactor_every=args.refactor_every,
                                        mg_levels=args.mg_levels, mg_coarse_sweeps=args.mg_sweeps, mg_omega=args.mg_omega,
-                                       reuse_converged=args.reuse_converged)
+                                       reuse_converged=args.reuse_converged, while_unroll=args.while_unroll)
             try:
                 one.run(DT, args.warmup, sweeps=SWEEPS, has_old=HAS_OLD)
                 stream.synchronize()
@@ -472,7 +475,7 @@ def run_gpu(args, rank, world, local_rank):
             'run': {'parallelism': 'single GPU' if world == 1 else (f'members sharded over {world} ranks, no collective' if ensemble else f'axial slabs x{world}, ' + ('NVLink peer-memory halo rows + CG scalars fused into the kernels, one CUDA graph per step' if args.comm == 'p2p' else 'NCCL send/recv halo + all-gathered CG scalars, host-driven loop')),
                     'solver': f'PCG ({args.precond}) tol {args.tol:g} K', 'pcg_iterations_per_step': iters / args.steps, 'loop_mode': loop_mode,
                     'refactor_every_sweeps': args.refactor_every, 'reuse_converged_sweeps': bool(args.reuse_converged),
-                    'pcg_start': f"extrapolated from the step history, max order {os.environ.get('HP_EXTRAP', '3')}",
+                    'pcg_start': f"extrapolated from the step history, max order {args.extrapolate}",
                     'e2e_note': 'hp_run_host uploads the field every step but keeps the solver-side step history (T_old, increments) for the '
                                 'predicted PCG start; a caller uploading an unrelated field pays first-step iteration counts'},
             'e2e': {'value': e2e_value, 'unit': 'cell-timesteps/s', 'h2d_bytes_per_step': 8 * n_cells,
@@ -499,6 +502,9 @@ def main():
     ap.add_argument('--loop-mode', default='graph', choices=['graph', 'host'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-splu', action='store_true', help='--impl reference: skip the SuperLU variant (cpu_baseline_splu)')
+    ap.add_argument('--profile-slabs', action='store_true', help='N>1: per-kernel CUDA-event table of rank 0 (stream-launch pass on every rank)')
+    ap.add_argument('--while-unroll', type=int, default=1)
+    ap.add_argument('--extrapolate', type=int, default=3, help='maximum order of the extrapolated PCG start (0 = off)')
     ap.add_argument('--scaling-ref', action='store_true',
                     help='N=1: also time the 16384x4096 multi-GPU workload on this one GPU (extra key multi_gpu_workload_on_one_gpu)')
     ap.add_argument('--no-single-gpu-ref', action='store_true', help='N>1: skip the one-GPU run of the same workload (strong-scaling denominator)')

@@ -595,8 +595,9 @@ static int emit_mg_setup(Emitter& e, bool always) {
         rows += h->lev[l].nz;
     }
     if (rows == 0) return 0;
-    void* pf[] = {&ls, &nr, &skip};
-    return emit(e, hpk::desc_factor_levels(rows), pf, KIND_MG_SETUP);
+    int first = 1;
+    void* pf[] = {&ls, &first, &nr, &skip};
+    return emit(e, hpk::desc_factor_rows(h->cfg, rows), pf, KIND_MG_SETUP);
 }
 
 // mgline V(1,1) cycle on r (level-0 rhs) starting from zline = M^-1 r in d.z (left there by k_cg_B); leaves the
@@ -742,7 +743,13 @@ static int emit_sweep_head(Emitter& e, HpKArgs& a, bool refactor, bool shift) {
     if (emit(e, hpk::desc_diag(h->cfg, d), p40, KIND_DIAG)) return -1;
     if (emit_combine(e, a0, 0)) return -1;
     if (h->opts.precond >= 1 && refactor) {
-        if (emit(e, hpk::desc_factor(h->cfg, d), params, KIND_FACTOR)) return -1;
+        HpLevelSet fine;
+        fine.n = 1;
+        fine.lev[0] = HpLevel{d.nz, d.cR, d.cZ, d.diag, d.dinv, nullptr, nullptr, nullptr, nullptr};
+        int first = 0, nr_ = d.nr;
+        const int* never = &d.st->_pad0;
+        void* pf[] = {&fine, &first, &nr_, &never};
+        if (emit(e, hpk::desc_factor_rows(h->cfg, d.nz), pf, KIND_FACTOR)) return -1;
     }
     if (shift) {
         // z holds T - T_prev (k_delta): one (A, B) pair with alpha := 1 moves the start of the solve to the extrapolated

@@ -149,7 +149,6 @@ struct HpLaunchCfg {
     int clF;                 // fused V-cycle stages: CTAs per row (thread-block cluster), 1 = one CTA team, 0 = unsupported
     int num_sms, nz;
     int grid_cell, cta_cell;                     // grid for thread-per-cell kernels
-    int grid_factor, cta_factor;
 };
 
 // launch descriptors (so that hp_api.cu can either launch on a stream or add CUDA-graph kernel nodes)
@@ -170,7 +169,7 @@ HpKernelLaunch desc_stash(const HpLaunchCfg&, const HpDev&);   // second sweep o
 HpKernelLaunch desc_delta(const HpLaunchCfg&, const HpDev&);   // z = extrapolated increment, Told <- T, on every row (ghosts included)
 HpKernelLaunch desc_diag(const HpLaunchCfg&, const HpDev&);     // args: (HpDev, hp_phys, HpKArgs, int write_dinv, int tpr_log2)
 int diag_tpr_log2(int nr);
-HpKernelLaunch desc_factor(const HpLaunchCfg&, const HpDev&);
+HpKernelLaunch desc_factor_rows(const HpLaunchCfg&, long long rows);   // args: (HpLevelSet, int first, int nr, const int* skip)
 HpKernelLaunch desc_cg_init(const HpLaunchCfg&, const HpDev&, int precond, int criterion);
 HpKernelLaunch desc_cg_A(const HpLaunchCfg&, const HpDev&);
 // 'mgline' V-cycle pieces (argument lists next to the kernels in hp_kernels.cu)
@@ -180,7 +179,6 @@ HpKernelLaunch desc_mg_line(const HpLaunchCfg&, int nz_level);
 HpKernelLaunch desc_mg_down(const HpLaunchCfg&, int nz_level);   // same args: residual + restriction + pre-smoothing of level+1
 HpKernelLaunch desc_mg_up(const HpLaunchCfg&, int nz_level);     // args: (HpDev, HpKArgs, HpLevel, HpMgResArgs): fused prolong+residual+smooth
 bool mg_fused_supported(const HpLaunchCfg&);
-HpKernelLaunch desc_factor_levels(int total_coarse_rows);   // args: (HpLevelSet, int nr, const int* skip)
 HpKernelLaunch desc_wait();       // args: (HpDev, hp_phys, HpKArgs, int kind): peer-memory variant of finalize
 HpKernelLaunch desc_finalize();   // args: (HpDev, hp_phys, HpKArgs, int kind) kind: 0 diag, 1 A, 2 B, 3 init
 HpKernelLaunch desc_cg_B(const HpLaunchCfg&, const HpDev&, int precond, int criterion);

@@ -243,10 +243,13 @@ __device__ __forceinline__ void stash_local(const HpDev& d, const double (&tot)[
 #pragma unroll
         for (int k = 0; k < NV; ++k) c->red[kind][d.rank][k] = tot[k];
     }
+    // ONE system fence orders the sums (and, through the tickets, every CTA's boundary rows) before all the flags; the flag
+    // stores themselves are relaxed and pipeline over NVLink (a release per flag serialises a round trip per rank: 8 ranks
+    // cost ~25 us per reducing kernel)
     __threadfence_system();
     for (int r = 0; r < d.nranks; ++r) {
         unsigned long long* f = &d.comm_peer[r]->flag[kind][d.rank];
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(sq) : "memory");
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(f), "l"(sq) : "memory");
     }
 }
 
@@ -486,61 +489,6 @@ __global__ void __launch_bounds__(256, 2) k_diag(HpDev d, hp_phys ph, HpKArgs a,
         if (d.nranks > 1) stash_local<2>(d, tot, HP_COMM_DIAG);
         else finalize_diag(d, a, tot[0], tot[1]);
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_factor_rline : pivots of the radial-line tridiagonal  M_j = tridiag(-cR[i-1], diag[i], -cR[i])
-//   w_0 = diag_0 ; w_i = diag_i - cR_{i-1}^2 / w_{i-1} ; dinv_i = 1/w_i          thread per row
-// A nonlinear first-order recurrence, so rows are the parallel axis; loads of the next block are issued
-// before the dependent chain of the current one.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void factor_row(const double* __restrict__ dg, const double* __restrict__ cr,
-                                           double* __restrict__ out, int nr) {
-    double prev = 0.0;    // cR_{i-1}^2 * dinv_{i-1}
-    constexpr int B = 8;
-    double db[B], cb[B];
-    int i = 0;
-    const int nfull = nr / B * B;
-    if (nfull > 0) {
-#pragma unroll
-        for (int k = 0; k < B; ++k) { db[k] = dg[k]; cb[k] = cr[k]; }
-    }
-    for (; i < nfull; i += B) {
-        double dn[B], cn[B];
-        const bool more = (i + B) < nfull;
-        if (more) {
-#pragma unroll
-            for (int k = 0; k < B; ++k) { dn[k] = dg[i + B + k]; cn[k] = cr[i + B + k]; }
-        }
-        double res[B];
-#pragma unroll
-        for (int k = 0; k < B; ++k) {
-            const double w = db[k] - prev;
-            const double inv = 1.0 / w;
-            res[k] = inv;
-            prev = cb[k] * cb[k] * inv;
-        }
-#pragma unroll
-        for (int k = 0; k < B; ++k) out[i + k] = res[k];
-        if (more) {
-#pragma unroll
-            for (int k = 0; k < B; ++k) { db[k] = dn[k]; cb[k] = cn[k]; }
-        }
-    }
-    for (; i < nr; ++i) {
-        const double w = dg[i] - prev;
-        const double inv = 1.0 / w;
-        out[i] = inv;
-        const double c = cr[i];
-        prev = c * c * inv;
-    }
-}
-
-__global__ void __launch_bounds__(32) k_factor_rline(HpDev d, hp_phys ph, HpKArgs a) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= d.nz) return;
-    const long long base = (long long)(j + 1) * d.nr;
-    factor_row(d.diag + base, d.cR + base, d.dinv + base, d.nr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1086,8 +1034,23 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpKArgs& a, co
     const long long npairs = (nz + 1) / 2;
     int ja = 0, jb = 0;
     if (chunk < nchunks) {
-        ja = (int)(2 * (chunk * npairs / nchunks));
-        jb = (int)(2 * ((chunk + 1) * npairs / nchunks));
+        // Under peer-memory slabs the first / last row pair gets a chunk of its own when the level is tall enough: that
+        // team consumes the neighbour's boundary row and produces this slab's one within two rows of work, so the
+        // hand-over chain between the slabs runs ahead of the interior teams instead of adding its NVLink latency to
+        // every stage (an edge team that marches a full chunk produces its far boundary row at the END of the kernel and
+        // the neighbour's next stage needs it at its START).
+        const long long e0 = (d.p2p && d.rank > 0 && (m.xc.wait >= 0 || m.xc.push_lo) && nchunks >= 4 && npairs >= 4 * nchunks) ? 1 : 0;
+        const long long e1 = (d.p2p && d.rank < d.nranks - 1 && (m.xc.wait >= 0 || m.xc.push_hi) && nchunks >= 4 && npairs >= 4 * nchunks) ? 1 : 0;
+        long long pa, pb;
+        if (e0 && chunk == 0) { pa = 0; pb = 1; }
+        else if (e1 && chunk == nchunks - 1) { pa = npairs - 1; pb = npairs; }
+        else {
+            const long long ci = chunk - e0, Ci = nchunks - e0 - e1, Pi = npairs - e0 - e1;
+            pa = e0 + ci * Pi / Ci;
+            pb = e0 + (ci + 1) * Pi / Ci;
+        }
+        ja = (int)(2 * pa);
+        jb = (int)(2 * pb);
         if (jb > nz) jb = nz;
     }
     const bool has_l = (lane == 0) && (i0 != 0) && (i0 < nr);
@@ -1340,20 +1303,125 @@ const void* fn_mg_res() { return (const void*)k_mg_res<TPL, EPT, VEC>; }
 template <int TPL, int EPT, bool VEC>
 const void* fn_mg_line() { return (const void*)k_mg_line<TPL, EPT, VEC>; }
 
-// pivots of ALL coarse levels in one launch (thread per row of any level: the recurrence is a serial chain of nr
-// steps whatever the row count, so one launch costs the same latency as one level alone)
-__global__ void __launch_bounds__(32) k_factor_levels(HpLevelSet ls, int nr, const int* skip) {
+// ------------------------------------------------------------------------------------------------
+// k_factor_team : pivots of the radial-line tridiagonal blocks  M_j = tridiag(-cR[i-1], diag[i], -cR[i])
+//   w_0 = diag_0 ;  w_i = diag_i - cR_{i-1}^2 / w_{i-1} ;  dinv_i = 1 / w_i
+// of the rows of levels first..n-1 of a level set (the fine level alone, or all coarse levels in one launch).
+// The recurrence is a Moebius map, i.e. linear on the pair (p, q) with w = p / q:
+//   (p_i, q_i)^T = [[diag_i, -cR_{i-1}^2], [1, 0]] (p_{i-1}, q_{i-1})^T ,  (p_-1, q_-1) = (1, 0)
+// so the prefix products of those 2x2 matrices are an associative scan: a row team (the shape of the line solve: EPT
+// cells per thread) composes its cells, the warp scans the products with shuffles, the warps of the team exchange their
+// totals through shared memory, and every thread restarts the true recurrence from w at the cell before its first one.
+// The partial products are continuants and grow geometrically: every combination is rescaled by a power of two (exact).
+// The scanned start value carries a relative error of ~1e-10 (nr = 1024) .. 3e-9 (nr = 4096) against the sequential
+// recurrence (tools/proto_pivot_scan.py); the pivots only define the preconditioner M = L D L^T (symmetric positive
+// definite for any positive w), never the answer.  Replaces a thread-per-row chain of nr dependent divisions
+// (0.13 ms at 4096 x 1024, 0.52 ms at nr = 4096 whatever the row count).
+// ------------------------------------------------------------------------------------------------
+struct M2 { double a, b, c, d; };       // [[a, b], [c, d]]
+__device__ __forceinline__ void m2_rescale(M2& m) {
+    const double s = fmax(fmax(fabs(m.a), fabs(m.b)), fmax(fabs(m.c), fabs(m.d)));
+    const int ex = (__double2hiint(s) >> 20) & 0x7ff;                       // biased exponent of the largest entry
+    const double sc = __hiloint2double((2046 - ex) << 20, 0);               // 2^-(exponent): exact scaling
+    m.a *= sc; m.b *= sc; m.c *= sc; m.d *= sc;
+}
+// the map `later` applied after the map `earlier`
+__device__ __forceinline__ M2 m2_after(const M2& later, const M2& earlier) {
+    M2 r;
+    r.a = fma(later.a, earlier.a, later.b * earlier.c);
+    r.b = fma(later.a, earlier.b, later.b * earlier.d);
+    r.c = fma(later.c, earlier.a, later.d * earlier.c);
+    r.d = fma(later.c, earlier.b, later.d * earlier.d);
+    return r;
+}
+
+template <int TPL, int EPT, bool VEC>
+__global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT)) k_factor_team(HpLevelSet ls, int first, int nr,
+                                                                                            const int* skip) {
+    using G = TeamGeom<TPL>;
     if (*skip) return;
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int l = 1; l < ls.n; ++l) {
-        if (j < ls.lev[l].nz) {
-            const long long base = (long long)(j + 1) * nr;
-            factor_row(ls.lev[l].diag + base, ls.lev[l].cR + base, ls.lev[l].dinv + base, nr);
-            return;
+    constexpr int NW = G::NW, W = G::W;
+    __shared__ double s_tot[G::LPC][NW][4];
+    const int team_in_cta = threadIdx.x / TPL, tl = threadIdx.x % TPL, lane = threadIdx.x & (W - 1);
+    const int wt = tl >> 5;
+    const int i0 = tl * EPT;
+    const unsigned tm = team_mask<TPL>();
+    long long total = 0;
+    for (int l = first; l < ls.n; ++l) total += ls.lev[l].nz;
+    const long long team = (long long)blockIdx.x * G::LPC + team_in_cta, nteams = (long long)gridDim.x * G::LPC;
+    const long long Ra = team * total / nteams, Rb = (team + 1) * total / nteams;
+    int l = first;
+    long long base = 0;                          // rows of the levels before level l
+    for (long long R = Ra; R < Rb; ++R) {
+        while (R - base >= ls.lev[l].nz) { base += ls.lev[l].nz; ++l; }
+        const long long rb = (R - base + 1) * nr;
+        const double* __restrict__ dgr = ls.lev[l].diag + rb;
+        const double* __restrict__ crr = ls.lev[l].cR + rb;
+        double dv[EPT], cv[EPT];
+        load_row<EPT, VEC>(dgr, i0, nr, dv);
+        load_row<EPT, VEC>(crr, i0, nr, cv);
+        double c_edge = 0.0;                     // coupling to the cell before this warp's first one
+        if (lane == 0 && tl != 0 && i0 < nr) c_edge = crr[i0 - 1];
+        double cprev = __shfl_up_sync(tm, cv[EPT - 1], 1, W);
+        if (lane == 0) cprev = c_edge;
+        // this thread's cells composed: T = M_{i0+EPT-1} ... M_{i0}
+        M2 T{dv[0], -cprev * cprev, 1.0, 0.0};
+#pragma unroll
+        for (int e = 1; e < EPT; ++e) {
+            const double c2 = cv[e - 1] * cv[e - 1];
+            M2 n{fma(dv[e], T.a, -c2 * T.c), fma(dv[e], T.b, -c2 * T.d), T.a, T.b};
+            T = n;
         }
-        j -= ls.lev[l].nz;
+        m2_rescale(T);
+        // inclusive scan over the lanes of the warp (sub-warp teams: over the team's lanes)
+        M2 S = T;
+#pragma unroll
+        for (int o = 1; o < W; o <<= 1) {
+            M2 P;
+            P.a = __shfl_up_sync(tm, S.a, o, W); P.b = __shfl_up_sync(tm, S.b, o, W);
+            P.c = __shfl_up_sync(tm, S.c, o, W); P.d = __shfl_up_sync(tm, S.d, o, W);
+            if (lane >= o) { S = m2_after(S, P); m2_rescale(S); }
+        }
+        // exclusive prefix inside the warp
+        M2 E;
+        E.a = __shfl_up_sync(tm, S.a, 1, W); E.b = __shfl_up_sync(tm, S.b, 1, W);
+        E.c = __shfl_up_sync(tm, S.c, 1, W); E.d = __shfl_up_sync(tm, S.d, 1, W);
+        if (lane == 0) { E.a = 1.0; E.b = 0.0; E.c = 0.0; E.d = 1.0; }
+        // (p, q) at the cell before this thread's first one = (E * carry) (1, 0)^T, carry = product of the warps before
+        double p = E.a, q = E.c;
+        if constexpr (NW > 1) {
+            if (lane == W - 1) {
+                double* t = s_tot[team_in_cta][wt];
+                t[0] = S.a; t[1] = S.b; t[2] = S.c; t[3] = S.d;
+            }
+            team_barrier<TPL>(team_in_cta);
+            double ca = 1.0, cc = 0.0;           // first column of the carry (the second one is never needed)
+            for (int w = 0; w < wt; ++w) {
+                const double* t = s_tot[team_in_cta][w];
+                const double na = fma(t[0], ca, t[1] * cc), nc = fma(t[2], ca, t[3] * cc);
+                const double s = fmax(fabs(na), fabs(nc));
+                const int ex = (__double2hiint(s) >> 20) & 0x7ff;
+                const double sc = __hiloint2double((2046 - ex) << 20, 0);
+                ca = na * sc; cc = nc * sc;
+            }
+            p = fma(E.a, ca, E.b * cc);
+            q = fma(E.c, ca, E.d * cc);
+            team_barrier<TPL>(team_in_cta);      // s_tot is rewritten by the next row
+        }
+        // true recurrence from w_{i0-1} = p / q
+        double prev = (tl == 0) ? 0.0 : cprev * cprev * (q / p);
+        double out[EPT];
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const double inv = 1.0 / (dv[e] - prev);
+            out[e] = inv;
+            prev = cv[e] * cv[e] * inv;
+        }
+        store_row<EPT, VEC>(ls.lev[l].dinv + rb, i0, nr, out);
     }
 }
+template <int TPL, int EPT, bool VEC>
+const void* fn_factor_team() { return (const void*)k_factor_team<TPL, EPT, VEC>; }
 
 // ---- instantiation table -----------------------------------------------------------------------
 template <int TPL, int EPT, bool VEC>
@@ -1426,8 +1494,6 @@ bool pick_config(int nr, int nz, int num_sms, HpLaunchCfg* cfg, const char** err
     long long cap = (long long)num_sms * 8;
     cfg->grid_cell = (int)(gc < cap ? gc : cap);
     if (cfg->grid_cell > HP_MAX_PARTIALS) cfg->grid_cell = HP_MAX_PARTIALS;
-    cfg->cta_factor = 32;
-    cfg->grid_factor = (nz + 31) / 32;
     return true;
 }
 
@@ -1474,8 +1540,15 @@ HpKernelLaunch desc_diag(const HpLaunchCfg& c, const HpDev& d) {
     if (g > HP_MAX_PARTIALS) g = HP_MAX_PARTIALS;
     return {(const void*)k_diag, dim3((unsigned)(g < 1 ? 1 : g)), dim3(256), 0};
 }
-HpKernelLaunch desc_factor(const HpLaunchCfg& c, const HpDev& d) {
-    return {(const void*)k_factor_rline, dim3(c.grid_factor), dim3(c.cta_factor), 0};
+// pivots of `rows` rows in total (the fine level, or every coarse level in one launch): args (HpLevelSet, int first, int nr, const int* skip)
+HpKernelLaunch desc_factor_rows(const HpLaunchCfg& c, long long rows) {
+    const void* f = nullptr;
+#define HP_X(T, E, V) f = fn_factor_team<T, E, V>()
+    HP_DISPATCH(c, HP_X);
+#undef HP_X
+    HpLaunchCfg cl = c;
+    cl.nz = (int)(rows < 1 ? 1 : rows);
+    return {f, dim3(team_grid(f, cl, c.cta_threads, c.teams_per_cta, 1)), dim3(c.cta_threads), 0};
 }
 HpKernelLaunch desc_mg_coarsen(const HpLaunchCfg& c, int nzc, int nr) {
     long long g = ((long long)(nzc + 1) * nr + 255) / 256;
@@ -1542,9 +1615,6 @@ HpKernelLaunch desc_mg_line(const HpLaunchCfg& c, int nz_level) {
 bool mg_fused_supported(const HpLaunchCfg& c) {
     if (c.clF > 1) return true;                       // cluster teams (1024 < nr <= 4096)
     return c.clF == 1 && c.ncolA == 1 && c.tplA == c.tpl && c.eptA == c.ept && c.vecA == c.vec && c.ctaA == c.cta_threads;
-}
-HpKernelLaunch desc_factor_levels(int total_coarse_rows) {
-    return {(const void*)k_factor_levels, dim3((total_coarse_rows + 31) / 32), dim3(32), 0};
 }
 HpKernelLaunch desc_finalize() { return {(const void*)k_finalize, dim3(1), dim3(32), 0}; }
 HpKernelLaunch desc_wait() { return {(const void*)k_wait, dim3(1), dim3(32), 0}; }
