@@ -356,6 +356,13 @@ def run_gpu(args, rank, world, local_rank):
             e2e_ms = float(t.item())
         e2e_value = n_cells * args.steps / (e2e_ms * 1e-3)
 
+        slab_field = None
+        if world > 1 and not ensemble and not args.no_single_gpu_ref:
+            # field after the end-to-end region = W + K steps from the ambient field, the state the one-GPU run ends in
+            from heat_pipe_solver_b200.distributed import gather_field
+            full = gather_field(solver.value_tensor())
+            slab_field = full if rank == 0 else None
+            del full
         # ---- per-kernel CUDA-event times (stream-launch mode, same workload continuing) ----------------------
         roof = None
         if world == 1 or (args.profile_slabs and not ensemble and args.comm == 'p2p'):
@@ -390,13 +397,6 @@ def run_gpu(args, rank, world, local_rank):
                     'all_kernels': {k: {'launches': c, 'total_ms': m, 'full_launches': fc, 'avg_ms': (fm / fc if fc else None),
                                         'GBps': (BYTES_PER_CELL.get(k, 0) * n_loc / (fm / fc * 1e-3) / 1e9 if fc else None)}
                                     for k, (c, m, fc, fm) in kt.items() if c}}
-        slab_field = None
-        if world > 1 and not ensemble and not args.no_single_gpu_ref:
-            # field after the end-to-end region = W + K steps from the ambient field, the state the one-GPU run ends in
-            from heat_pipe_solver_b200.distributed import gather_field
-            full = gather_field(solver.value_tensor())
-            slab_field = full if rank == 0 else None
-            del full
         solver.close()
         # strong-scaling reference: the same 16384x4096 workload on ONE GPU (rank 0, after the slab handles are gone), over
         # the SAME time steps (the cost of a step falls along the transient, so the step indices must match)

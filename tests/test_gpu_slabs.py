@@ -20,6 +20,22 @@ def _free_port():
     return p
 
 
+def _run_workers(world, shape, n_steps, sweeps, out, comm, loop_mode, precond):
+    """One process per GPU.  The rendezvous port is probed free and can still be taken by the time rank 0 binds it
+    (EADDRINUSE): retry with another port before calling it a failure."""
+    for attempt in range(3):
+        port = _free_port()
+        procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, 'tests', 'slab_worker.py'), str(r), str(world), str(port),
+                                   ','.join(map(str, shape)), str(n_steps), str(sweeps), out, comm, loop_mode, precond],
+                                  stderr=subprocess.PIPE, text=True) for r in range(world)]
+        outs = [p.communicate(timeout=600)[1] for p in procs]
+        if all(p.returncode == 0 for p in procs):
+            return
+        if not any('EADDRINUSE' in (o or '') for o in outs):
+            break
+    raise AssertionError('slab workers failed:\n' + '\n'.join((o or '')[-1500:] for o in outs))
+
+
 @pytest.mark.parametrize('comm,loop_mode,precond', [('nccl', 'host', 'rline'), ('p2p', 'host', 'rline'), ('p2p', 'graph', 'rline'),
                                                     ('p2p', 'graph', 'mgline'), ('nccl', 'host', 'mgline')])
 @pytest.mark.parametrize('world,shape', [(2, (64, 4, 8, 20)), (2, (50, 32, 64, 160)), (4, (96, 12, 24, 64))])
@@ -29,12 +45,8 @@ def test_slabs_match_single_domain_oracle(cfg, tmp_path, world, shape, comm, loo
         pytest.skip(f"needs {world} GPUs")
     from oracle import fv_oracle as fo
     out = str(tmp_path / 'slab.npy')
-    port = _free_port()
     n_steps, sweeps = 2, 3
-    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, 'tests', 'slab_worker.py'), str(r), str(world), str(port),
-                               ','.join(map(str, shape)), str(n_steps), str(sweeps), out, comm, loop_mode, precond]) for r in range(world)]
-    for p in procs:
-        assert p.wait(timeout=300) == 0
+    _run_workers(world, shape, n_steps, sweeps, out, comm, loop_mode, precond)
     T = np.load(out)
     grid = fo.build_grid(fo.synthetic_mesh_params(*shape), cfg['dimensions'])
     z = grid.z_c[:, None] / grid.z_v[-1]
@@ -45,14 +57,6 @@ def test_slabs_match_single_domain_oracle(cfg, tmp_path, world, shape, comm, loo
         for _ in range(sweeps):
             o.sweep(0.1, solver='banded' if grid.nr <= 160 else 'splu')
     assert np.max(np.abs(T - o.T)) <= 1e-6 * n_steps * sweeps
-
-
-def _run_workers(world, shape, n_steps, sweeps, out, comm, loop_mode, precond):
-    port = _free_port()
-    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, 'tests', 'slab_worker.py'), str(r), str(world), str(port),
-                               ','.join(map(str, shape)), str(n_steps), str(sweeps), out, comm, loop_mode, precond]) for r in range(world)]
-    for p in procs:
-        assert p.wait(timeout=600) == 0
 
 
 @pytest.mark.parametrize('world,shape', [(2, (256, 8, 16, 40)),          # 5 levels, fused stages (nr = 64)
