@@ -415,7 +415,40 @@ __global__ void __launch_bounds__(256) k_coef(HpDev d, hp_phys ph, HpKArgs a) {
 //   rhs  = cap*T_old (+ Robin*g + evaporator)                                     main.py:146-150
 //   r    = rhs - L T          (PCG start residual; FiPy's `res` = ||L T - rhs||_2) main.py:202
 // ------------------------------------------------------------------------------------------------
+// one cell of the assembly: diagonal, right-hand side and start residual from the loaded neighbourhood
+struct DiagCell { double dg, rhs, r0; };
+__device__ __forceinline__ DiagCell diag_cell(const HpDev& d, const hp_phys& ph, const HpKArgs& a, int g, int i, unsigned zf, double dzg,
+                                              double Tc, double To, double cE, double cW, double cN, double cS, double Tnb) {
+    double rho, cp;
+    hp::rho_cp_region(ph, d.cell_band[i], zf, Tc, rho, cp);
+    const double vol = d.wc[i] * d.dr[i] * dzg;
+    const double cap = cp * rho * vol / a.dt;
+    double dg = cap;
+    dg += cE; dg += cW; dg += cN; dg += cS;
+    double rhs = cap * To;
+    if (i == d.nr - 1) {
+        const double kout = k_outface(d, ph, g, Tc);
+        const double k0 = (ph.gamma == 0) ? d.k0_out[g] : kout;
+        const double A_out = d.A_out_r * dzg;
+        const double h = d.h_line[g], Ta = d.Tamb_line[g];
+        if (zf & HP_ZF_BC_COND) {
+            const double robin = kout * A_out / (h * d.d_out + k0);
+            dg += robin * h;
+            double gs = h * Ta;
+            if (ph.radiation) gs += ph.sigma * d.eps_line[g] * (Ta * Ta * Ta * Ta - Tc * Tc * Tc * Tc);
+            rhs += robin * gs;
+        }
+        if (zf & HP_ZF_BC_EVAP) {
+            const double q = d.q_line[g];
+            rhs += ((ph.source == 0) ? (q / kout) : q) * A_out;
+        }
+    }
+    const double LT = dg * Tc - Tnb;
+    return DiagCell{dg, rhs, rhs - LT};
+}
+
 constexpr int DIAG_U = 4;      // cells per thread whose loads are issued before any of their (long, fp64) property chains
+template <bool ROWS_OVER_LANES>
 __global__ void __launch_bounds__(256, 2) k_diag(HpDev d, hp_phys ph, HpKArgs a, int write_dinv_jacobi, int tpr_log2) {
     // rows over CTAs (and over row groups inside a CTA when a row is shorter than the CTA), columns over threads:
     // no integer division per cell, per-row quantities read once
@@ -427,6 +460,35 @@ __global__ void __launch_bounds__(256, 2) k_diag(HpDev d, hp_phys ph, HpKArgs a,
     const int tpr = 1 << tpr_log2, rpb = blockDim.x >> tpr_log2;
     const int col0 = threadIdx.x & (tpr - 1), rsub = threadIdx.x >> tpr_log2;
     double acc[2] = {0.0, 0.0};
+    if constexpr (ROWS_OVER_LANES) {
+        // Very short rows (the native 9-cell rows of the ensembles): with columns over lanes a warp holds cells of all three
+        // bands and executes the vapor-core, wick AND wall laws one after the other.  Here lanes run over ROWS and a warp
+        // handles one column at a time (one band, one law); the strided loads of a tile of 32 rows hit the same L1 lines
+        // column after column.
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+        for (long long j0 = (long long)blockIdx.x * 32; j0 < d.nz; j0 += (long long)gridDim.x * 32) {
+            const long long j = j0 + lane;
+            if (j < d.nz) {
+                const int g = (int)j + 1;
+                const long long rb = (long long)g * nr;
+                const unsigned zf = d.zc_flags[g];
+                const double dzg = d.dz[g];
+                for (int i = warp; i < nr; i += nwarp) {
+                    const long long idx = rb + i;
+                    const double Tc = d.T[idx], To = a.has_old ? d.Told[idx] : Tc;
+                    const double cE = d.cR[idx], cW = d.cR[idx - 1], cN = d.cZ[idx], cS = d.cZ[idx - nr];
+                    const double Tnb = cE * d.T[idx + 1] + cW * d.T[idx - 1] + cN * d.T[idx + nr] + cS * d.T[idx - nr];
+                    const DiagCell c = diag_cell(d, ph, a, g, i, zf, dzg, Tc, To, cE, cW, cN, cS, Tnb);
+                    d.diag[idx] = c.dg;
+                    d.r[idx] = c.r0;
+                    if (write_dinv_jacobi) d.dinv[idx] = 1.0 / c.dg;
+                    if (a.rhs_out) a.rhs_out[idx] = c.rhs;
+                    acc[0] += c.r0 * c.r0;
+                    acc[1] += c.rhs * c.rhs;
+                }
+            }
+        }
+    } else {
     for (long long j = (long long)blockIdx.x * rpb + rsub; j < d.nz; j += (long long)gridDim.x * rpb) {
         const int g = (int)j + 1;
         const long long rb = (long long)g * nr;
@@ -449,40 +511,16 @@ __global__ void __launch_bounds__(256, 2) k_diag(HpDev d, hp_phys ph, HpKArgs a,
                 const int i = ib + u * tpr;
                 if (i >= nr) break;
                 const long long idx = rb + i;
-                double rho, cp;
-                hp::rho_cp_region(ph, d.cell_band[i], zf, Tc[u], rho, cp);
-                const double vol = d.wc[i] * d.dr[i] * dzg;
-                const double cap = cp * rho * vol / a.dt;
-                double dg = cap;
-                dg += cE[u]; dg += cW[u]; dg += cN[u]; dg += cS[u];
-                double rhs = cap * To[u];
-                if (i == nr - 1) {
-                    const double kout = k_outface(d, ph, g, Tc[u]);
-                    const double k0 = (ph.gamma == 0) ? d.k0_out[g] : kout;
-                    const double A_out = d.A_out_r * dzg;
-                    const double h = d.h_line[g], Ta = d.Tamb_line[g];
-                    if (zf & HP_ZF_BC_COND) {
-                        const double robin = kout * A_out / (h * d.d_out + k0);
-                        dg += robin * h;
-                        double gs = h * Ta;
-                        if (ph.radiation) gs += ph.sigma * d.eps_line[g] * (Ta * Ta * Ta * Ta - Tc[u] * Tc[u] * Tc[u] * Tc[u]);
-                        rhs += robin * gs;
-                    }
-                    if (zf & HP_ZF_BC_EVAP) {
-                        const double q = d.q_line[g];
-                        rhs += ((ph.source == 0) ? (q / kout) : q) * A_out;
-                    }
-                }
-                const double LT = dg * Tc[u] - Tnb[u];
-                const double r0 = rhs - LT;
-                d.diag[idx] = dg;
-                d.r[idx] = r0;
-                if (write_dinv_jacobi) d.dinv[idx] = 1.0 / dg;
-                if (a.rhs_out) a.rhs_out[idx] = rhs;
-                acc[0] += r0 * r0;
-                acc[1] += rhs * rhs;
+                const DiagCell c = diag_cell(d, ph, a, g, i, zf, dzg, Tc[u], To[u], cE[u], cW[u], cN[u], cS[u], Tnb[u]);
+                d.diag[idx] = c.dg;
+                d.r[idx] = c.r0;
+                if (write_dinv_jacobi) d.dinv[idx] = 1.0 / c.dg;
+                if (a.rhs_out) a.rhs_out[idx] = c.rhs;
+                acc[0] += c.r0 * c.r0;
+                acc[1] += c.rhs * c.rhs;
             }
         }
+    }
     }
     double tot[2];
     if (cta_publish<2>(acc, 0u, d.partials, &d.st->ticket, tot, d.p2p != 0) && threadIdx.x == 0) {
@@ -1534,11 +1572,12 @@ int diag_tpr_log2(int nr) {
 HpKernelLaunch desc_diag(const HpLaunchCfg& c, const HpDev& d) {
     const int rpb = 256 >> diag_tpr_log2(d.nr);
     int occ = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_diag, 256, 0) != cudaSuccess || occ < 1) occ = 1;
+    const void* f = d.nr <= 16 ? (const void*)k_diag<true> : (const void*)k_diag<false>;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f, 256, 0) != cudaSuccess || occ < 1) occ = 1;
     long long g = ((long long)d.nz + rpb - 1) / rpb, cap = (long long)c.num_sms * occ;
     if (g > cap) g = cap;
     if (g > HP_MAX_PARTIALS) g = HP_MAX_PARTIALS;
-    return {(const void*)k_diag, dim3((unsigned)(g < 1 ? 1 : g)), dim3(256), 0};
+    return {f, dim3((unsigned)(g < 1 ? 1 : g)), dim3(256), 0};
 }
 // pivots of `rows` rows in total (the fine level, or every coarse level in one launch): args (HpLevelSet, int first, int nr, const int* skip)
 HpKernelLaunch desc_factor_rows(const HpLaunchCfg& c, long long rows) {

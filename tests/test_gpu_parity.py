@@ -387,6 +387,44 @@ def test_ensemble_stack_matches_independent_pipes(cfg):
         assert np.max(np.abs(T[m] - refs[m])) <= 4 * PER_STEP_TOL_K, m
 
 
+def test_ensemble_of_64_members_with_radiation(cfg):
+    """BASELINE configs[4] in small: 64 members with their own heat input, film coefficient, ambient temperature AND
+    emissivity (radiative condenser on), advanced together with updateOld + 3 sweeps; every member against its own
+    oracle run.  Both preconditioners (the stacked mesh coarsens across member boundaries, where the coupling is zero)."""
+    mp = fo.synthetic_mesh_params(40, 2, 4, 10)
+    M = 64
+    rng = np.random.default_rng(1234)
+    qs = cfg['parameters']['Q_input_flux'] * rng.uniform(0.5, 1.5, M)
+    hs = rng.uniform(2, 20, M)
+    Ts = rng.uniform(280, 300, M)
+    es = rng.uniform(0.0, 0.9, M)
+    grid = fo.build_grid(mp, cfg['dimensions'])
+    refs = []
+    for m in range(M):
+        case = fo.case_from_config(h=hs[m], radiation=True)
+        case.parameters['Q_input_flux'] = qs[m]
+        case.parameters['T_amb'] = Ts[m]
+        case.parameters['emissivity'] = es[m]
+        o = fo.Oracle(grid, case, has_old=True)
+        for _ in range(3):
+            o.update_old()
+            for _ in range(3):
+                o.sweep(0.2, solver='banded')
+        refs.append(o.T)
+    from heat_pipe_solver_b200.ensemble import EnsembleSolver
+    for precond in ('rline', 'mgline'):
+        with EnsembleSolver(mp, cfg['dimensions'], cfg['parameters'], cfg['constants'], q=qs, h=hs, T_amb=Ts, emissivity=es,
+                            radiation=True, precond=precond) as ens:
+            ens.run(0.2, 3, sweeps=3, has_old=True)
+            T = ens.value()
+            assert all(st['converged'] for st in ens.stats(9))
+            assert ens.solver.effective_precond == precond
+        worst = max(float(np.max(np.abs(T[m] - refs[m]))) for m in range(M))
+        assert worst <= 9 * PER_STEP_TOL_K, (precond, worst)
+    # members really differ (the test would pass trivially on identical pipes otherwise)
+    assert np.ptp([r.max() for r in refs]) > 1.0
+
+
 def test_full_size_sweep_residual_property(cfg):
     """BASELINE configs[2] size (4096 x 1024): one sweep from a hot state; the oracle re-assembles the system on
     the host at the pre-sweep field and checks that the GPU's answer solves it (row-scaled residual in K)."""
