@@ -298,7 +298,7 @@ def run_gpu(args, rank, world, local_rank):
             solver = make_solver_for_rank(mesh, cfg, rank, world, comm=args.comm, tol=args.tol, loop_mode=loop_mode,
                                           extrapolate=args.extrapolate, precond=args.precond,
                                           mg_levels=args.mg_levels, mg_coarse_sweeps=args.mg_sweeps, mg_omega=args.mg_omega,
-                                          refactor_every=args.refactor_every, reuse_converged=args.reuse_converged, while_unroll=args.while_unroll)
+                                          refactor_every=args.refactor_every, reuse_converged=args.reuse_converged, while_unroll=args.while_unroll, tma_rows=bool(args.tma_rows))
 
         def barrier():
             stream.synchronize()
@@ -404,7 +404,7 @@ def run_gpu(args, rank, world, local_rank):
             one = make_solver_for_rank(big_mesh, cfg, 0, 1, tol=args.tol, loop_mode=args.loop_mode, precond=args.precond,
                                        extrapolate=args.extrapolate, refactor_every=args.refactor_every,
                                        mg_levels=args.mg_levels, mg_coarse_sweeps=args.mg_sweeps, mg_omega=args.mg_omega,
-                                       reuse_converged=args.reuse_converged, while_unroll=args.while_unroll)
+                                       reuse_converged=args.reuse_converged, while_unroll=args.while_unroll, tma_rows=bool(args.tma_rows))
             try:
                 one.run(DT, args.warmup, sweeps=SWEEPS, has_old=HAS_OLD)
                 stream.synchronize()
@@ -474,7 +474,7 @@ def run_gpu(args, rank, world, local_rank):
                                       members=(int(args.workload.split(':')[1]) if ensemble and ':' in args.workload else 1024)),
             'run': {'parallelism': 'single GPU' if world == 1 else (f'members sharded over {world} ranks, no collective' if ensemble else f'axial slabs x{world}, ' + ('NVLink peer-memory halo rows + CG scalars fused into the kernels, one CUDA graph per step' if args.comm == 'p2p' else 'NCCL send/recv halo + all-gathered CG scalars, host-driven loop')),
                     'solver': f'PCG ({args.precond}) tol {args.tol:g} K', 'pcg_iterations_per_step': iters / args.steps, 'loop_mode': loop_mode,
-                    'refactor_every_sweeps': args.refactor_every, 'reuse_converged_sweeps': bool(args.reuse_converged),
+                    'refactor_every_sweeps': args.refactor_every, 'tma_rows': bool(args.tma_rows), 'reuse_converged_sweeps': bool(args.reuse_converged),
                     'pcg_start': f"extrapolated from the step history, max order {args.extrapolate}",
                     'e2e_note': 'hp_run_host uploads the field every step but keeps the solver-side step history (T_old, increments) for the '
                                 'predicted PCG start; a caller uploading an unrelated field pays first-step iteration counts'},
@@ -504,6 +504,7 @@ def main():
     ap.add_argument('--no-splu', action='store_true', help='--impl reference: skip the SuperLU variant (cpu_baseline_splu)')
     ap.add_argument('--profile-slabs', action='store_true', help='N>1: per-kernel CUDA-event table of rank 0 (stream-launch pass on every rank)')
     ap.add_argument('--while-unroll', type=int, default=1)
+    ap.add_argument('--tma-rows', type=int, default=0, help='1: k_cg_B with the cp.async.bulk / mbarrier row pipeline (hp_solve_opts.tma_rows)')
     ap.add_argument('--extrapolate', type=int, default=3, help='maximum order of the extrapolated PCG start (0 = off)')
     ap.add_argument('--scaling-ref', action='store_true',
                     help='N=1: also time the 16384x4096 multi-GPU workload on this one GPU (extra key multi_gpu_workload_on_one_gpu)')

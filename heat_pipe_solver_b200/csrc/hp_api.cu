@@ -391,7 +391,7 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
     h->opts.precond = 1; h->opts.criterion = 0; h->opts.tol = 1e-9; h->opts.max_iter = 5000;
     h->opts.loop_mode = 1; h->opts.poll_chunk = 8; h->opts.refactor_every = 1; h->opts.extrapolate = 3;
     h->opts.mg_levels = 6; h->opts.mg_coarse_sweeps = 2; h->opts.mg_omega = 0.6; h->opts.reuse_converged = 0;
-    h->opts.while_unroll = 1; h->opts.peer_timeout_ms = 60000; h->opts.mg_zscale = 0.5;
+    h->opts.while_unroll = 1; h->opts.peer_timeout_ms = 60000; h->opts.mg_zscale = 0.5; h->opts.tma_rows = 0;
 
     // initial field + snapshots (main.py:34,133,145,152)
     CK(hpk::launch_fill_rows(d, d.T, h->stream));
@@ -723,7 +723,7 @@ static int emit_iteration(Emitter& e, HpKArgs& a) {
     }
     if (emit(e, hpk::desc_cg_A(h->cfg, d), params, KIND_A)) return -1;
     if (emit_combine(e, a, 1)) return -1;
-    if (emit(e, hpk::desc_cg_B(h->cfg, d, h->opts.precond != 0, h->opts.criterion), params, KIND_B)) return -1;
+    if (emit(e, hpk::desc_cg_B(h->cfg, d, h->opts.precond != 0, h->opts.criterion, h->opts.tma_rows), params, KIND_B)) return -1;
     if (emit_combine(e, a, 2)) return -1;
     return 0;
 }
@@ -763,7 +763,7 @@ static int emit_sweep_head(Emitter& e, HpKArgs& a, bool refactor, bool shift) {
         }
         if (emit(e, hpk::desc_cg_A(h->cfg, d), ps, KIND_A)) return -1;
         if (emit_combine(e, as, 1)) return -1;
-        if (emit(e, hpk::desc_cg_B(h->cfg, d, h->opts.precond != 0, h->opts.criterion), ps, KIND_B)) return -1;
+        if (emit(e, hpk::desc_cg_B(h->cfg, d, h->opts.precond != 0, h->opts.criterion, h->opts.tma_rows), ps, KIND_B)) return -1;
         if (emit_combine(e, as, 3)) return -1;
         if (a.mg && refactor && emit_mg_setup(e, h->opts.refactor_every > 1)) return -1;
     } else {
@@ -815,7 +815,7 @@ static bool same_opts(const hp_solve_opts& a, const hp_solve_opts& b) {
            a.loop_mode == b.loop_mode && a.refactor_every == b.refactor_every && a.extrapolate == b.extrapolate &&
            a.mg_levels == b.mg_levels && a.mg_coarse_sweeps == b.mg_coarse_sweeps && a.mg_omega == b.mg_omega &&
            a.reuse_converged == b.reuse_converged && a.while_unroll == b.while_unroll && a.mg_zscale == b.mg_zscale &&
-           a.peer_timeout_ms == b.peer_timeout_ms;
+           a.peer_timeout_ms == b.peer_timeout_ms && a.tma_rows == b.tma_rows;
 }
 
 static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int update_old, GraphEntry** out) {

@@ -181,7 +181,8 @@ HpKernelLaunch desc_mg_up(const HpLaunchCfg&, int nz_level);     // args: (HpDev
 bool mg_fused_supported(const HpLaunchCfg&);
 HpKernelLaunch desc_wait();       // args: (HpDev, hp_phys, HpKArgs, int kind): peer-memory variant of finalize
 HpKernelLaunch desc_finalize();   // args: (HpDev, hp_phys, HpKArgs, int kind) kind: 0 diag, 1 A, 2 B, 3 init
-HpKernelLaunch desc_cg_B(const HpLaunchCfg&, const HpDev&, int precond, int criterion);
+HpKernelLaunch desc_cg_B(const HpLaunchCfg&, const HpDev&, int precond, int criterion, int tma);
+bool cg_B_tma_supported(const HpLaunchCfg&, int precond, int criterion);
 
 cudaError_t launch_eval_property(const hp_phys& ph, int id, const double* T, double* out, long long n, cudaStream_t s);
 cudaError_t launch_cell_fields(const HpDev& d, const hp_phys& ph, double* rho, double* cp, double* kavg, cudaStream_t s);

@@ -875,6 +875,125 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_B(EPT)
     }
 }
 
+
+// ---- k_cg_B_tma : k_cg_B with a TMA-staged row pipeline ----------------------------------------------------------------
+// Same arithmetic as k_cg_B<TPL 256, EPT 4, RLINE, !INIT>.  The six operand rows of the NEXT row(s) (r, x, p, q, dinv, cR:
+// 6 x nr x 8 bytes) are brought into shared memory by bulk asynchronous copies (cp.async.bulk global -> shared, completion
+// on an mbarrier) issued by one thread, so they are in flight while the team runs the two scans and the two named barriers
+// of the current row; in k_cg_B the loads of a row are issued at the top of its iteration and nothing is in flight during
+// its line solve (ncu: long_scoreboard + barrier stalls, 0.82 of the copy peak).  Radial neighbours (the multiplier
+// entering a warp) come from the staged row instead of an extra global load.  Results go out through registers as before.
+constexpr int BT_STAGES = 2, BT_ARR = 6;
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void lds4(const double* p, double (&v)[4]) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(smem_u32(p)));
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[2]), "=d"(v[3]) : "r"(smem_u32(p + 2)));
+}
+
+__global__ void __launch_bounds__(256, 2) k_cg_B_tma(HpDev d, hp_phys ph, HpKArgs a) {
+    constexpr int TPL = 256, EPT = 4;
+    using G = TeamGeom<TPL>;
+    const HpState s0 = *d.st;
+    if (s0.done) return;
+    extern __shared__ __align__(128) unsigned char bt_smem[];
+    const int nr = d.nr, nz = d.nz;
+    const int rowp = (nr + 3) & ~3;                                  // staged row length (doubles)
+    double* stage0 = reinterpret_cast<double*>(bt_smem);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(stage0 + (size_t)BT_STAGES * BT_ARR * rowp);
+    __shared__ double s_fA[G::NW], s_fB[G::NW], s_bA[G::NW], s_bB[G::NW];
+    const int tl = threadIdx.x, lane = tl & 31, wt = tl >> 5;
+    const int i0 = tl * EPT;
+    const long long team = blockIdx.x, nteams = gridDim.x;
+    const int ja = (int)(team * nz / nteams), jb = (int)((team + 1) * nz / nteams);
+    const double alpha = a.shift ? 1.0 : s0.alpha;
+    const double* __restrict__ pcur = s0.parity ? d.p1 : d.p0;
+    const unsigned row_bytes = (unsigned)nr * 8u;
+    if (tl == 0) {
+        for (int s = 0; s < BT_STAGES; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int g, int s) {             // one thread: the six operand rows of row g -> stage s
+        const long long rb = (long long)g * nr;
+        double* st = stage0 + (size_t)s * BT_ARR * rowp;
+        mbar_expect_tx(&bars[s], BT_ARR * row_bytes);
+        bulk_g2s(st + 0 * rowp, d.r + rb, row_bytes, &bars[s]);
+        bulk_g2s(st + 1 * rowp, d.T + rb, row_bytes, &bars[s]);
+        bulk_g2s(st + 2 * rowp, pcur + rb, row_bytes, &bars[s]);
+        bulk_g2s(st + 3 * rowp, d.q + rb, row_bytes, &bars[s]);
+        bulk_g2s(st + 4 * rowp, d.dinv + rb, row_bytes, &bars[s]);
+        bulk_g2s(st + 5 * rowp, d.cR + rb, row_bytes, &bars[s]);
+    };
+    if (tl == 0)
+        for (int k = 0; k < BT_STAGES && ja + 1 + k <= jb; ++k) issue(ja + 1 + k, k);
+
+    double acc[3] = {0.0, 0.0, 0.0};   // rz, rr, crit(max)
+    for (int g = ja + 1; g <= jb; ++g) {
+        const int k = g - ja - 1, s = k % BT_STAGES;
+        const long long rb = (long long)g * nr;
+        const double* st = stage0 + (size_t)s * BT_ARR * rowp;
+        mbar_wait(&bars[s], (unsigned)(k / BT_STAGES) & 1u);
+        double rv[EPT], xv[EPT], pv[EPT], qv[EPT], dv[EPT], cr[EPT], zv[EPT];
+        double m0_edge = 0.0;
+        if (i0 < nr) {
+            lds4(st + 0 * rowp + i0, rv); lds4(st + 1 * rowp + i0, xv); lds4(st + 2 * rowp + i0, pv);
+            lds4(st + 3 * rowp + i0, qv); lds4(st + 4 * rowp + i0, dv); lds4(st + 5 * rowp + i0, cr);
+            if (lane == 0 && tl != 0) m0_edge = st[5 * rowp + i0 - 1] * st[4 * rowp + i0 - 1];
+        } else {
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) { rv[e] = xv[e] = pv[e] = qv[e] = dv[e] = cr[e] = 0.0; }
+        }
+        // every thread has taken its operands out of the stage: refill it with the row BT_STAGES ahead
+        asm volatile("bar.sync 15, 256;" ::: "memory");
+        if (tl == 0 && g + BT_STAGES <= jb) issue(g + BT_STAGES, s);
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            xv[e] = fma(alpha, pv[e], xv[e]);
+            rv[e] = fma(-alpha, qv[e], rv[e]);
+        }
+        store_row<EPT, true>(d.T + rb, i0, nr, xv);
+        store_row<EPT, true>(d.r + rb, i0, nr, rv);
+        if (d.p2p) {
+            if (g == 1 && d.T_lo) store_row<EPT, true>(d.T_lo, i0, nr, xv);
+            if (g == nz && d.T_hi) store_row<EPT, true>(d.T_hi, i0, nr, xv);
+        }
+        line_solve<TPL, EPT>(rv, dv, cr, m0_edge, lane, wt, 0, s_fA, s_fB, s_bA, s_bB, zv);
+        store_row<EPT, true>(d.z + rb, i0, nr, zv);
+        if (d.p2p) {
+            if (g == 1 && d.z_lo) store_row<EPT, true>(d.z_lo, i0, nr, zv);
+            if (g == nz && d.z_hi) store_row<EPT, true>(d.z_hi, i0, nr, zv);
+        }
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            acc[2] = fmax(acc[2], fabs(zv[e]));
+            acc[0] = fma(rv[e], zv[e], acc[0]);
+            acc[1] = fma(rv[e], rv[e], acc[1]);
+        }
+    }
+    double tot[3];
+    if (cta_publish<3>(acc, 4u, d.partials, &d.st->ticket, tot, d.p2p != 0) && threadIdx.x == 0) {
+        if (d.nranks > 1) stash_local<3>(d, tot, HP_COMM_B);
+        else finalize_B(d, a, a.shift, tot[0], tot[1], tot[2], a.mg ? 1 : 0);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // auxiliary kernels
 // ------------------------------------------------------------------------------------------------
@@ -1672,7 +1791,29 @@ static HpKernelLaunch desc_B(const HpLaunchCfg& c, int precond, int init) {
     return {f, dim3(team_grid(f, c, c.cta_threads, c.teams_per_cta, 1)), dim3(c.cta_threads), 0};
 }
 HpKernelLaunch desc_cg_init(const HpLaunchCfg& c, const HpDev& d, int precond, int criterion) { return desc_B(c, precond, 1); }
-HpKernelLaunch desc_cg_B(const HpLaunchCfg& c, const HpDev& d, int precond, int criterion) { return desc_B(c, precond, 0); }
+// the TMA-staged variant serves the 256-thread x 4-cell row shape (512 < nr <= 1024, nr % 4 == 0) with the line
+// preconditioner and a stopping rule that does not need the diagonal
+bool cg_B_tma_supported(const HpLaunchCfg& c, int precond, int criterion) {
+    return precond != 0 && criterion != 1 && c.tpl == 256 && c.ept == 4 && c.vec;
+}
+HpKernelLaunch desc_cg_B(const HpLaunchCfg& c, const HpDev& d, int precond, int criterion, int tma) {
+    if (!(tma && cg_B_tma_supported(c, precond, criterion))) return desc_B(c, precond, 0);
+    const void* f = (const void*)k_cg_B_tma;
+    const int rowp = (d.nr + 3) & ~3;
+    const size_t smem = (size_t)BT_STAGES * BT_ARR * rowp * sizeof(double) + BT_STAGES * sizeof(unsigned long long);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 6 * 1024 * 8 + 64);
+        attr_set = true;
+    }
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f, 256, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
+    long long chunks = (long long)c.num_sms * occ;
+    if (chunks > c.nz) chunks = c.nz;
+    if (chunks > 1 && c.nz / chunks < 2) chunks = (c.nz + 1) / 2;
+    if (chunks > HP_MAX_PARTIALS) chunks = HP_MAX_PARTIALS;
+    return {f, dim3((unsigned)(chunks < 1 ? 1 : chunks)), dim3(256), smem};
+}
 
 cudaError_t launch_eval_property(const hp_phys& ph, int id, const double* T, double* out, long long n, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;

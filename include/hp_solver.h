@@ -89,6 +89,10 @@ typedef struct hp_solve_opts {
                                error until hp_comm_clear_fault */
     double mg_zscale;       /* mgline: axial coupling of a coarse operator relative to the Galerkin (row-pair aggregation) value;
                                1 = Galerkin, 0.5 (default) = what a discretisation on the coarse rows gives */
+    int32_t tma_rows;       /* 1: k_cg_B stages its operand rows in shared memory with bulk asynchronous copies (cp.async.bulk +
+                               mbarrier, the next rows in flight during the scans of the current one) where the row shape allows
+                               (512 < nr <= 1024, nr % 4 == 0); 0: register-direct 256-bit loads */
+    int32_t _pad;
 } hp_solve_opts;
 
 typedef struct hp_sweep_stat {

@@ -387,6 +387,21 @@ def test_ensemble_stack_matches_independent_pipes(cfg):
         assert np.max(np.abs(T[m] - refs[m])) <= 4 * PER_STEP_TOL_K, m
 
 
+@pytest.mark.parametrize('tag', ['s48x1024', 's24x1000'])
+def test_tma_row_pipeline_is_bit_identical(cfg, tag):
+    """hp_solve_opts.tma_rows: k_cg_B fed by cp.async.bulk + mbarrier stages instead of register-direct loads -- the same
+    arithmetic in the same order, so fields, residuals and iteration counts are bit-identical."""
+    got = {}
+    for tma in (False, True):
+        s, o = make_pair(cfg, SHAPES[tag], T0=hot_field, has_old=True, solver_kw=dict(precond='rline', tma_rows=tma))
+        with s:
+            s.run(0.1, 3, sweeps=3, has_old=True)
+            got[tma] = (s.value.copy(), [(st['iters'], st['residual_l2'], st['crit']) for st in s.stats(9)])
+    assert np.array_equal(got[True][0], got[False][0])
+    assert got[True][1] == got[False][1]
+    assert sum(it for it, _, _ in got[True][1]) > 20          # the kernel under test did run
+
+
 def test_ensemble_of_64_members_with_radiation(cfg):
     """BASELINE configs[4] in small: 64 members with their own heat input, film coefficient, ambient temperature AND
     emissivity (radiative condenser on), advanced together with updateOld + 3 sweeps; every member against its own

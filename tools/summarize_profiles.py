@@ -19,7 +19,13 @@ tag = sys.argv[1] if len(sys.argv) > 1 else 'r1'
 os.makedirs(P, exist_ok=True)
 
 # ---- launch list -----------------------------------------------------------------------------
-rows = list(csv.reader(open(os.path.join(G, 'launches.csv'))))
+def src(name):
+    """gpurun_out/<tag>_<name> (r2 scripts) or gpurun_out/<name> (r1 scripts)"""
+    p = os.path.join(G, f'{tag}_{name}')
+    return p if os.path.exists(p) else os.path.join(G, name)
+
+
+rows = list(csv.reader(open(src('launches.csv'))))
 hi = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
 hdr, data = rows[hi], rows[hi + 1:]
 kn, mv, mn, mu = (hdr.index(x) for x in ('Kernel Name', 'Metric Value', 'Metric Name', 'Metric Unit'))
@@ -34,16 +40,16 @@ for r in data:
     c[1] += v
 tot = sum(v[1] for v in agg.values())
 with open(os.path.join(P, f'{tag}_launches_summary.txt'), 'w') as f:
-    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-single-gpu-ref --loop-mode host` (default preconditioner)\n")
+    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --loop-mode host` (default preconditioner)\n")
     f.write("# (cold-cache, serialised launches: compare SHARES, not absolutes)\n")
     f.write(f"{'kernel':58s} {'launches':>8s} {'total ms':>10s} {'avg us':>9s} {'share':>7s}\n")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"{k:58s} {v[0]:8d} {v[1] / 1e6:10.3f} {v[1] / v[0] / 1e3:9.2f} {100 * v[1] / tot:6.1f}%\n")
-with open(os.path.join(G, 'launches.csv'), 'rb') as src, gzip.open(os.path.join(P, f'{tag}_launches.csv.gz'), 'wb') as dst:
-    shutil.copyfileobj(src, dst)
+with open(src('launches.csv'), 'rb') as fsrc, gzip.open(os.path.join(P, f'{tag}_launches.csv.gz'), 'wb') as dst:
+    shutil.copyfileobj(fsrc, dst)
 
 # ---- full capture of the PCG kernels -----------------------------------------------------------
-rep = os.path.join(G, 'prof_cg.ncu-rep')
+rep = src('prof.ncu-rep') if os.path.exists(src('prof.ncu-rep')) else src('prof_cg.ncu-rep')
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rr = list(csv.reader(raw.splitlines()))
 h, units, body = rr[0], rr[1], rr[2:]
@@ -61,13 +67,13 @@ idx = [h.index(k) for k in keep if k in h]
 traffic = {}
 with open(os.path.join(P, f'{tag}_ncu_cg_metrics.csv'), 'w', newline='') as f:
     w = csv.writer(f)
-    w.writerow(['# ncu --set full --clock-control none --import-source on -k regex:k_cg_A|k_cg_B|k_mg_res|k_mg_line|k_mg_fused -s 5666 -c 16 = one PCG iteration of the first sweep of a step (cold cache per replay: the L2 window does not show here)'])
+    w.writerow(['# ncu --set full --clock-control none --import-source on -k regex:k_cg_A|k_cg_B|k_mg_res|k_mg_line|k_mg_fused|k_diag|k_factor -s <skip> -c <n>: consecutive launches of the hot kernels inside one time step (cold cache per replay: the L2 window does not show here)'])
     w.writerow([h[i] for i in idx])
     w.writerow([units[i] for i in idx])
     for r in body:
         w.writerow([r[i] for i in idx])
         kname = r[h.index('Kernel Name')]
-        name = next((v for k, v in (('k_cg_A', 'cg_A'), ('k_cg_B', 'cg_B'), ('k_mg_res', 'mg_res'), ('k_mg_fused', 'mg_res'), ('k_mg_line', 'mg_line')) if k in kname), 'other')
+        name = next((v for k, v in (('k_cg_A', 'cg_A'), ('k_cg_B', 'cg_B'), ('k_mg_res', 'mg_res'), ('k_mg_fused', 'mg_res'), ('k_mg_line', 'mg_line'), ('k_diag', 'diag'), ('k_factor', 'factor')) if k in kname), 'other')
 
         def tobytes(col):
             v, u = float(r[h.index(col)].replace(',', '')), units[h.index(col)]
@@ -75,9 +81,8 @@ with open(os.path.join(P, f'{tag}_ncu_cg_metrics.csv'), 'w', newline='') as f:
         traffic.setdefault(name, []).append(tobytes('dram__bytes_read.sum') + tobytes('dram__bytes_write.sum'))
 # the capture also holds coarse-level launches of the V-cycle kernels: the fine level is the one with the most traffic
 json.dump({k: max(v) for k, v in traffic.items()}, open(os.path.join(P, 'ncu_traffic.json'), 'w'), indent=1)
-for name in ('bench.json', 'bench_ref.json', 'bench_rline.json'):
-    src = os.path.join(G, name)
-    if os.path.exists(src):
-        shutil.copy(src, os.path.join(P, f'{tag}_{name}'))
+for name in ('bench.json', 'bench_ref.json', 'bench_rline.json', 'ensemble_rline.json', 'ensemble_mgline.json'):
+    if os.path.exists(src(name)):
+        shutil.copy(src(name), os.path.join(P, f'{tag}_{name}'))
 print(open(os.path.join(P, f'{tag}_launches_summary.txt')).read())
 print(json.load(open(os.path.join(P, 'ncu_traffic.json'))))
