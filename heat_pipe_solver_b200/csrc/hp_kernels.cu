@@ -628,7 +628,20 @@ __device__ __forceinline__ void line_solve(const double (&rv)[EPT], const double
             if (lane == W - 1) { s_fA[wt] = A; s_fB[wt] = B; }
         }
         team_barrier<TPL, CL>(team_in_cta);
-        for (int w = 0; w < wt; ++w) carry = fma(s_fA[w], carry, s_fB[w]);
+        if constexpr (NW >= 16) {
+            // many warps per row (wide rows, cluster teams): a serial walk over up to NW-1 totals costs ~1000 cycles for the
+            // last warp, twice per row; every warp scans the NW maps y -> A y + B with shuffles instead (5 steps)
+            double ca = (lane < NW) ? s_fA[lane] : 1.0, cb = (lane < NW) ? s_fB[lane] : 0.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double ap = __shfl_up_sync(0xffffffffu, ca, o), bp = __shfl_up_sync(0xffffffffu, cb, o);
+                if (lane >= o) { cb = fma(ca, bp, cb); ca *= ap; }
+            }
+            const double through = __shfl_sync(0xffffffffu, cb, wt > 0 ? wt - 1 : 0);
+            carry = wt > 0 ? through : 0.0;
+        } else {
+            for (int w = 0; w < wt; ++w) carry = fma(s_fA[w], carry, s_fB[w]);
+        }
     }
     const double ybefore = fma(Ax, carry, Bx);
 #pragma unroll
@@ -662,7 +675,19 @@ __device__ __forceinline__ void line_solve(const double (&rv)[EPT], const double
             if (lane == 0) { s_bA[wt] = A; s_bB[wt] = B; }
         }
         team_barrier<TPL, CL>(team_in_cta);
-        for (int w = NW - 1; w > wt; --w) carry = fma(s_bA[w], carry, s_bB[w]);
+        if constexpr (NW >= 16) {
+            // lane j holds the map of warp NW-1-j: the walk from the last warp down becomes an upward scan
+            double ca = (lane < NW) ? s_bA[NW - 1 - lane] : 1.0, cb = (lane < NW) ? s_bB[NW - 1 - lane] : 0.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double ap = __shfl_up_sync(0xffffffffu, ca, o), bp = __shfl_up_sync(0xffffffffu, cb, o);
+                if (lane >= o) { cb = fma(ca, bp, cb); ca *= ap; }
+            }
+            const double through = __shfl_sync(0xffffffffu, cb, wt < NW - 1 ? NW - 2 - wt : 0);
+            carry = wt < NW - 1 ? through : 0.0;
+        } else {
+            for (int w = NW - 1; w > wt; --w) carry = fma(s_bA[w], carry, s_bB[w]);
+        }
     }
     const double zafter = fma(Ax, carry, Bx);
 #pragma unroll
@@ -1656,14 +1681,14 @@ bool pick_config(int nr, int nz, int num_sms, HpLaunchCfg* cfg, const char** err
 
 // Grid of a marching kernel: exactly one resident wave (occupancy of THIS instantiation x SM count) so that no
 // partially filled second wave appears; fewer CTAs when the mesh has too few rows (>= 2 rows per team).
-static int team_grid(const void* func, const HpLaunchCfg& c, int cta_threads, int teams_per_cta, int ncol) {
+static int team_grid(const void* func, const HpLaunchCfg& c, int cta_threads, int teams_per_cta, int ncol, int min_units = 2) {
     int occ = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, cta_threads, 0) != cudaSuccess || occ < 1) occ = 1;
     long long max_teams = (long long)c.num_sms * occ * teams_per_cta;
     long long chunks = max_teams / ncol;                 // row chunks; each is served by ncol column-tile teams
     if (chunks < 1) chunks = 1;
     if (chunks > c.nz) chunks = c.nz;
-    if (chunks > 1 && c.nz / chunks < 2) chunks = (c.nz + 1) / 2;
+    if (chunks > 1 && c.nz / chunks < min_units) chunks = (c.nz + min_units - 1) / min_units;
     long long teams = chunks * ncol;
     long long grid = (teams + teams_per_cta - 1) / teams_per_cta;
     if (grid < 1) grid = 1;
@@ -1719,8 +1744,9 @@ HpKernelLaunch desc_mg_res(const HpLaunchCfg& c, int nz_level) {
     HP_DISPATCH_A(c, HP_X);
 #undef HP_X
     HpLaunchCfg cl = c;
-    cl.nz = (nz_level + 1) / 2;                      // chunks are whole row pairs
-    return {f, dim3(team_grid(f, cl, c.ctaA, c.teams_per_ctaA, c.ncolA)), dim3(c.ctaA), 0};
+    cl.nz = (nz_level + 1) / 2;                      // chunks are whole row pairs; small levels: one pair per team (they are
+                                                     // chains of dependent row latencies, not bandwidth)
+    return {f, dim3(team_grid(f, cl, c.ctaA, c.teams_per_ctaA, c.ncolA, 1)), dim3(c.ctaA), 0};
 }
 // fused stage on cluster teams: one resident wave of clusters, >= one row pair per cluster
 static HpKernelLaunch desc_fused_cluster(const HpLaunchCfg& c, int nz_level, int mode) {
@@ -1748,7 +1774,7 @@ HpKernelLaunch desc_mg_up(const HpLaunchCfg& c, int nz_level) {       // only wh
 #undef HP_X
     HpLaunchCfg cl = c;
     cl.nz = (nz_level + 1) / 2;
-    return {f, dim3(team_grid(f, cl, c.ctaA, c.teams_per_ctaA, 1)), dim3(c.ctaA), 0};
+    return {f, dim3(team_grid(f, cl, c.ctaA, c.teams_per_ctaA, 1, 1)), dim3(c.ctaA), 0};
 }
 HpKernelLaunch desc_mg_down(const HpLaunchCfg& c, int nz_level) {     // only when mg_fused_supported(c)
     if (c.clF > 1) return desc_fused_cluster(c, nz_level, 2);
@@ -1758,7 +1784,7 @@ HpKernelLaunch desc_mg_down(const HpLaunchCfg& c, int nz_level) {     // only wh
 #undef HP_X
     HpLaunchCfg cl = c;
     cl.nz = (nz_level + 1) / 2;
-    return {f, dim3(team_grid(f, cl, c.ctaA, c.teams_per_ctaA, 1)), dim3(c.ctaA), 0};
+    return {f, dim3(team_grid(f, cl, c.ctaA, c.teams_per_ctaA, 1, 1)), dim3(c.ctaA), 0};
 }
 HpKernelLaunch desc_mg_line(const HpLaunchCfg& c, int nz_level) {
     const void* f = nullptr;
