@@ -494,7 +494,11 @@ __global__ void __launch_bounds__(256, 2) k_diag(HpDev d, hp_phys ph, HpKArgs a,
         const long long rb = (long long)g * nr;
         const unsigned zf = d.zc_flags[g];
         const double dzg = d.dz[g];
-        for (int ib = col0; ib < nr; ib += tpr * DIAG_U) {
+        // The vapor-core columns cost several times the wall columns (pow / exp / log chains) and sit in the first warps'
+        // column groups: rotate the warp -> column-group assignment with the row so that every warp of the CTA gets its
+        // share of them (no barrier in this loop: the warps run through their rows independently)
+        const int colr = (tpr == 256) ? ((col0 + 32 * (int)(j & 7)) & 255) : col0;
+        for (int ib = colr; ib < nr; ib += tpr * DIAG_U) {
             double Tc[DIAG_U], To[DIAG_U], cE[DIAG_U], cW[DIAG_U], cN[DIAG_U], cS[DIAG_U], Tnb[DIAG_U];
 #pragma unroll
             for (int u = 0; u < DIAG_U; ++u) {
