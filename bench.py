@@ -365,7 +365,9 @@ def run_gpu(args, rank, world, local_rank):
             del full
         # ---- per-kernel CUDA-event times (stream-launch mode, same workload continuing) ----------------------
         roof = None
-        if world == 1 or (args.profile_slabs and not ensemble and args.comm == 'p2p'):
+        if (world == 1 and not (ensemble and args.precond == 'rline')) or (args.profile_slabs and not ensemble and args.comm == 'p2p'):
+            # (ensembles with the line preconditioner run each pipe's step inside one CTA, k_pipe_step: on chip, no per-kernel
+            #  HBM roofline to speak of -- BASELINE.md section 4)
             # (slabs: every rank runs the same stream-mode pass -- the flag protocol needs all of them; rank 0's table is
             #  printed, its per-kernel times include the waits for the neighbours)
             solver.profile_begin(16384)

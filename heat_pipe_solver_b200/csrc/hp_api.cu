@@ -122,6 +122,10 @@ struct hp_solver_s {
     double *lv_lo = nullptr, *lv_hi = nullptr;      // level blocks of the lower / upper neighbour (peer mappings)
     std::vector<int> nz_of_rank;
     int* h_fault = nullptr;          // pinned + mapped: raised by a kernel whose wait for a peer timed out
+    // persistent one-pipe-per-CTA step (k_pipe_step): the mesh is pipe_M uncoupled members of pipe_nzm rows each
+    int pipe_nzm = 0, pipe_M = 0;
+    double* pipe_part = nullptr;     // [sweeps][M][4] member partials of a step
+    int pipe_part_sweeps = 0;
     // peer-memory exchange (hp_peer_export / hp_peer_import)
     HpComm* comm = nullptr;          // my mailbox
     double* qz_block = nullptr;      // base of the (q, z) allocation (IPC handle is per allocation)
@@ -358,6 +362,21 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
     UP(Tamb_line, std::vector<double>(m->Tamb_line, m->Tamb_line + nz + 2));
     UP(eps_line, std::vector<double>(m->eps_line, m->eps_line + nz + 2));
 #undef UP
+    {   // uncoupled members: maximal runs of rows between non-conducting faces (a single pipe is one member)
+        int first = -1, len = -1, count = 0;
+        bool uniform = m->axial_open[0] == 0 && m->axial_open[nz] == 0;
+        for (int g = 0; g <= nz && uniform; ++g) {
+            if (m->axial_open[g]) continue;
+            if (first >= 0) {
+                const int l = g - first;
+                if (len < 0) len = l;
+                uniform = uniform && (l == len);
+                ++count;
+            }
+            first = g;
+        }
+        if (uniform && count >= 1 && (long long)count * len == nz && hpk::pipe_kernel_supported(nr, len)) { h->pipe_nzm = len; h->pipe_M = count; }
+    }
     h->field_elems = (size_t)(nz + 2) * nr + 64;
     double** fields[] = {&d.T, &d.Told, &d.cR, &d.cZ, &d.diag, &d.dinv, &d.r, &d.p0, &d.p1};
     for (double** f : fields) {
@@ -392,6 +411,7 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
     h->opts.loop_mode = 1; h->opts.poll_chunk = 8; h->opts.refactor_every = 1; h->opts.extrapolate = 3;
     h->opts.mg_levels = 6; h->opts.mg_coarse_sweeps = 2; h->opts.mg_omega = 0.6; h->opts.reuse_converged = 0;
     h->opts.while_unroll = 1; h->opts.peer_timeout_ms = 60000; h->opts.mg_zscale = 0.5; h->opts.tma_rows = 0;
+    h->opts.pipe_kernel = 1;
 
     // initial field + snapshots (main.py:34,133,145,152)
     CK(hpk::launch_fill_rows(d, d.T, h->stream));
@@ -815,7 +835,7 @@ static bool same_opts(const hp_solve_opts& a, const hp_solve_opts& b) {
            a.loop_mode == b.loop_mode && a.refactor_every == b.refactor_every && a.extrapolate == b.extrapolate &&
            a.mg_levels == b.mg_levels && a.mg_coarse_sweeps == b.mg_coarse_sweeps && a.mg_omega == b.mg_omega &&
            a.reuse_converged == b.reuse_converged && a.while_unroll == b.while_unroll && a.mg_zscale == b.mg_zscale &&
-           a.peer_timeout_ms == b.peer_timeout_ms && a.tma_rows == b.tma_rows;
+           a.peer_timeout_ms == b.peer_timeout_ms && a.tma_rows == b.tma_rows && a.pipe_kernel == b.pipe_kernel;
 }
 
 static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int update_old, GraphEntry** out) {
@@ -902,6 +922,29 @@ static int run_steps(hp_solver_s* h, double dt, int n_steps, int sweeps, int has
     if (!(dt > 0.0)) return fail("dt must be > 0");
     if (sweeps < 1) return fail("sweeps must be >= 1");
     if (check_fault(h)) return -1;
+    // Small uncoupled pipes (the native 500 x 9 mesh, ensembles of it) with the line preconditioner: one CTA per pipe
+    // runs the whole step on chip (k_pipe_step) instead of ~150 latency-bound launches / one HBM pass per PCG iteration
+    if (h->opts.pipe_kernel && h->pipe_nzm > 0 && h->nranks == 1 && h->opts.precond == 1 && h->phys.gamma == 0 &&
+        !h->rhs_dbg && !h->prof_on && sweeps <= 64) {
+        HpDev& d = h->d;
+        if (h->pipe_part_sweeps < sweeps) {
+            if (dev_alloc(h, (void**)&h->pipe_part, (size_t)sweeps * h->pipe_M * 4 * sizeof(double))) return -1;
+            h->pipe_part_sweeps = sweeps;
+        }
+        HpKArgs a = make_args(h, dt, has_old);
+        int nzm = h->pipe_nzm, M = h->pipe_M, sw = sweeps, upd = (is_step && has_old) ? 1 : 0;
+        double* part = h->pipe_part;
+        const HpKernelLaunch ks = hpk::desc_pipe_step(d.nr, nzm, M), kf = hpk::desc_pipe_finalize();
+        for (int s = 0; s < n_steps; ++s) {
+            void* p1[] = {&d, &h->phys, &a, &nzm, &sw, &upd, &part};
+            if (launch(h, ks, p1)) return -1;
+            void* p2[] = {&d, &a, &M, &sw, &part};
+            if (launch(h, kf, p2)) return -1;
+            h->sweeps_host += sweeps;
+        }
+        h->hist = 0; h->c2_stashed = false;          // the predicted-start history of the row-kernel path is not maintained here
+        return 0;
+    }
     const int max_order = is_step ? (h->opts.extrapolate > 3 ? 3 : h->opts.extrapolate) : 0;
     const bool ext = max_order > 0;
     if (ext && h->hist_dt != dt) { if (h->hist > 1) h->hist = 1; h->hist_dt = dt; }     // increments scale with dt
@@ -1023,7 +1066,7 @@ int64_t hp_total_iters(hp_handle h) {
 }
 int64_t hp_kernel_launches(hp_handle h) {
     if (!h || fetch_state(h)) return -1;
-    long long graph_iters = h->h_state->total_iters - h->stream_mode_iters;
+    long long graph_iters = h->h_state->total_iters - h->stream_mode_iters - h->h_state->pipe_iters;
     return h->launches_host + (long long)h->graph_body_nodes * graph_iters;
 }
 

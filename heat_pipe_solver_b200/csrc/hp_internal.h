@@ -32,6 +32,7 @@ struct HpState {
     int32_t mg_init;     // 1 -> the next V-cycle is the first of its sweep (its last kernel starts the rz recurrence: no beta)
     unsigned int ticket; // last-CTA election
     unsigned int _pad2;
+    long long pipe_iters;       // PCG iterations run inside k_pipe_step (not separate launches)
     unsigned long long cycle;   // V-cycles started so far (sequence number of the stage flags between neighbouring slabs)
     long long sweep_count;
     long long total_iters;
@@ -183,6 +184,10 @@ HpKernelLaunch desc_wait();       // args: (HpDev, hp_phys, HpKArgs, int kind): 
 HpKernelLaunch desc_finalize();   // args: (HpDev, hp_phys, HpKArgs, int kind) kind: 0 diag, 1 A, 2 B, 3 init
 HpKernelLaunch desc_cg_B(const HpLaunchCfg&, const HpDev&, int precond, int criterion, int tma);
 bool cg_B_tma_supported(const HpLaunchCfg&, int precond, int criterion);
+// persistent one-pipe-per-CTA step: args (HpDev, hp_phys, HpKArgs, int nzm, int sweeps, int update_old, double* part)
+bool pipe_kernel_supported(int nr, int nzm);
+HpKernelLaunch desc_pipe_step(int nr, int nzm, int members);
+HpKernelLaunch desc_pipe_finalize();                 // args (HpDev, HpKArgs, int M, int sweeps, const double* part)
 
 cudaError_t launch_eval_property(const hp_phys& ph, int id, const double* T, double* out, long long n, cudaStream_t s);
 cudaError_t launch_cell_fields(const HpDev& d, const hp_phys& ph, double* rho, double* cp, double* kavg, cudaStream_t s);

@@ -1023,6 +1023,241 @@ __global__ void __launch_bounds__(256, 2) k_cg_B_tma(HpDev d, hp_phys ph, HpKArg
     }
 }
 
+
+// ================================================================================================
+// k_pipe_step : one whole time step ([T.updateOld()] + `sweeps` sweeps, each = assembly + PCG with the radial-line
+// preconditioner) of ONE heat pipe per CTA, everything on chip.          (main.py:200-202 / 267-271)
+// The native Faghri mesh (500 x 9 = 4500 cells) and the members of a parameter ensemble are far too small to stream:
+// through the row kernels a step is ~150 dependent launches of microseconds of work each (latency-bound), and an
+// ensemble streams every vector through HBM once per PCG iteration.  Here thread j owns radial line j of its pipe:
+//   registers      : x (= T), r, p, q / z of the line's NR cells
+//   shared memory  : cR, cZ, T_old, diag, pivots of the whole pipe (column-major: [i][j], conflict-free) + one exchange
+//                    buffer for the axial neighbours of p / T   (6 x NR x nz x 8 B = 211 KB for 500 x 9)
+// so the line solve is a 9-step recurrence inside a thread (no shuffles), the stencil needs one shared-memory exchange,
+// the dot products are block reductions, and nothing but the field is read or written in global memory per step.  Every
+// pipe runs its own PCG to the tolerance (the stacked formulation shares the CG scalars over the ensemble and iterates
+// until the slowest member is done).  Per-sweep statistics go to `part` [sweep][member][4] = res2, b2, crit, iters+flags;
+// k_pipe_finalize folds them in member order (deterministic) into the statistics ring.
+// ================================================================================================
+template <int NS, int NM>
+__device__ __forceinline__ void pipe_reduce(double (&v)[NS + NM], double (*s_red)[5][16], int& par) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NS + NM; ++k) {
+        const double w = k < NS ? warp_sum(v[k]) : warp_max(v[k]);
+        if (lane == 0) s_red[par][k][warp] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NS + NM; ++k) {
+        double acc = 0.0;                                   // every max-reduced quantity is >= 0
+        for (int w = 0; w < nwarp; ++w) acc = k < NS ? acc + s_red[par][k][w] : fmax(acc, s_red[par][k][w]);
+        v[k] = acc;
+    }
+    par ^= 1;       // the next reduction writes the other buffer; the one after that is separated by a barrier
+}
+
+template <int NR>
+__global__ void __launch_bounds__(512, 1) k_pipe_step(HpDev d, hp_phys ph, HpKArgs a, int nzm, int sweeps, int update_old,
+                                                     double* __restrict__ part) {
+    extern __shared__ __align__(16) double pipe_sm[];
+    __shared__ double s_red[2][5][16];
+    const int NZP = nzm;
+    double* s_cR = pipe_sm;
+    double* s_cZ = s_cR + NR * NZP;
+    double* s_To = s_cZ + NR * NZP;
+    double* s_dg = s_To + NR * NZP;
+    double* s_dv = s_dg + NR * NZP;
+    double* s_x = s_dv + NR * NZP;
+    const int m = blockIdx.x, M = gridDim.x, t = threadIdx.x;
+    const bool act = t < nzm;
+    const int g = m * nzm + (act ? t : 0) + 1;              // ghost-inclusive row of this thread's line
+    const long long rb = (long long)g * NR;
+    const unsigned zf = d.zc_flags[g];
+    const double dzg = d.dz[g];
+    int par = 0;
+    double x[NR], r[NR], p[NR], q[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        x[i] = act ? d.T[rb + i] : 0.0;
+        r[i] = p[i] = q[i] = 0.0;
+        if (act) {
+            s_cR[i * NZP + t] = d.cR[rb + i];
+            s_cZ[i * NZP + t] = d.cZ[rb + i];
+            const double to = update_old ? x[i] : d.Told[rb + i];
+            s_To[i * NZP + t] = to;
+            if (update_old) d.Told[rb + i] = to;            // T.updateOld() (main.py:269), kept visible to the other entry points
+        }
+    }
+    // z = M^-1 v on this thread's line (pivots in s_dv): forward / backward substitution of the LDL^T factors
+    auto line_solve_local = [&](const double (&v)[NR], double (&z)[NR]) {
+        double y[NR];
+        y[0] = v[0];
+#pragma unroll
+        for (int i = 1; i < NR; ++i) y[i] = fma(s_cR[(i - 1) * NZP + t] * s_dv[(i - 1) * NZP + t], y[i - 1], v[i]);
+        z[NR - 1] = s_dv[(NR - 1) * NZP + t] * y[NR - 1];
+#pragma unroll
+        for (int i = NR - 2; i >= 0; --i) {
+            const double dv = s_dv[i * NZP + t];
+            z[i] = fma(s_cR[i * NZP + t] * dv, z[i + 1], dv * y[i]);
+        }
+    };
+    for (int s = 0; s < sweeps; ++s) {
+        // ---- assembly at the current iterate (k_diag's arithmetic: diag_cell) ----
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < NR; ++i) if (act) s_x[i * NZP + t] = x[i];
+        __syncthreads();
+        double red[5] = {0.0, 0.0, 0.0, 0.0, 0.0};          // res2, b2, rz, rr | crit
+        if (act) {
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const double cE = s_cR[i * NZP + t], cW = i > 0 ? s_cR[(i - 1) * NZP + t] : 0.0;
+                const double cN = s_cZ[i * NZP + t], cS = t > 0 ? s_cZ[i * NZP + t - 1] : 0.0;
+                const double Tn = t + 1 < nzm ? s_x[i * NZP + t + 1] : 0.0, Ts = t > 0 ? s_x[i * NZP + t - 1] : 0.0;
+                const double Te = i + 1 < NR ? x[i + 1 < NR ? i + 1 : i] : 0.0, Tw = i > 0 ? x[i > 0 ? i - 1 : 0] : 0.0;
+                const double Tnb = cE * Te + cW * Tw + cN * Tn + cS * Ts;
+                const double To = a.has_old ? s_To[i * NZP + t] : x[i];
+                const DiagCell c = diag_cell(d, ph, a, g, i, zf, dzg, x[i], To, cE, cW, cN, cS, Tnb);
+                s_dg[i * NZP + t] = c.dg;
+                r[i] = c.r0;
+                red[0] += c.r0 * c.r0;
+                red[1] += c.rhs * c.rhs;
+            }
+            // pivots of the line (w_i = d_i - c_{i-1}^2 / w_{i-1})
+            double prev = 0.0;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const double inv = 1.0 / (s_dg[i * NZP + t] - prev);
+                s_dv[i * NZP + t] = inv;
+                const double c = s_cR[i * NZP + t];
+                prev = c * c * inv;
+            }
+            line_solve_local(r, q);
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                red[2] = fma(r[i], q[i], red[2]);
+                red[3] = fma(r[i], r[i], red[3]);
+                red[4] = fmax(red[4], a.criterion == 1 ? fabs(r[i] / s_dg[i * NZP + t]) : fabs(q[i]));
+            }
+        }
+        pipe_reduce<4, 1>(red, s_red, par);
+        const double res2 = red[0], b2 = red[1];
+        double rz = red[2], rr = red[3], crit = red[4];
+        int iters = 0, flags = 0;
+        bool done = false;
+        if (converged(a, crit, rr, b2)) { done = true; flags |= 1; }
+        else if (!isfinite(crit) || !isfinite(rz)) { done = true; flags |= 4; }
+#pragma unroll
+        for (int i = 0; i < NR; ++i) p[i] = q[i];
+        while (!done) {
+            // q = L p  (axial neighbours through shared memory), p.q
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < NR; ++i) if (act) s_x[i * NZP + t] = p[i];
+            __syncthreads();
+            double pq[1] = {0.0};
+            if (act) {
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    const double pn = t + 1 < nzm ? s_x[i * NZP + t + 1] : 0.0, ps = t > 0 ? s_x[i * NZP + t - 1] : 0.0;
+                    const double cS = t > 0 ? s_cZ[i * NZP + t - 1] : 0.0;
+                    double v = s_dg[i * NZP + t] * p[i];
+                    if (i + 1 < NR) v = fma(-s_cR[i * NZP + t], p[i + 1 < NR ? i + 1 : i], v);
+                    if (i > 0) v = fma(-s_cR[(i - 1) * NZP + t], p[i > 0 ? i - 1 : 0], v);
+                    v = fma(-s_cZ[i * NZP + t], pn, v);
+                    v = fma(-cS, ps, v);
+                    q[i] = v;
+                    pq[0] = fma(p[i], v, pq[0]);
+                }
+            }
+            pipe_reduce<1, 0>(pq, s_red, par);
+            if (!(pq[0] > 0.0) || !isfinite(pq[0])) { flags |= 4; break; }          // breakdown
+            const double alpha = rz / pq[0];
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                x[i] = fma(alpha, p[i], x[i]);
+                r[i] = fma(-alpha, q[i], r[i]);
+            }
+            double rd[3] = {0.0, 0.0, 0.0};                 // rz_new, rr | crit
+            if (act) {
+                line_solve_local(r, q);                      // q <- z
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    rd[0] = fma(r[i], q[i], rd[0]);
+                    rd[1] = fma(r[i], r[i], rd[1]);
+                    rd[2] = fmax(rd[2], a.criterion == 1 ? fabs(r[i] / s_dg[i * NZP + t]) : fabs(q[i]));
+                }
+            }
+            pipe_reduce<2, 1>(rd, s_red, par);
+            ++iters;
+            rr = rd[1]; crit = rd[2];
+            if (converged(a, crit, rr, b2)) { flags |= 1; break; }
+            if (!isfinite(crit) || !isfinite(rd[0])) { flags |= 4; break; }
+            if (iters >= a.max_iter) { flags |= 2; break; }
+            const double beta = rz != 0.0 ? rd[0] / rz : 0.0;
+            rz = rd[0];
+#pragma unroll
+            for (int i = 0; i < NR; ++i) p[i] = fma(beta, p[i], q[i]);
+        }
+        if (t == 0) {
+            double* o = part + ((size_t)s * M + m) * 4;
+            o[0] = res2; o[1] = b2; o[2] = (a.criterion == 2) ? sqrt(rr) : crit; o[3] = (double)(iters + (flags << 24));
+        }
+    }
+    if (act) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) d.T[rb + i] = x[i];
+    }
+}
+
+// member partials -> statistics ring and solver state (one CTA; fixed summation order)
+__global__ void __launch_bounds__(256) k_pipe_finalize(HpDev d, HpKArgs a, int M, int sweeps, const double* __restrict__ part) {
+    __shared__ double s_v[4][256];
+    HpState* st = d.st;
+    for (int s = 0; s < sweeps; ++s) {
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        int fl_and = 1, fl_or = 0, it = 0;
+        for (int m = threadIdx.x; m < M; m += 256) {
+            const double* o = part + ((size_t)s * M + m) * 4;
+            v[0] += o[0]; v[1] += o[1]; v[2] = fmax(v[2], o[2]);
+            const int packed = (int)o[3];
+            const int f = packed >> 24, i = packed & 0xffffff;
+            it = i > it ? i : it;
+            fl_and &= (f & 1); fl_or |= (f & 6);
+        }
+        v[3] = (double)(it + ((fl_and | fl_or | 8) << 24));      // bit3 marks "this thread saw members" for the AND below
+        if (threadIdx.x >= M) v[3] = -1.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_v[k][threadIdx.x] = v[k];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double res2 = 0.0, b2 = 0.0, crit = 0.0;
+            int iters = 0, all_conv = 1, bad = 0;
+            const int n = M < 256 ? M : 256;
+            for (int k = 0; k < n; ++k) {
+                res2 += s_v[0][k]; b2 += s_v[1][k]; crit = fmax(crit, s_v[2][k]);
+                const int packed = (int)s_v[3][k];
+                const int f = packed >> 24, i = packed & 0xffffff;
+                iters = i > iters ? i : iters;
+                all_conv &= (f & 1); bad |= (f & 6);
+            }
+            hp_sweep_stat* stt = &d.stats[st->sweep_count % HP_STATS_CAP];
+            stt->residual_l2 = sqrt(res2);
+            stt->rhs_l2 = sqrt(b2);
+            stt->crit = crit;
+            stt->iters = iters;
+            stt->flags = (all_conv && !bad ? 1 : 0) | bad;
+            st->sweep_count += 1;
+            st->total_iters += iters;
+            st->pipe_iters += iters;
+            st->res2 = res2; st->b2 = b2; st->crit = crit; st->iter = iters; st->flags = (st->flags & 8) | stt->flags;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { st->done = 1; st->mg_skip = 1; st->noop_ok = 0; }
+}
+
 // ------------------------------------------------------------------------------------------------
 // auxiliary kernels
 // ------------------------------------------------------------------------------------------------
@@ -1844,6 +2079,20 @@ HpKernelLaunch desc_cg_B(const HpLaunchCfg& c, const HpDev& d, int precond, int 
     if (chunks > HP_MAX_PARTIALS) chunks = HP_MAX_PARTIALS;
     return {f, dim3((unsigned)(chunks < 1 ? 1 : chunks)), dim3(256), smem};
 }
+
+// one pipe per CTA (nr == 9 rows of <= 512 lines); returns false when this row shape has no instantiation
+bool pipe_kernel_supported(int nr, int nzm) { return nr == 9 && nzm >= 1 && nzm <= 512; }
+HpKernelLaunch desc_pipe_step(int nr, int nzm, int members) {
+    const void* f = (const void*)k_pipe_step<9>;
+    const size_t smem = (size_t)6 * nr * nzm * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 9 * 512 * 8);
+        attr_set = true;
+    }
+    return {f, dim3((unsigned)members), dim3((unsigned)((nzm + 31) / 32 * 32)), smem};
+}
+HpKernelLaunch desc_pipe_finalize() { return {(const void*)k_pipe_finalize, dim3(1), dim3(256), 0}; }
 
 cudaError_t launch_eval_property(const hp_phys& ph, int id, const double* T, double* out, long long n, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;

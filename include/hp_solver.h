@@ -92,7 +92,9 @@ typedef struct hp_solve_opts {
     int32_t tma_rows;       /* 1: k_cg_B stages its operand rows in shared memory with bulk asynchronous copies (cp.async.bulk +
                                mbarrier, the next rows in flight during the scans of the current one) where the row shape allows
                                (512 < nr <= 1024, nr % 4 == 0); 0: register-direct 256-bit loads */
-    int32_t _pad;
+    int32_t pipe_kernel;    /* 1 (default): meshes made of small uncoupled pipes (9 radial cells, <= 512 rows each: the native
+                               Faghri mesh, ensembles of it) with precond = 1 run each pipe's whole time step in ONE CTA, on
+                               chip (every pipe its own PCG to `tol`); 0: always the row kernels */
 } hp_solve_opts;
 
 typedef struct hp_sweep_stat {

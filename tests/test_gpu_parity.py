@@ -440,6 +440,50 @@ def test_ensemble_of_64_members_with_radiation(cfg):
     assert np.ptp([r.max() for r in refs]) > 1.0
 
 
+@pytest.mark.parametrize('pipe_kernel', [True, False])
+def test_native_mesh_ensemble_pipe_kernel(cfg, pipe_kernel):
+    """BASELINE configs[4] on the reference's own mesh (500 x 9 per pipe): 12 members with their own q / h / T_amb, advanced
+    together (updateOld + 5 sweeps, main.py:267-271); every member against its own oracle run.  pipe_kernel=True is the
+    default route for this shape (one CTA per pipe, whole step on chip), False the stacked row-kernel route: same fields."""
+    M = 12
+    rng = np.random.default_rng(1234)
+    qs = cfg['parameters']['Q_input_flux'] * rng.uniform(0.5, 1.5, M)
+    hs = rng.uniform(2, 20, M)
+    Ts = rng.uniform(280, 300, M)
+    grid = fo.build_grid(dict(cfg['mesh']), cfg['dimensions'])
+    refs, res_ref = [], np.zeros(15)
+    for m in range(M):
+        case = fo.case_from_config(h=hs[m])
+        case.parameters['Q_input_flux'] = qs[m]
+        case.parameters['T_amb'] = Ts[m]
+        o = fo.Oracle(grid, case, has_old=True)
+        k = 0
+        for _ in range(3):
+            o.update_old()
+            for _ in range(5):
+                res_ref[k] += o.sweep(0.5, solver='banded') ** 2
+                k += 1
+        refs.append(o.T)
+    from heat_pipe_solver_b200.ensemble import EnsembleSolver
+    with EnsembleSolver(dict(cfg['mesh']), cfg['dimensions'], cfg['parameters'], cfg['constants'], q=qs, h=hs, T_amb=Ts,
+                        precond='rline', pipe_kernel=pipe_kernel) as ens:
+        ens.run(0.5, 3, sweeps=5, has_old=True)
+        T = ens.value()
+        stats = ens.stats(15)
+        launches = ens.solver.kernel_launches
+    assert all(st['converged'] and not st['breakdown'] for st in stats), stats
+    worst = max(float(np.max(np.abs(T[m] - refs[m]))) for m in range(M))
+    assert worst <= 15 * PER_STEP_TOL_K, worst
+    # FiPy's pre-solve residual of the stacked system = root of the members' squared residuals
+    got = np.array([st['residual_l2'] for st in stats])
+    big = np.sqrt(res_ref) > 1e-6
+    assert np.allclose(got[big], np.sqrt(res_ref)[big], rtol=1e-6)
+    if pipe_kernel:
+        assert launches <= 3 * 2 + 8            # two launches per step (+ the create-time kernels), not hundreds
+    else:
+        assert launches > 100
+
+
 def test_full_size_sweep_residual_property(cfg):
     """BASELINE configs[2] size (4096 x 1024): one sweep from a hot state; the oracle re-assembles the system on
     the host at the pre-sweep field and checks that the GPU's answer solves it (row-scaled residual in K)."""
