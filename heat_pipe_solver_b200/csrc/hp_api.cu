@@ -126,6 +126,8 @@ struct hp_solver_s {
     int pipe_nzm = 0, pipe_M = 0;
     double* pipe_part = nullptr;     // [sweeps][M][4] member partials of a step
     int pipe_part_sweeps = 0;
+    int pipe_hist = 0;               // 1: Told holds the start field of the step before the last completed one
+    double pipe_hist_dt = 0.0;
     // peer-memory exchange (hp_peer_export / hp_peer_import)
     HpComm* comm = nullptr;          // my mailbox
     double* qz_block = nullptr;      // base of the (q, z) allocation (IPC handle is per allocation)
@@ -507,7 +509,7 @@ int hp_set_T_dev(hp_handle h, const double* d_T) {
     if (!h || !d_T) return fail("hp_set_T_dev: null argument");
     CK(cudaMemcpyAsync(h->d.T + h->d.nr, d_T, owned_bytes(h), cudaMemcpyDeviceToDevice, h->stream));
     h->ghost_dirty = true;
-    h->hist = 0; h->c2_stashed = false;
+    h->hist = 0; h->c2_stashed = false; h->pipe_hist = 0;
     return invalidate_noop(h);
 }
 int hp_get_T_dev(hp_handle h, double* d_T) {
@@ -520,7 +522,7 @@ int hp_set_T_host(hp_handle h, const double* h_T) {
     if (!h || !h_T) return fail("hp_set_T_host: null argument");
     CK(cudaMemcpyAsync(h->d.T + h->d.nr, h_T, owned_bytes(h), cudaMemcpyHostToDevice, h->stream));
     h->ghost_dirty = true;
-    h->hist = 0; h->c2_stashed = false;
+    h->hist = 0; h->c2_stashed = false; h->pipe_hist = 0;
     return invalidate_noop(h);
 }
 int hp_get_T_host(hp_handle h, double* h_T) {
@@ -932,17 +934,23 @@ static int run_steps(hp_solver_s* h, double dt, int n_steps, int sweeps, int has
             h->pipe_part_sweeps = sweeps;
         }
         HpKArgs a = make_args(h, dt, has_old);
-        int nzm = h->pipe_nzm, M = h->pipe_M, sw = sweeps, upd = (is_step && has_old) ? 1 : 0;
+        // whole steps keep Told = field at the step start (like the row-kernel path with `extrapolate`), so the next step
+        // can start its first solve from T + (T - Told): linear prediction, when the previous step used the same dt
+        int nzm = h->pipe_nzm, M = h->pipe_M, sw = sweeps, upd = is_step ? 1 : 0;
+        if (is_step && !has_old) a.has_old = 0;      // hasOld=False: the transient term uses the iterate, Told is history only
         double* part = h->pipe_part;
         const HpKernelLaunch ks = hpk::desc_pipe_step(d.nr, nzm, M), kf = hpk::desc_pipe_finalize();
+        if (h->pipe_hist_dt != dt) h->pipe_hist = 0;
         for (int s = 0; s < n_steps; ++s) {
-            void* p1[] = {&d, &h->phys, &a, &nzm, &sw, &upd, &part};
+            int predict = (is_step && h->opts.extrapolate >= 1 && h->pipe_hist >= 1) ? 1 : 0;
+            void* p1[] = {&d, &h->phys, &a, &nzm, &sw, &upd, &predict, &part};
             if (launch(h, ks, p1)) return -1;
             void* p2[] = {&d, &a, &M, &sw, &part};
             if (launch(h, kf, p2)) return -1;
             h->sweeps_host += sweeps;
+            if (is_step) { h->pipe_hist = 1; h->pipe_hist_dt = dt; } else h->pipe_hist = 0;
         }
-        h->hist = 0; h->c2_stashed = false;          // the predicted-start history of the row-kernel path is not maintained here
+        h->hist = 0; h->c2_stashed = false;          // the higher-order history of the row-kernel path is not maintained here
         return 0;
     }
     const int max_order = is_step ? (h->opts.extrapolate > 3 ? 3 : h->opts.extrapolate) : 0;
@@ -1034,10 +1042,10 @@ int hp_run_host(hp_handle h, const double* h_T_in, double* h_T_out, double dt, i
     if (!h || !h_T_in || !h_T_out) return fail("hp_run_host: null argument");
     // the uploaded field continues the transient: the previous step start kept in Told stays the history of the
     // extrapolated PCG start (it only seeds the solver; a stale history costs iterations, never accuracy)
-    const int keep = h->hist;
+    const int keep = h->hist, keep_pipe = h->pipe_hist;
     const bool keep_c2 = h->c2_stashed;
     if (hp_set_T_host(h, h_T_in)) return -1;
-    h->hist = keep; h->c2_stashed = keep_c2;
+    h->hist = keep; h->c2_stashed = keep_c2; h->pipe_hist = keep_pipe;
     if (hp_run(h, dt, n_steps, sweeps, has_old)) return -1;
     return hp_get_T_host(h, h_T_out);
 }

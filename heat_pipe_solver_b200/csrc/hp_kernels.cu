@@ -1059,7 +1059,7 @@ __device__ __forceinline__ void pipe_reduce(double (&v)[NS + NM], double (*s_red
 
 template <int NR>
 __global__ void __launch_bounds__(512, 1) k_pipe_step(HpDev d, hp_phys ph, HpKArgs a, int nzm, int sweeps, int update_old,
-                                                     double* __restrict__ part) {
+                                                     int predict, double* __restrict__ part) {
     extern __shared__ __align__(16) double pipe_sm[];
     __shared__ double s_red[2][5][16];
     const int NZP = nzm;
@@ -1084,7 +1084,11 @@ __global__ void __launch_bounds__(512, 1) k_pipe_step(HpDev d, hp_phys ph, HpKAr
         if (act) {
             s_cR[i * NZP + t] = d.cR[rb + i];
             s_cZ[i * NZP + t] = d.cZ[rb + i];
-            const double to = update_old ? x[i] : d.Told[rb + i];
+            const double told = d.Told[rb + i];
+            // predict: Told still holds the field at the start of the PREVIOUS step, so x - Told is that step's increment:
+            // the first solve of this step starts from x + (x - Told) (the system is still assembled at x)
+            if (predict) p[i] = x[i] - told;
+            const double to = update_old ? x[i] : told;
             s_To[i * NZP + t] = to;
             if (update_old) d.Told[rb + i] = to;            // T.updateOld() (main.py:269), kept visible to the other entry points
         }
@@ -1133,23 +1137,33 @@ __global__ void __launch_bounds__(512, 1) k_pipe_step(HpDev d, hp_phys ph, HpKAr
                 const double c = s_cR[i * NZP + t];
                 prev = c * c * inv;
             }
-            line_solve_local(r, q);
-#pragma unroll
-            for (int i = 0; i < NR; ++i) {
-                red[2] = fma(r[i], q[i], red[2]);
-                red[3] = fma(r[i], r[i], red[3]);
-                red[4] = fmax(red[4], a.criterion == 1 ? fabs(r[i] / s_dg[i * NZP + t]) : fabs(q[i]));
-            }
         }
-        pipe_reduce<4, 1>(red, s_red, par);
-        const double res2 = red[0], b2 = red[1];
-        double rz = red[2], rr = red[3], crit = red[4];
+        // predicted start (first sweep of a step): p already holds delta = last step's increment; the first pass of the loop
+        // below then runs with alpha := 1 (x <- x + delta, r <- r0 - L delta) and ends like this INIT decision
+        bool shift = predict && s == 0;
+        double rz = 0.0, rr = 0.0, crit = 0.0;
         int iters = 0, flags = 0;
         bool done = false;
-        if (converged(a, crit, rr, b2)) { done = true; flags |= 1; }
-        else if (!isfinite(crit) || !isfinite(rz)) { done = true; flags |= 4; }
+        if (!shift) {
+            if (act) {
+                line_solve_local(r, q);
 #pragma unroll
-        for (int i = 0; i < NR; ++i) p[i] = q[i];
+                for (int i = 0; i < NR; ++i) {
+                    red[2] = fma(r[i], q[i], red[2]);
+                    red[3] = fma(r[i], r[i], red[3]);
+                    red[4] = fmax(red[4], a.criterion == 1 ? fabs(r[i] / s_dg[i * NZP + t]) : fabs(q[i]));
+                }
+            }
+            pipe_reduce<4, 1>(red, s_red, par);
+            rz = red[2]; rr = red[3]; crit = red[4];
+            if (converged(a, crit, rr, red[1])) { done = true; flags |= 1; }
+            else if (!isfinite(crit) || !isfinite(rz)) { done = true; flags |= 4; }
+#pragma unroll
+            for (int i = 0; i < NR; ++i) p[i] = q[i];
+        } else {
+            pipe_reduce<4, 1>(red, s_red, par);
+        }
+        const double res2 = red[0], b2 = red[1];
         while (!done) {
             // q = L p  (axial neighbours through shared memory), p.q
             __syncthreads();
@@ -1171,9 +1185,12 @@ __global__ void __launch_bounds__(512, 1) k_pipe_step(HpDev d, hp_phys ph, HpKAr
                     pq[0] = fma(p[i], v, pq[0]);
                 }
             }
-            pipe_reduce<1, 0>(pq, s_red, par);
-            if (!(pq[0] > 0.0) || !isfinite(pq[0])) { flags |= 4; break; }          // breakdown
-            const double alpha = rz / pq[0];
+            double alpha = 1.0;
+            if (!shift) {
+                pipe_reduce<1, 0>(pq, s_red, par);
+                if (!(pq[0] > 0.0) || !isfinite(pq[0])) { flags |= 4; break; }      // breakdown
+                alpha = rz / pq[0];
+            }
 #pragma unroll
             for (int i = 0; i < NR; ++i) {
                 x[i] = fma(alpha, p[i], x[i]);
@@ -1190,13 +1207,14 @@ __global__ void __launch_bounds__(512, 1) k_pipe_step(HpDev d, hp_phys ph, HpKAr
                 }
             }
             pipe_reduce<2, 1>(rd, s_red, par);
-            ++iters;
             rr = rd[1]; crit = rd[2];
+            if (!shift) ++iters;
             if (converged(a, crit, rr, b2)) { flags |= 1; break; }
             if (!isfinite(crit) || !isfinite(rd[0])) { flags |= 4; break; }
             if (iters >= a.max_iter) { flags |= 2; break; }
-            const double beta = rz != 0.0 ? rd[0] / rz : 0.0;
+            const double beta = (!shift && rz != 0.0) ? rd[0] / rz : 0.0;     // after the shift pass the direction restarts: p = z
             rz = rd[0];
+            shift = false;
 #pragma unroll
             for (int i = 0; i < NR; ++i) p[i] = fma(beta, p[i], q[i]);
         }
