@@ -484,6 +484,26 @@ def test_native_mesh_ensemble_pipe_kernel(cfg, pipe_kernel):
         assert launches > 100
 
 
+def test_options_in_force_and_fault_api(cfg):
+    """hp_get_opts reports what the library actually runs ('mgline' falls back to 'rline' on a mesh too short to coarsen);
+    the peer-fault entry points are callable on a single-GPU handle (no fault, clearing is a no-op that keeps the field)."""
+    s, o = make_pair(cfg, SHAPES['s24x1000'], T0=hot_field, solver_kw=dict(precond='mgline'))
+    with s:
+        assert s.effective_precond == 'rline'                 # 24 rows: nothing to coarsen
+        s.sweep(0.1)
+        before = s.value.copy()
+        assert not s.peer_fault
+        s.clear_peer_fault()
+        assert not s.peer_fault and np.array_equal(s.value, before)
+        s.sweep(0.1)
+        assert s.stats(1)[0]['converged']
+    s2, _ = make_pair(cfg, SHAPES['s128x256'], solver_kw=dict(precond='mgline'))
+    with s2:
+        assert s2.effective_precond == 'mgline'
+    with pytest.raises(Exception):
+        make_pair(cfg, SHAPES['s64x32'], solver_kw=dict(precond='nonsense'))
+
+
 def test_full_size_sweep_residual_property(cfg):
     """BASELINE configs[2] size (4096 x 1024): one sweep from a hot state; the oracle re-assembles the system on
     the host at the pre-sweep field and checks that the GPU's answer solves it (row-scaled residual in K)."""

@@ -211,3 +211,22 @@ def test_long_golden_matches_the_reference_plot_readoffs_and_the_oracle():
     assert np.max(np.abs(mod.run_case(short)['T_1000'] - simple['T_1000'])) <= 1e-9
     # constant properties conserve energy exactly: monotone heating, bounded by the input
     assert np.all(np.diff(simple['wall'][:, 0]) > 0)
+
+
+def test_row_block_threads_are_bit_identical(cfg):
+    """oracle.set_threads(n): matvec / line solves / property evaluation on row blocks in a thread pool -- the same numbers
+    as the serial path (every block evaluates the serial expression on whole rows)."""
+    grid = fo.build_grid(fo.synthetic_mesh_params(384, 8, 16, 40), cfg['dimensions'])
+    z = grid.z_c[:, None] / grid.z_v[-1]
+    T0 = 290.0 + 300.0 * np.exp(-((z - 0.1) / 0.35) ** 2) * np.ones((1, grid.nr))
+    got = {}
+    try:
+        for n in (1, 3):
+            fo.set_threads(n)
+            o = fo.Oracle(grid, fo.case_from_config(), T0=T0, has_old=True)
+            o.update_old()
+            res = [o.sweep(0.1, solver='pcg_mgline', tol=1e-9) for _ in range(2)]
+            got[n] = (o.T.copy(), res, o.last_solver_info['iterations'])
+    finally:
+        fo.set_threads(1)
+    assert np.array_equal(got[1][0], got[3][0]) and got[1][1] == got[3][1] and got[1][2] == got[3][2]
