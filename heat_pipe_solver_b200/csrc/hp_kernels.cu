@@ -1522,10 +1522,8 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpKArgs& a, co
         double xc_l = 0.0, xc_r = 0.0;
         xrow(ja, xm);
         xrow(ja + 1, xc);
-        if constexpr (MODE != 2) {
-            if (has_l) xc_l = xat(ja + 1, i0 - 1);
-            if (has_r) xc_r = xat(ja + 1, i0 + EPT);
-        }
+        if (has_l) xc_l = xat(ja + 1, i0 - 1);
+        if (has_r) xc_r = xat(ja + 1, i0 + EPT);
         load_row<EPT, VEC>(L.cZ + (long long)ja * nr, i0, nr, czm);
         if (ja == 0) {
             if (d.mg_local) {
@@ -1538,15 +1536,12 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpKArgs& a, co
         for (int k = 0; k < EPT; ++k) rprev[k] = 0.0;
         for (int g = ja + 1; g <= jb; ++g) {
             const long long rb = (long long)g * nr;
-            [[maybe_unused]] double cr[EPT], dg[EPT];
-            double cz[EPT], rh[EPT];
+            double cr[EPT], cz[EPT], dg[EPT], rh[EPT];
             [[maybe_unused]] double dv[EPT];
             xrow(g + 1, xn);
-            if constexpr (MODE != 2) {
-                load_row<EPT, VEC>(L.cR + rb, i0, nr, cr);
-                load_row<EPT, VEC>(L.diag + rb, i0, nr, dg);
-            }
+            load_row<EPT, VEC>(L.cR + rb, i0, nr, cr);
             load_row<EPT, VEC>(L.cZ + rb, i0, nr, cz);
+            load_row<EPT, VEC>(L.diag + rb, i0, nr, dg);
             load_row<EPT, VEC>(L.rhs + rb, i0, nr, rh);
             [[maybe_unused]] double m0_edge = 0.0;
             if constexpr (MODE == 1) {
@@ -1564,11 +1559,9 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpKArgs& a, co
                     if (lane == 0 && tl != 0 && i0 < nr) m0_edge = m.c_cR[cb + i0 - 1] * m.c_dinv[cb + i0 - 1];
                 }
             }
-            [[maybe_unused]] double xn_l = 0.0, xn_r = 0.0, crl_e = 0.0;
-            if constexpr (MODE != 2) {
-                if (has_l) { xn_l = xat(g + 1, i0 - 1); crl_e = L.cR[rb + i0 - 1]; }
-                if (has_r) xn_r = xat(g + 1, i0 + EPT);
-            }
+            double xn_l = 0.0, xn_r = 0.0, crl_e = 0.0;
+            if (has_l) { xn_l = xat(g + 1, i0 - 1); crl_e = L.cR[rb + i0 - 1]; }
+            if (has_r) xn_r = xat(g + 1, i0 + EPT);
             if (g == nz) {
                 if (d.mg_local) {
 #pragma unroll
@@ -1576,33 +1569,25 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpKArgs& a, co
                 }
                 if (m.xout_ghost) store_row<EPT, VEC>(m.xout + rb + nr, i0, nr, xn);
             }
+            const unsigned tm = team_mask<TPL>();
+            constexpr int W = TeamGeom<TPL>::W;
+            double xl = __shfl_up_sync(tm, xc[EPT - 1], 1, W);
+            double crl = __shfl_up_sync(tm, cr[EPT - 1], 1, W);
+            double xr = __shfl_down_sync(tm, xc[0], 1, W);
+            if (lane == 0) { xl = xc_l; crl = crl_e; }
+            if (lane == W - 1) xr = xc_r;
             double res[EPT];
-            if constexpr (MODE == 2) {
-                // Down leg: the iterate is x = omega M^-1 rhs exactly (pre-smoothing from zero; level 0: omega z_line), and
-                // L = M - N with N the axial couplings, so  rhs - L x = (1 - omega) rhs + N x : no diagonal, no radial
-                // couplings, no radial neighbours -- two operand rows and the edge loads / shuffles less per row
 #pragma unroll
-                for (int k = 0; k < EPT; ++k) res[k] = fma(cz[k], xn[k], fma(czm[k], xm[k], (1.0 - omega) * rh[k]));
-            } else {
-                const unsigned tm = team_mask<TPL>();
-                constexpr int W = TeamGeom<TPL>::W;
-                double xl = __shfl_up_sync(tm, xc[EPT - 1], 1, W);
-                double crl = __shfl_up_sync(tm, cr[EPT - 1], 1, W);
-                double xr = __shfl_down_sync(tm, xc[0], 1, W);
-                if (lane == 0) { xl = xc_l; crl = crl_e; }
-                if (lane == W - 1) xr = xc_r;
-#pragma unroll
-                for (int k = 0; k < EPT; ++k) {
-                    const double left = (k == 0) ? xl : xc[k - 1];
-                    const double cleft = (k == 0) ? crl : cr[k - 1];
-                    const double right = (k == EPT - 1) ? xr : xc[(k + 1) % EPT];
-                    double t = dg[k] * xc[k];
-                    t = fma(-cr[k], right, t);
-                    t = fma(-cleft, left, t);
-                    t = fma(-cz[k], xn[k], t);
-                    t = fma(-czm[k], xm[k], t);
-                    res[k] = rh[k] - t;
-                }
+            for (int k = 0; k < EPT; ++k) {
+                const double left = (k == 0) ? xl : xc[k - 1];
+                const double cleft = (k == 0) ? crl : cr[k - 1];
+                const double right = (k == EPT - 1) ? xr : xc[(k + 1) % EPT];
+                double t = dg[k] * xc[k];
+                t = fma(-cr[k], right, t);
+                t = fma(-cleft, left, t);
+                t = fma(-cz[k], xn[k], t);
+                t = fma(-czm[k], xm[k], t);
+                res[k] = rh[k] - t;
             }
             if constexpr (MODE == 1) {
                 double zv[EPT];
@@ -1655,7 +1640,7 @@ k_mg_res(HpDev d, HpKArgs a, HpLevel L, HpMgResArgs m) {
 // ---- k_mg_up : prolong + residual + post-smoothing of one coarse level in ONE pass (one stage instead of two in the
 // latency-bound coarse part of the cycle):  xout = xt + omega M_L^-1 (rhs - L xt),  xt = xin + P ec
 template <int TPL, int EPT, bool VEC, int MODE>
-__global__ void __launch_bounds__(TeamGeom<TPL>::CTA, (MODE == 2 && TPL == 256) ? 3 : TeamGeom<TPL>::minb_A(EPT))
+__global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_A(EPT))
 k_mg_fused(HpDev d, HpKArgs a, HpLevel L, HpMgResArgs m) {
     using G = TeamGeom<TPL>;
     if (d.st->mg_skip) return;
