@@ -941,14 +941,23 @@ static int run_steps(hp_solver_s* h, double dt, int n_steps, int sweeps, int has
         double* part = h->pipe_part;
         const HpKernelLaunch ks = hpk::desc_pipe_step(d.nr, nzm, M), kf = hpk::desc_pipe_finalize();
         if (h->pipe_hist_dt != dt) h->pipe_hist = 0;
+        if (is_step && h->opts.extrapolate >= 2 && !d.d1) {
+            const size_t bytes = h->field_elems * sizeof(double);
+            if (dev_alloc(h, (void**)&d.d1, bytes) || dev_alloc(h, (void**)&d.d2, bytes)) return -1;
+            CK(cudaMemsetAsync(d.d1, 0, bytes, h->stream));
+            CK(cudaMemsetAsync(d.d2, 0, bytes, h->stream));
+        }
         for (int s = 0; s < n_steps; ++s) {
+            // order of the predicted start: linear once one step of history exists (Told), quadratic once the increment of
+            // the step before has been stored too (d1, written by every predicting step)
             int predict = (is_step && h->opts.extrapolate >= 1 && h->pipe_hist >= 1) ? 1 : 0;
+            if (predict && h->opts.extrapolate >= 2 && h->pipe_hist >= 3 && d.d1) predict = 2;
             void* p1[] = {&d, &h->phys, &a, &nzm, &sw, &upd, &predict, &part};
             if (launch(h, ks, p1)) return -1;
             void* p2[] = {&d, &a, &M, &sw, &part};
             if (launch(h, kf, p2)) return -1;
             h->sweeps_host += sweeps;
-            if (is_step) { h->pipe_hist = 1; h->pipe_hist_dt = dt; } else h->pipe_hist = 0;
+            if (is_step) { if (h->pipe_hist < 3) h->pipe_hist++; h->pipe_hist_dt = dt; } else h->pipe_hist = 0;
         }
         h->hist = 0; h->c2_stashed = false;          // the higher-order history of the row-kernel path is not maintained here
         return 0;

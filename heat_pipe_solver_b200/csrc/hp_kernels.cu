@@ -1085,9 +1085,14 @@ __global__ void __launch_bounds__(512, 1) k_pipe_step(HpDev d, hp_phys ph, HpKAr
             s_cR[i * NZP + t] = d.cR[rb + i];
             s_cZ[i * NZP + t] = d.cZ[rb + i];
             const double told = d.Told[rb + i];
-            // predict: Told still holds the field at the start of the PREVIOUS step, so x - Told is that step's increment:
-            // the first solve of this step starts from x + (x - Told) (the system is still assembled at x)
-            if (predict) p[i] = x[i] - told;
+            // predict >= 1: Told still holds the field at the start of the PREVIOUS step, so x - Told is that step's
+            // increment D: the first solve of this step starts from x + D (the system is still assembled at x);
+            // predict == 2: d1 holds the increment of the step before, start from x + 2 D - d1 (quadratic in the step index)
+            if (predict) {
+                const double inc = x[i] - told;
+                p[i] = (predict >= 2) ? 2.0 * inc - d.d1[rb + i] : inc;
+                if (d.d1) d.d1[rb + i] = inc;
+            }
             const double to = update_old ? x[i] : told;
             s_To[i * NZP + t] = to;
             if (update_old) d.Told[rb + i] = to;            // T.updateOld() (main.py:269), kept visible to the other entry points
