@@ -126,7 +126,8 @@ struct hp_solver_s {
     int pipe_nzm = 0, pipe_M = 0;
     double* pipe_part = nullptr;     // [sweeps][M][4] member partials of a step
     int pipe_part_sweeps = 0;
-    int pipe_hist = 0;               // 1: Told holds the start field of the step before the last completed one
+    int pipe_hist = 0;               // completed steps of history (Told = start field of the last step, d1 = increment before)
+    bool pipe_c2_valid = false;      // d.c2 holds the re-sweep correction of the last completed step
     double pipe_hist_dt = 0.0;
     // peer-memory exchange (hp_peer_export / hp_peer_import)
     HpComm* comm = nullptr;          // my mailbox
@@ -940,8 +941,14 @@ static int run_steps(hp_solver_s* h, double dt, int n_steps, int sweeps, int has
         if (is_step && !has_old) a.has_old = 0;      // hasOld=False: the transient term uses the iterate, Told is history only
         double* part = h->pipe_part;
         const HpKernelLaunch ks = hpk::desc_pipe_step(d.nr, nzm, M), kf = hpk::desc_pipe_finalize();
-        if (h->pipe_hist_dt != dt) h->pipe_hist = 0;
-        if (is_step && h->opts.extrapolate >= 2 && !d.d1) {
+        if (h->pipe_hist_dt != dt) { h->pipe_hist = 0; h->pipe_c2_valid = false; }
+        if (h->pipe_hist == 0) h->pipe_c2_valid = false;
+        if (is_step && sweeps >= 2 && h->opts.extrapolate >= 1 && !d.c2) {
+            const size_t bytes = h->field_elems * sizeof(double);
+            if (dev_alloc(h, (void**)&d.c2, bytes)) return -1;
+            CK(cudaMemsetAsync(d.c2, 0, bytes, h->stream));
+        }
+        if (is_step && h->opts.extrapolate >= 1 && !d.d1) {
             const size_t bytes = h->field_elems * sizeof(double);
             if (dev_alloc(h, (void**)&d.d1, bytes) || dev_alloc(h, (void**)&d.d2, bytes)) return -1;
             CK(cudaMemsetAsync(d.d1, 0, bytes, h->stream));
@@ -952,12 +959,16 @@ static int run_steps(hp_solver_s* h, double dt, int n_steps, int sweeps, int has
             // the step before has been stored too (d1, written by every predicting step)
             int predict = (is_step && h->opts.extrapolate >= 1 && h->pipe_hist >= 1) ? 1 : 0;
             if (predict && h->opts.extrapolate >= 2 && h->pipe_hist >= 3 && d.d1) predict = 2;
-            void* p1[] = {&d, &h->phys, &a, &nzm, &sw, &upd, &predict, &part};
+            // re-sweep correction (second-sweep start): bit0 keep S1 / form C this step, bit1 C of the previous step is valid
+            int track = (is_step && sweeps >= 2 && h->opts.extrapolate >= 1 && d.c2 && d.d2) ? 1 : 0;
+            if (track && h->pipe_c2_valid) track |= 2;
+            void* p1[] = {&d, &h->phys, &a, &nzm, &sw, &upd, &predict, &track, &part};
             if (launch(h, ks, p1)) return -1;
             void* p2[] = {&d, &a, &M, &sw, &part};
             if (launch(h, kf, p2)) return -1;
             h->sweeps_host += sweeps;
             if (is_step) { if (h->pipe_hist < 3) h->pipe_hist++; h->pipe_hist_dt = dt; } else h->pipe_hist = 0;
+            h->pipe_c2_valid = (track & 1) != 0;
         }
         h->hist = 0; h->c2_stashed = false;          // the higher-order history of the row-kernel path is not maintained here
         return 0;

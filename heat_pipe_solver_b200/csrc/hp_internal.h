@@ -184,7 +184,7 @@ HpKernelLaunch desc_wait();       // args: (HpDev, hp_phys, HpKArgs, int kind): 
 HpKernelLaunch desc_finalize();   // args: (HpDev, hp_phys, HpKArgs, int kind) kind: 0 diag, 1 A, 2 B, 3 init
 HpKernelLaunch desc_cg_B(const HpLaunchCfg&, const HpDev&, int precond, int criterion, int tma);
 bool cg_B_tma_supported(const HpLaunchCfg&, int precond, int criterion);
-// persistent one-pipe-per-CTA step: args (HpDev, hp_phys, HpKArgs, int nzm, int sweeps, int update_old, int predict, double* part)
+// persistent one-pipe-per-CTA step: args (HpDev, hp_phys, HpKArgs, int nzm, int sweeps, int update_old, int predict, int track, double* part)
 bool pipe_kernel_supported(int nr, int nzm);
 HpKernelLaunch desc_pipe_step(int nr, int nzm, int members);
 HpKernelLaunch desc_pipe_finalize();                 // args (HpDev, HpKArgs, int M, int sweeps, const double* part)

@@ -1059,7 +1059,7 @@ __device__ __forceinline__ void pipe_reduce(double (&v)[NS + NM], double (*s_red
 
 template <int NR>
 __global__ void __launch_bounds__(512, 1) k_pipe_step(HpDev d, hp_phys ph, HpKArgs a, int nzm, int sweeps, int update_old,
-                                                     int predict, double* __restrict__ part) {
+                                                     int predict, int track, double* __restrict__ part) {
     extern __shared__ __align__(16) double pipe_sm[];
     __shared__ double s_red[2][5][16];
     const int NZP = nzm;
@@ -1145,7 +1145,13 @@ __global__ void __launch_bounds__(512, 1) k_pipe_step(HpDev d, hp_phys ph, HpKAr
         }
         // predicted start (first sweep of a step): p already holds delta = last step's increment; the first pass of the loop
         // below then runs with alpha := 1 (x <- x + delta, r <- r0 - L delta) and ends like this INIT decision
-        bool shift = predict && s == 0;
+        // Second sweep of a step (track bit1): the first solve of a step stops short of the step's final field by the
+        // correction the re-sweeps add (property update, smooth in time); start from x + C of the PREVIOUS step (c2).
+        if (s == 1 && (track & 2) && act) {
+#pragma unroll
+            for (int i = 0; i < NR; ++i) p[i] = d.c2[rb + i];
+        }
+        bool shift = (predict && s == 0) || (s == 1 && (track & 2));
         double rz = 0.0, rr = 0.0, crit = 0.0;
         int iters = 0, flags = 0;
         bool done = false;
@@ -1223,6 +1229,10 @@ __global__ void __launch_bounds__(512, 1) k_pipe_step(HpDev d, hp_phys ph, HpKAr
 #pragma unroll
             for (int i = 0; i < NR; ++i) p[i] = fma(beta, p[i], q[i]);
         }
+        if (s == 0 && (track & 1) && act) {                 // first-sweep solution, kept for the correction formed at the end
+#pragma unroll
+            for (int i = 0; i < NR; ++i) d.d2[rb + i] = x[i];
+        }
         if (t == 0) {
             double* o = part + ((size_t)s * M + m) * 4;
             o[0] = res2; o[1] = b2; o[2] = (a.criterion == 2) ? sqrt(rr) : crit; o[3] = (double)(iters + (flags << 24));
@@ -1231,6 +1241,10 @@ __global__ void __launch_bounds__(512, 1) k_pipe_step(HpDev d, hp_phys ph, HpKAr
     if (act) {
 #pragma unroll
         for (int i = 0; i < NR; ++i) d.T[rb + i] = x[i];
+        if ((track & 1) && sweeps >= 2) {
+#pragma unroll
+            for (int i = 0; i < NR; ++i) d.c2[rb + i] = x[i] - d.d2[rb + i];
+        }
     }
 }
 
