@@ -161,7 +161,7 @@ int hp_eval_cell_fields(hp_handle h, double* d_rho, double* d_cp, double* d_kavg
 /* per-kernel device times by CUDA events (bench.py roofline).  Between begin and end every sweep runs in
  * stream-launch mode with an event pair around each kernel launch (at most max_launches are recorded).
  * kinds: 0 other, 1 coef, 2 diag, 3 factor, 4 cg_init, 5 cg_A, 6 cg_B, 7 mg_res (fine level), 8 mg_line (fine level),
- * 9 mg kernels of the replicated (multi-GPU) coarse levels, 10 mg setup (coarsening + coarse pivots),
+ * 9 (unused since the distributed hierarchy replaced the replicated coarse levels), 10 mg setup (coarsening + coarse pivots),
  * 11..15 mg kernels of local coarse level 1..5 (15 = level 5 and deeper) */
 typedef struct hp_kernel_times {
     int64_t count[16];          /* every launch of the kind */
