@@ -152,3 +152,51 @@ def test_aligned_slab_cuts_and_global_precond_resolution():
     assert resolve_precond('jacobi', 4096, 1024, 8, 'p2p') == 'jacobi'
     with pytest.raises(ValueError):
         slab_rows(64, 0, 9, 8)
+
+
+def _coarsen_slab(cR, cZ, dg, cZ_below, zs):
+    """numpy mirror of k_mg_coarsen on one slab: cZ[j] couples row j to row j+1 (the last row's entry is the coupling to
+    the slab above, 0 at the physical top); cZ_below couples the first row to the slab below."""
+    nz = dg.shape[0]
+    nzc = (nz + 1) // 2
+    cRc, cZc, dgc = np.zeros((nzc,) + cR.shape[1:]), np.zeros((nzc,) + cR.shape[1:]), np.zeros((nzc,) + cR.shape[1:])
+    for J in range(nzc):
+        g0, two = 2 * J, 2 * J + 1 < nz
+        inner = cZ[g0] if two else 0.0
+        up = cZ[g0 + 1] if two else cZ[g0]
+        dn = cZ[g0 - 1] if g0 > 0 else cZ_below
+        cRc[J] = cR[g0] + (cR[g0 + 1] if two else 0.0)
+        cZc[J] = zs * up
+        dgc[J] = dg[g0] + ((dg[g0 + 1] - 2.0 * inner) if two else 0.0) - (1.0 - zs) * (up + dn)
+    return cRc, cZc, dgc, zs * cZ_below
+
+
+@pytest.mark.parametrize('nz,world', [(256, 2), (512, 4), (1000, 3), (96, 4)])
+def test_distributed_hierarchy_equals_the_single_domain_one(cfg, nz, world):
+    """With the slab cuts aligned to 2^(levels-1) rows (distributed.slab_alignment) every coarse coefficient of the V-cycle
+    is a function of the slab's own rows: coarsening slab by slab -- what every rank's k_mg_coarsen does, no communication --
+    gives exactly the rows of the whole-mesh hierarchy (the oracle's), level after level."""
+    from heat_pipe_solver_b200.distributed import mg_level_count, slab_alignment, slab_rows
+    from oracle import fv_oracle as fo
+    grid = fo.build_grid(fo.synthetic_mesh_params(nz, 4, 8, 20), cfg['dimensions'])
+    z = grid.z_c[:, None] / grid.z_v[-1]
+    T0 = 290.0 + 300.0 * np.exp(-((z - 0.1) / 0.35) ** 2) * np.ones((1, grid.nr))
+    S = fo.Oracle(grid, fo.case_from_config(), T0=T0).assemble(0.1)
+    align = slab_alignment(nz, world)
+    levels = 1 + int(np.log2(align))
+    assert levels <= mg_level_count(nz)
+    ref = fo.mg_hierarchy(S, max_levels=levels, zscale=0.5)
+    assert len(ref) == levels
+    cuts = [slab_rows(nz, r, world, align) for r in range(world)]
+    slabs = []
+    for (a, b) in cuts:
+        below = S.cZ[a - 1] if a > 0 else np.zeros(grid.nr)
+        slabs.append((S.cR[a:b].copy(), S.cZ[a:b].copy(), S.diag[a:b].copy(), below))
+    for l in range(1, levels):
+        slabs = [_coarsen_slab(cR, cZ, dg, below, 0.5) for cR, cZ, dg, below in slabs]
+        for name, k in (('cR', 0), ('cZ', 1), ('diag', 2)):
+            got = np.concatenate([s[k] for s in slabs], axis=0)
+            want = getattr(ref[l].S, name)
+            assert got.shape == want.shape, (l, name)
+            scale = np.abs(want).max()
+            assert np.max(np.abs(got - want)) <= 1e-13 * scale, (l, name)
