@@ -511,8 +511,8 @@ def main():
     ap.add_argument('--scaling-ref', action='store_true',
                     help='N=1: also time the 16384x4096 multi-GPU workload on this one GPU (extra key multi_gpu_workload_on_one_gpu)')
     ap.add_argument('--no-single-gpu-ref', action='store_true', help='N>1: skip the one-GPU run of the same workload (strong-scaling denominator)')
-    ap.add_argument('--precond', default='mgline', choices=['rline', 'mgline', 'jacobi'],
-                    help='PCG preconditioner: mgline (V-cycle over radial-line smoothing, default), rline (the radial-line '
+    ap.add_argument('--precond', default=None, choices=['rline', 'mgline', 'jacobi'],
+                    help='PCG preconditioner: mgline (V-cycle over radial-line smoothing, default for meshes), rline (the radial-line '
                          'tridiagonal preconditioner alone), jacobi')
     ap.add_argument('--refactor-every', type=int, default=SWEEPS,
                     help='re-factor the line pivots / coarse operators every k-th sweep of a step (default: once per step; '
@@ -524,6 +524,8 @@ def main():
                     help='sweeps that exactly repeat a converged sweep only redo the bookkeeping (off: every sweep assembles, like the reference)')
     ap.add_argument('--comm', default='p2p', choices=['p2p', 'nccl'], help='slab exchange: NVLink peer stores fused into the kernels, or NCCL calls')
     args = ap.parse_args()
+    if args.precond is None:        # meshes: multigrid over lines; ensembles of small pipes: the line preconditioner (-> k_pipe_step)
+        args.precond = 'rline' if (args.workload or '').startswith('ensemble') else 'mgline'
     guard_stdout()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
