@@ -26,6 +26,7 @@ SHAPES = {
     's16x4096': (16, 512, 1024, 2560),   # nr = 4096 (TPL 512, EPT 8)
     's64x4096': (64, 512, 1024, 2560),   # nr = 4096, 3 mgline levels: the cluster-team fused stages (4 CTAs per row)
     's64x2048': (64, 256, 512, 1280),    # nr = 2048: cluster teams of 2 CTAs
+    's64x2050': (64, 250, 520, 1280),    # nr = 2050: cluster teams of 4 CTAs with scalar (ragged) loads
     's64x4100': (64, 500, 1000, 2600),   # nr = 4100 (TPL 1024, EPT 8, scalar loads): V-cycle as separate residual / line-solve launches
 }
 
@@ -137,7 +138,7 @@ def test_solver_options_agree(cfg, opts):
         assert err <= 3 * PER_STEP_TOL_K
 
 
-@pytest.mark.parametrize('tag', ['native', 's64x32', 's96x100', 's80x130', 's128x256', 's48x1024', 's16x4096', 's64x4096', 's64x2048', 's64x4100'])
+@pytest.mark.parametrize('tag', ['native', 's64x32', 's96x100', 's80x130', 's128x256', 's48x1024', 's16x4096', 's64x4096', 's64x2048', 's64x2050', 's64x4100'])
 def test_mgline_sweep_matches_oracle(cfg, tag):
     """'mgline' (V-cycle, axial semi-coarsening, radial-line smoother): same answer as the direct solve, and the same
     PCG iteration count as the oracle's twin of the cycle (+-1).  Covers odd row counts on coarse levels (500 -> 250 ->
