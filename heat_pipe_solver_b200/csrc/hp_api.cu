@@ -724,9 +724,17 @@ static int emit_vcycle(Emitter& e, const HpKArgs& a_in, int init_phase) {
         cur = L[l].x2;
     }
     // ---- level 0: z = xt + omega M^-1 (r - L xt); its boundary rows travel with the r.z reduction
-    if (res(0, L[0].x2, cur, L[1].nz, d.z, L[0].tmp, nullptr, 1.0, 0, xwait(sig))) return -1;
-    HpXchg xf{dist ? d.z_lo : nullptr, dist ? d.z_hi : nullptr, -1, -1};
-    if (line(0, L[0].tmp, d.z, d.z, 1, xf)) return -1;
+    if (upf) {
+        // one pass: prolong + residual + line smoothing straight into z, r.z accumulated on the way
+        HpXchg xf{dist ? d.z_lo : nullptr, dist ? d.z_hi : nullptr, -1, dist ? sig : -1};
+        HpMgResArgs m{L[0].x2, cur, d.z, nullptr, nullptr, 1.0, L[1].nz, nullptr, nullptr, nullptr, 0, xf};
+        void* p[] = {&d, &a, &L[0], &m};
+        if (emit(e, hpk::desc_mg_final(h->cfg, L[0].nz), p, KIND_MG_LINE0)) return -1;
+    } else {
+        if (res(0, L[0].x2, cur, L[1].nz, d.z, L[0].tmp, nullptr, 1.0, 0, xwait(sig))) return -1;
+        HpXchg xf{dist ? d.z_lo : nullptr, dist ? d.z_hi : nullptr, -1, -1};
+        if (line(0, L[0].tmp, d.z, d.z, 1, xf)) return -1;
+    }
     HpKArgs af = a;
     return emit_combine(e, af, 4);
 }

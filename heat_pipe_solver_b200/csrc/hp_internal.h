@@ -178,6 +178,7 @@ HpKernelLaunch desc_mg_coarsen(const HpLaunchCfg&, int nzc, int nr);   // args: 
 HpKernelLaunch desc_mg_res(const HpLaunchCfg&, int nz_level);
 HpKernelLaunch desc_mg_line(const HpLaunchCfg&, int nz_level);
 HpKernelLaunch desc_mg_down(const HpLaunchCfg&, int nz_level);   // same args: residual + restriction + pre-smoothing of level+1
+HpKernelLaunch desc_mg_final(const HpLaunchCfg&, int nz_level);  // same args: level-0 prolong + residual + smoothing = z, r.z (end of the cycle)
 HpKernelLaunch desc_mg_up(const HpLaunchCfg&, int nz_level);     // args: (HpDev, HpKArgs, HpLevel, HpMgResArgs): fused prolong+residual+smooth
 bool mg_fused_supported(const HpLaunchCfg&);
 HpKernelLaunch desc_wait();       // args: (HpDev, hp_phys, HpKArgs, int kind): peer-memory variant of finalize

@@ -1475,8 +1475,11 @@ __global__ void __launch_bounds__(256) k_mg_coarsen(HpLevel f, HpLevel c, int nr
 // row g only needs the residual of row g).  MODE 2 fuses the pre-smoothing of the NEXT level into the restriction:
 // c_x(J) = omega * M_{L+1}^-1 crhs(J) as soon as the coarse row J = pair-sum of residual rows is complete.  Both need the
 // team to own whole rows (no column tiles).
+// MODE 3 = MODE 1 on the fine level at the END of the cycle: the output is the preconditioned residual z of the PCG; the
+// pass also accumulates r.z (returned; the kernel publishes it and advances beta / rz) -- one launch instead of the residual
+// pass + the final line solve (48 B/cell less per iteration: the residual and the prolonged iterate never go to memory).
 template <int TPL, int EPT, bool VEC, int MODE = 0, int CL = 1>
-__device__ __forceinline__ void mg_res_body(const HpDev& d, const HpKArgs& a, const HpLevel& L, const HpMgResArgs& m, long long team,
+__device__ __forceinline__ double mg_res_body(const HpDev& d, const HpKArgs& a, const HpLevel& L, const HpMgResArgs& m, long long team,
                                             long long nteams, double omega = 0.0, double* s_fA = nullptr,
                                             double* s_fB = nullptr, double* s_bA = nullptr, double* s_bB = nullptr) {
     const int nr = d.nr, nz = L.nz;
@@ -1515,6 +1518,8 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpKArgs& a, co
     const bool has_r = (lane == TeamGeom<TPL>::W - 1) && (i0 + EPT < nr);
     const bool prolong = m.ec != nullptr;
     const double scale = m.scale;
+    constexpr bool UP = (MODE == 1 || MODE == 3);
+    double rz_acc = 0.0;
     // coarse ghost-inclusive row of fine row g: the ghost rows 0 / nz+1 map to the coarse ghost rows 0 / nzc+1 (the
     // neighbouring slab's boundary pair; never-written zeros at a physical end, where the coupling is zero)
     auto crow = [&](int g) { return (long long)(((g - 1) >> 1) + 1) * nr; };
@@ -1563,7 +1568,7 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpKArgs& a, co
             load_row<EPT, VEC>(L.diag + rb, i0, nr, dg);
             load_row<EPT, VEC>(L.rhs + rb, i0, nr, rh);
             [[maybe_unused]] double m0_edge = 0.0;
-            if constexpr (MODE == 1) {
+            if constexpr (UP) {
                 load_row<EPT, VEC>(L.dinv + rb, i0, nr, dv);
                 if (lane == 0 && tl != 0 && i0 < nr) m0_edge = L.cR[rb + i0 - 1] * L.dinv[rb + i0 - 1];
             }
@@ -1608,12 +1613,16 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpKArgs& a, co
                 t = fma(-czm[k], xm[k], t);
                 res[k] = rh[k] - t;
             }
-            if constexpr (MODE == 1) {
+            if constexpr (UP) {
                 double zv[EPT];
                 line_solve<TPL, EPT, CL>(res, dv, cr, m0_edge, lane, tl >> 5, team_in_cta, s_fA, s_fB, s_bA, s_bB, zv);
 #pragma unroll
                 for (int k = 0; k < EPT; ++k) zv[k] = fma(omega, zv[k], xc[k]);
                 store_row<EPT, VEC>(m.xout + rb, i0, nr, zv);
+                if constexpr (MODE == 3) {
+#pragma unroll
+                    for (int k = 0; k < EPT; ++k) rz_acc = fma(rh[k], zv[k], rz_acc);      // rhs of level 0 is the PCG residual r
+                }
                 if (g == 1 && m.xc.push_lo) stage_push<TPL, EPT, VEC, CL>(d, m.xc, true, m.xc.push_lo, i0, nr, zv, tl, team_in_cta, cyc);
                 if (g == nz && m.xc.push_hi) stage_push<TPL, EPT, VEC, CL>(d, m.xc, false, m.xc.push_hi, i0, nr, zv, tl, team_in_cta, cyc);
             } else {
@@ -1646,6 +1655,16 @@ __device__ __forceinline__ void mg_res_body(const HpDev& d, const HpKArgs& a, co
             xc_l = xn_l; xc_r = xn_r;
         }
     }
+    return rz_acc;
+}
+
+// end of the V-cycle: r.z of this CTA -> grid sum -> beta / rz recurrences (finalize_B stage 2), or this rank's mailbox slots
+__device__ __forceinline__ void mg_final_publish(const HpDev& d, const HpKArgs& a, double (&acc)[1]) {
+    double tot[1];
+    if (cta_publish<1>(acc, 0u, d.partials, &d.st->ticket, tot, d.p2p != 0) && threadIdx.x == 0) {
+        if (d.nranks > 1) stash_local<1>(d, tot, HP_COMM_MG);
+        else finalize_B(d, a, a.init_phase != 0, tot[0], 0.0, 0.0, 2);
+    }
 }
 
 template <int TPL, int EPT, bool VEC>
@@ -1653,7 +1672,7 @@ __global__ void __launch_bounds__(TeamGeom<TPL>::CTA, TeamGeom<TPL>::minb_A(EPT)
 k_mg_res(HpDev d, HpKArgs a, HpLevel L, HpMgResArgs m) {
     using G = TeamGeom<TPL>;
     if (d.st->mg_skip) return;
-    mg_res_body<TPL, EPT, VEC>(d, a, L, m, (long long)blockIdx.x * G::LPC + threadIdx.x / TPL, (long long)gridDim.x * G::LPC);
+    (void)mg_res_body<TPL, EPT, VEC>(d, a, L, m, (long long)blockIdx.x * G::LPC + threadIdx.x / TPL, (long long)gridDim.x * G::LPC);
 }
 
 // ---- k_mg_up : prolong + residual + post-smoothing of one coarse level in ONE pass (one stage instead of two in the
@@ -1665,8 +1684,10 @@ k_mg_fused(HpDev d, HpKArgs a, HpLevel L, HpMgResArgs m) {
     if (d.st->mg_skip) return;
     __shared__ double s_fA[G::LPC][G::NW], s_fB[G::LPC][G::NW], s_bA[G::LPC][G::NW], s_bB[G::LPC][G::NW];
     const int tic = threadIdx.x / TPL;
-    mg_res_body<TPL, EPT, VEC, MODE>(d, a, L, m, (long long)blockIdx.x * G::LPC + tic, (long long)gridDim.x * G::LPC, a.omega,
-                                     s_fA[tic], s_fB[tic], s_bA[tic], s_bB[tic]);
+    double acc[1];
+    acc[0] = mg_res_body<TPL, EPT, VEC, MODE>(d, a, L, m, (long long)blockIdx.x * G::LPC + tic, (long long)gridDim.x * G::LPC,
+                                              a.omega, s_fA[tic], s_fB[tic], s_bA[tic], s_bB[tic]);
+    if constexpr (MODE == 3) mg_final_publish(d, a, acc);
 }
 // the same stages for rows of 1024 < nr <= 4096 cells: a cluster of CL CTAs (256 threads x 4 cells each) owns a row.  The
 // cluster shape is a compile-time attribute, so plain launches and graph kernel nodes need no launch attribute.
@@ -1676,23 +1697,29 @@ k_mg_fused(HpDev d, HpKArgs a, HpLevel L, HpMgResArgs m) {
     k_mg_fused_cl##CLN(HpDev d, HpKArgs a, HpLevel L, HpMgResArgs m) {                                                 \
         if (d.st->mg_skip) return;                                                                                     \
         __shared__ double s_fA[8 * CLN], s_fB[8 * CLN], s_bA[8 * CLN], s_bB[8 * CLN];                                  \
-        mg_res_body<256, 4, VEC, MODE, CLN>(d, a, L, m, (long long)(blockIdx.x / CLN), (long long)(gridDim.x / CLN),   \
-                                            a.omega, s_fA, s_fB, s_bA, s_bB);                                          \
+        double acc[1];                                                                                                 \
+        acc[0] = mg_res_body<256, 4, VEC, MODE, CLN>(d, a, L, m, (long long)(blockIdx.x / CLN),                        \
+                                                     (long long)(gridDim.x / CLN), a.omega, s_fA, s_fB, s_bA, s_bB);   \
+        if constexpr (MODE == 3) mg_final_publish(d, a, acc);                                                          \
     }
 HP_CLUSTER_FUSED(2)
 HP_CLUSTER_FUSED(4)
 #undef HP_CLUSTER_FUSED
 static const void* fn_mg_fused_cluster(int cl, bool vec, int mode) {
     if (cl == 2) {
+        if (mode == 3) return vec ? (const void*)k_mg_fused_cl2<true, 3> : (const void*)k_mg_fused_cl2<false, 3>;
         if (mode == 1) return vec ? (const void*)k_mg_fused_cl2<true, 1> : (const void*)k_mg_fused_cl2<false, 1>;
         return vec ? (const void*)k_mg_fused_cl2<true, 2> : (const void*)k_mg_fused_cl2<false, 2>;
     }
+    if (mode == 3) return vec ? (const void*)k_mg_fused_cl4<true, 3> : (const void*)k_mg_fused_cl4<false, 3>;
     if (mode == 1) return vec ? (const void*)k_mg_fused_cl4<true, 1> : (const void*)k_mg_fused_cl4<false, 1>;
     return vec ? (const void*)k_mg_fused_cl4<true, 2> : (const void*)k_mg_fused_cl4<false, 2>;
 }
 
 template <int TPL, int EPT, bool VEC>
 const void* fn_mg_up() { return (const void*)k_mg_fused<TPL, EPT, VEC, 1>; }
+template <int TPL, int EPT, bool VEC>
+const void* fn_mg_final() { return (const void*)k_mg_fused<TPL, EPT, VEC, 3>; }
 template <int TPL, int EPT, bool VEC>
 const void* fn_mg_down() { return (const void*)k_mg_fused<TPL, EPT, VEC, 2>; }
 
@@ -2046,6 +2073,16 @@ HpKernelLaunch desc_mg_up(const HpLaunchCfg& c, int nz_level) {       // only wh
     if (c.clF > 1) return desc_fused_cluster(c, nz_level, 1);
     const void* f = nullptr;
 #define HP_X(T, E, V) f = fn_mg_up<T, E, V>()
+    HP_DISPATCH_A(c, HP_X);
+#undef HP_X
+    HpLaunchCfg cl = c;
+    cl.nz = (nz_level + 1) / 2;
+    return {f, dim3(team_grid(f, cl, c.ctaA, c.teams_per_ctaA, 1, 1)), dim3(c.ctaA), 0};
+}
+HpKernelLaunch desc_mg_final(const HpLaunchCfg& c, int nz_level) {    // only when mg_fused_supported(c)
+    if (c.clF > 1) return desc_fused_cluster(c, nz_level, 3);
+    const void* f = nullptr;
+#define HP_X(T, E, V) f = fn_mg_final<T, E, V>()
     HP_DISPATCH_A(c, HP_X);
 #undef HP_X
     HpLaunchCfg cl = c;
