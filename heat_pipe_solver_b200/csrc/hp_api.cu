@@ -724,8 +724,10 @@ static int emit_vcycle(Emitter& e, const HpKArgs& a_in, int init_phase) {
         cur = L[l].x2;
     }
     // ---- level 0: z = xt + omega M^-1 (r - L xt); its boundary rows travel with the r.z reduction
-    if (upf) {
-        // one pass: prolong + residual + line smoothing straight into z, r.z accumulated on the way
+    if (upf && h->cfg.clF == 1) {
+        // one pass: prolong + residual + line smoothing straight into z, r.z accumulated on the way (62 us instead of
+        // 40 + 37 at 4096 x 1024).  Not on cluster teams (nr > 1024): there the column-tiled residual kernel and the
+        // 512 x 8 line kernel stream at 5.3-5.5 TB/s and the fused pass at 3.1 (164 us against 88 + 78 at 2048 x 4096)
         HpXchg xf{dist ? d.z_lo : nullptr, dist ? d.z_hi : nullptr, -1, dist ? sig : -1};
         HpMgResArgs m{L[0].x2, cur, d.z, nullptr, nullptr, 1.0, L[1].nz, nullptr, nullptr, nullptr, 0, xf};
         void* p[] = {&d, &a, &L[0], &m};
