@@ -36,7 +36,8 @@ class HpSolveOpts(C.Structure):
                 ('loop_mode', C.c_int32), ('poll_chunk', C.c_int32), ('refactor_every', C.c_int32),
                 ('extrapolate', C.c_int32), ('mg_levels', C.c_int32), ('mg_coarse_sweeps', C.c_int32), ('reuse_converged', C.c_int32),
                 ('mg_omega', C.c_double), ('while_unroll', C.c_int32), ('peer_timeout_ms', C.c_int32),
-                ('mg_zscale', C.c_double), ('tma_rows', C.c_int32), ('pipe_kernel', C.c_int32)]
+                ('mg_zscale', C.c_double), ('tma_rows', C.c_int32), ('pipe_kernel', C.c_int32),
+                ('_pad', C.c_int32), ('ext_guard_tols', C.c_double)]
 
 
 class HpSweepStat(C.Structure):

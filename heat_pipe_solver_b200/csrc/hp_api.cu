@@ -288,6 +288,7 @@ static HpKArgs make_args(const hp_solver_s* h, double dt, int has_old) {
     // on every rank for the flag protocol, so single GPU only
     a.noop_enable = (h->opts.reuse_converged && h->nranks == 1) ? 1 : 0;
     a.timeout_ns = (unsigned long long)h->opts.peer_timeout_ms * 1000000ull;
+    a.ext_guard = h->opts.ext_guard_tols * h->opts.tol;
     return a;
 }
 
@@ -414,7 +415,7 @@ int hp_create(hp_handle* out, const hp_mesh_desc* m, const hp_phys* phys, void* 
     h->opts.loop_mode = 1; h->opts.poll_chunk = 8; h->opts.refactor_every = 1; h->opts.extrapolate = 3;
     h->opts.mg_levels = 6; h->opts.mg_coarse_sweeps = 2; h->opts.mg_omega = 0.6; h->opts.reuse_converged = 0;
     h->opts.while_unroll = 1; h->opts.peer_timeout_ms = 60000; h->opts.mg_zscale = 0.5; h->opts.tma_rows = 0;
-    h->opts.pipe_kernel = 1;
+    h->opts.pipe_kernel = 1; h->opts.ext_guard_tols = 300.0;
 
     // initial field + snapshots (main.py:34,133,145,152)
     CK(hpk::launch_fill_rows(d, d.T, h->stream));
@@ -493,6 +494,7 @@ int hp_set_opts(hp_handle h, const hp_solve_opts* o) {
     if (h->opts.while_unroll < 1) h->opts.while_unroll = 1;
     if (h->opts.while_unroll > 8) h->opts.while_unroll = 8;
     if (h->opts.peer_timeout_ms < 1) h->opts.peer_timeout_ms = 60000;
+    if (!(h->opts.ext_guard_tols >= 0.0)) h->opts.ext_guard_tols = 300.0;
     if (resolve_mg(h)) return -1;
     return invalidate_noop(h);
 }
@@ -848,7 +850,7 @@ static bool same_opts(const hp_solve_opts& a, const hp_solve_opts& b) {
            a.loop_mode == b.loop_mode && a.refactor_every == b.refactor_every && a.extrapolate == b.extrapolate &&
            a.mg_levels == b.mg_levels && a.mg_coarse_sweeps == b.mg_coarse_sweeps && a.mg_omega == b.mg_omega &&
            a.reuse_converged == b.reuse_converged && a.while_unroll == b.while_unroll && a.mg_zscale == b.mg_zscale &&
-           a.peer_timeout_ms == b.peer_timeout_ms && a.tma_rows == b.tma_rows && a.pipe_kernel == b.pipe_kernel;
+           a.peer_timeout_ms == b.peer_timeout_ms && a.tma_rows == b.tma_rows && a.pipe_kernel == b.pipe_kernel && a.ext_guard_tols == b.ext_guard_tols;
 }
 
 static int get_graph(hp_solver_s* h, double dt, int sweeps, int has_old, int update_old, GraphEntry** out) {

@@ -131,6 +131,7 @@ struct HpKArgs {
                                //    produces z, r.z and advances the recurrences
     int32_t init_phase;        // (unused since the V-cycle opens the loop body: HpState.mg_init tells the first cycle of a sweep)
     double omega;              // damping of the line smoother in the V-cycle
+    double ext_guard;          // k_delta: the cubic term of the predicted start is applied where it exceeds this [K]
     int32_t ext_order;         // k_delta: order of the extrapolated increment (1 linear, 2 quadratic, 3 cubic in the step index)
     int32_t c2_valid;          // k_delta / k_stash: d.c2 holds usable history
     int32_t noop_enable;       // k_diag / INIT kernel may take the bookkeeping-only path (single GPU, no debug outputs, no shift)

@@ -1374,8 +1374,15 @@ __global__ void __launch_bounds__(256) k_delta(HpDev d, hp_phys ph, HpKArgs a) {
         double z = dn;
         if (d.d1) {
             const double p1 = d.d1[c];
-            if (ord == 2) z = 2.0 * dn - p1;
-            else if (ord == 3) z = 3.0 * (dn - p1) + d.d2[c];
+            if (ord >= 2) z = 2.0 * dn - p1;
+            if (ord == 3) {
+                // the cubic term = third difference of the history.  Every stored field carries solver noise of the order of
+                // the tolerance and the third difference amplifies it 8x: once the transient is smooth enough for the term to
+                // sink to that floor it only injects noise (erratic iteration counts late in a run), so it is applied
+                // cell by cell only where it stands above the floor
+                const double d3 = dn - 2.0 * p1 + d.d2[c];
+                if (fabs(d3) > a.ext_guard) z += d3;
+            }
             d.d2[c] = p1;
             d.d1[c] = dn;
         }

@@ -102,7 +102,7 @@ class ConductionSolver:
                  face_k='masked_at_Tface', radiation=False, axial_break=None, rows=None,
                  precond='auto', criterion='precond_inf', tol=1e-9, max_iter=5000, loop_mode='graph',
                  poll_chunk=8, refactor_every=1, extrapolate=True, mg_levels=6, mg_coarse_sweeps=2, mg_omega=0.6,
-                 mg_zscale=0.5, reuse_converged=False, while_unroll=1, peer_timeout_ms=60000, tma_rows=False, pipe_kernel=True,
+                 mg_zscale=0.5, reuse_converged=False, while_unroll=1, peer_timeout_ms=60000, tma_rows=False, pipe_kernel=True, ext_guard_tols=300.0,
                  device=None, simple=(7200.0, 440.5, 55.0),
                  layout=None, regions=None):
         import torch
@@ -161,14 +161,14 @@ class ConductionSolver:
                          poll_chunk=poll_chunk, refactor_every=refactor_every, extrapolate=extrapolate,
                          mg_levels=mg_levels, mg_coarse_sweeps=mg_coarse_sweeps, mg_omega=mg_omega, mg_zscale=mg_zscale,
                          reuse_converged=reuse_converged, while_unroll=while_unroll, peer_timeout_ms=peer_timeout_ms,
-                         tma_rows=tma_rows, pipe_kernel=pipe_kernel)
+                         tma_rows=tma_rows, pipe_kernel=pipe_kernel, ext_guard_tols=ext_guard_tols)
 
     # ------------------------------------------------------------------ options
     def set_options(self, **kw):
         cur = getattr(self, 'options', dict(precond='rline', criterion='precond_inf', tol=1e-9, max_iter=5000,
                                             loop_mode='graph', poll_chunk=8, refactor_every=1, extrapolate=True,
                                             mg_levels=6, mg_coarse_sweeps=2, mg_omega=0.6, mg_zscale=0.5,
-                                            reuse_converged=False, while_unroll=1, peer_timeout_ms=60000, tma_rows=False, pipe_kernel=True))
+                                            reuse_converged=False, while_unroll=1, peer_timeout_ms=60000, tma_rows=False, pipe_kernel=True, ext_guard_tols=300.0))
         cur = dict(cur)
         for k, v in kw.items():
             if k not in cur:
@@ -188,6 +188,7 @@ class ConductionSolver:
         o.while_unroll, o.peer_timeout_ms = int(cur['while_unroll']), int(cur['peer_timeout_ms'])
         o.tma_rows = 1 if cur['tma_rows'] else 0
         o.pipe_kernel = 1 if cur['pipe_kernel'] else 0
+        o.ext_guard_tols = float(cur['ext_guard_tols'])
         _lib.check(self.lib.hp_set_opts(self._h, C.byref(o)), 'hp_set_opts')
         self.options = cur
 

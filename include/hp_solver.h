@@ -95,6 +95,10 @@ typedef struct hp_solve_opts {
     int32_t pipe_kernel;    /* 1 (default): meshes made of small uncoupled pipes (9 radial cells, <= 512 rows each: the native
                                Faghri mesh, ensembles of it) with precond = 1 run each pipe's whole time step in ONE CTA, on
                                chip (every pipe its own PCG to `tol`); 0: always the row kernels */
+    int32_t _pad;
+    double ext_guard_tols;  /* extrapolate = 3: the cubic term of the predicted start (third difference of the step history) is
+                               applied cell by cell only where it exceeds ext_guard_tols * tol -- below that it is solver noise
+                               (default 300; 0 = always apply) */
 } hp_solve_opts;
 
 typedef struct hp_sweep_stat {

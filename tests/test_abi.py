@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     from heat_pipe_solver_b200 import _lib
     assert C.sizeof(_lib.HpPhys) == 10 * 8 + 6 * 4
     assert C.sizeof(_lib.HpMeshDesc) == 4 * 4 + 12 * 8
-    assert C.sizeof(_lib.HpSolveOpts) == 80
+    assert C.sizeof(_lib.HpSolveOpts) == 96
     assert C.sizeof(_lib.HpSweepStat) == 32
     assert C.sizeof(_lib.HpKernelTimes) == 512
 

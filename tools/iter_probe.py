@@ -22,7 +22,7 @@ def main():
             if not item:
                 continue
             k, v = item.split('=')
-            kw[k] = v if k in ('precond', 'loop_mode') else (float(v) if ('.' in v or 'e' in v) else int(v))
+            kw[k] = v if k in ('precond', 'loop_mode') else (float(v) if ('.' in v or 'e' in v or k == 'ext_guard_tols') else int(v))
         opts = dict(precond='mgline', refactor_every=5, extrapolate=3)
         opts.update(kw)
         with ConductionSolver(mesh, cfg['dimensions'], cfg['parameters'], cfg['constants'], **opts) as s:
