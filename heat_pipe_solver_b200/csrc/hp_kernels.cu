@@ -1379,9 +1379,12 @@ __global__ void __launch_bounds__(256) k_delta(HpDev d, hp_phys ph, HpKArgs a) {
                 // the cubic term = third difference of the history.  Every stored field carries solver noise of the order of
                 // the tolerance and the third difference amplifies it 8x: once the transient is smooth enough for the term to
                 // sink to that floor it only injects noise (erratic iteration counts late in a run), so it is applied
-                // cell by cell only where it stands above the floor
+                // cell by cell with a weight that rises from 0 at the floor (ext_guard) to 1 at twice the floor
+                // (a taper, not a switch: a hard threshold puts steps of the size of the guard into the start field
+                // and makes the start depend discontinuously on round-off differences between decompositions)
                 const double d3 = dn - 2.0 * p1 + d.d2[c];
-                if (fabs(d3) > a.ext_guard) z += d3;
+                const double w = a.ext_guard > 0.0 ? fmin(1.0, fmax(0.0, (fabs(d3) - a.ext_guard) / a.ext_guard)) : 1.0;
+                z = fma(w, d3, z);
             }
             d.d2[c] = p1;
             d.d1[c] = dn;
