@@ -97,8 +97,8 @@ typedef struct hp_solve_opts {
                                chip (every pipe its own PCG to `tol`); 0: always the row kernels */
     int32_t _pad;
     double ext_guard_tols;  /* extrapolate = 3: the cubic term of the predicted start (third difference of the step history) is
-                               applied cell by cell only where it exceeds ext_guard_tols * tol -- below that it is solver noise
-                               (default 300; 0 = always apply) */
+                               applied cell by cell with a weight rising from 0 at ext_guard_tols * tol to 1 at twice that --
+                               below the floor it is solver noise (default 300; 0 = always apply in full) */
 } hp_solve_opts;
 
 typedef struct hp_sweep_stat {
