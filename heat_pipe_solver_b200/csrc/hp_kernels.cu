@@ -3,10 +3,16 @@
 //   k_snapshot_kout  outer-surface k at T_amb                      (main.py:145  `b = FaceVariable(value=k)`)
 //   k_coef           face conductivities -> couplings cR, cZ       (main.py:103-106,133; FiPy DiffusionTerm)
 //   k_diag           rho*cp, diagonal, boundary terms, r0 = b - L T, ||L T - b||^2   (main.py:108-117,123-150,202)
-//   k_factor_rline   LDL^T pivots of the radial-line tridiagonal blocks
+//   k_factor_team    LDL^T pivots of the radial-line tridiagonal blocks (2x2 scan on row teams)
 //   k_cg_B<INIT>     z = M^-1 r0, r.z                                (PCG start)
 //   k_cg_A           p = z + beta p ; q = L p ; p.q                  (PCG, fused direction update + stencil + dot)
 //   k_cg_B           x += alpha p ; r -= alpha q ; z = M^-1 r ; r.z  (PCG, fused updates + line solve + dots)
+//   k_cg_B_tma       the same with cp.async.bulk / mbarrier staged operand rows (opt-in)
+//   k_mg_coarsen, k_mg_res, k_mg_line, k_mg_fused<1|2|3>, k_mg_fused_cl2/cl4   the 'mgline' V-cycle (axial semi-coarsening,
+//                    line smoother; fused stages, cluster teams for wide rows, stage hand-over between slabs)
+//   k_delta, k_stash predicted PCG starts from the step history
+//   k_pipe_step      one whole time step of one small pipe per CTA, on chip (native 500 x 9 mesh, ensembles)
+//   k_wait, k_finalize   scalar recurrences under axial slabs (peer-memory flags / NCCL all-gather)
 //
 // Layout: every field has nz+2 rows of nr doubles (row 0 / nz+1 = ghost rows, zero-coupled at physical
 // ends, a neighbour's row under axial slabs).  r is the fast index, so flat neighbours are idx+-1 (radial;
